@@ -1,0 +1,16 @@
+"""CPU oracle for the PEANUT perception hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``peanut_b200/`` imports this package; only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may.
+
+Each module restates one stage of the reference in plain PyTorch / numpy and cites the reference
+file:line it follows.  Pinning status:
+
+* ``oracle.mapper``   - pinned against the reference's own ``nav/agent/mapping.py`` executed in the build
+  container (fixtures in tests/golden/semmap_*.npz, generator tests/golden/make_semmap_golden.py).
+* ``oracle.prednet``  - PARITY UNPINNED: mmcv 1.6.0 is not installable here and the reference tests hold
+  shape assertions only; pinned to those structural facts (46.61 M parameters,
+  61 convolutions, stage shapes) and to nothing numeric.
+* ``oracle.maskrcnn`` - PARITY UNPINNED: detectron2 0.6 is absent; restated from the config
+  nav/agent/utils/COCO-InstSeg/mask_rcnn_R_101_cat9.yaml and detectron2's published semantics.
+"""

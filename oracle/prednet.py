@@ -1,0 +1,255 @@
+"""Oracle for stage C: the map-completion encoder-decoder (ResNetV1c-50-D8 + PSPHead).
+
+PARITY UNPINNED (see oracle/__init__.py): a plain-PyTorch restatement, test infrastructure only.
+
+Follows, line by line:
+  * config                      nav/pred_model_cfg.py:2-42
+  * ResNetV1c / ResNet          prediction/mmseg/models/backbones/resnet.py:396-527, 591-674, 688-700
+  * Bottleneck (style=pytorch)  prediction/mmseg/models/backbones/resnet.py:99-307
+  * ResLayer                    prediction/mmseg/models/utils/res_layer.py:28-96
+  * PPM / PSPHead               prediction/mmseg/models/decode_heads/psp_head.py:11-117
+  * cls_seg                     prediction/mmseg/models/decode_heads/decode_head.py:225-230
+  * encode_decode / inference   prediction/mmseg/models/segmentors/encoder_decoder.py:63-80, 203-271
+  * run_inference / get_prediction  nav/agent/prediction.py:112-158
+mmcv's ConvModule is conv(no bias) -> BN -> ReLU; build_norm_layer names norms bn1/bn2/bn3.
+Module/attribute names reproduce the mmcv checkpoint keys so a real ``pred_model_wts.pth`` state_dict loads.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class ConvModule(nn.Module):
+    """mmcv.cnn.ConvModule with norm_cfg=BN, act_cfg=ReLU: attributes ``conv``, ``bn``."""
+
+    def __init__(self, cin, cout, k, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.conv(x)))
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None):
+        super().__init__()
+        # style='pytorch': stride sits on the 3x3 conv (resnet.py:148-153)
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, stride=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+
+    def forward(self, x):  # resnet.py:267-307
+        identity = x
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = F.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        if self.downsample is not None:
+            identity = self.downsample(x)
+        return F.relu(out + identity)
+
+
+def make_res_layer(inplanes, planes, num_blocks, stride, dilation, contract_dilation=True):
+    """res_layer.py:28-96 with avg_down=False, multi_grid=None."""
+    downsample = None
+    if stride != 1 or inplanes != planes * 4:
+        downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                   nn.BatchNorm2d(planes * 4))
+    first_dilation = dilation // 2 if (dilation > 1 and contract_dilation) else dilation
+    layers = [Bottleneck(inplanes, planes, stride, first_dilation, downsample)]
+    for _ in range(1, num_blocks):
+        layers.append(Bottleneck(planes * 4, planes, 1, dilation))
+    return nn.Sequential(*layers)
+
+
+class ResNetV1c50D8(nn.Module):
+    def __init__(self, in_channels=14):
+        super().__init__()
+        # deep stem, resnet.py:594-624 (stem_channels=64)
+        self.stem = nn.Sequential(
+            nn.Conv2d(in_channels, 32, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True),
+            nn.Conv2d(32, 32, 3, stride=1, padding=1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True),
+            nn.Conv2d(32, 64, 3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        blocks, strides, dilations = (3, 4, 6, 3), (1, 2, 1, 1), (1, 1, 2, 4)
+        inplanes = 64
+        for i in range(4):
+            planes = 64 * 2 ** i
+            setattr(self, f'layer{i + 1}', make_res_layer(inplanes, planes, blocks[i], strides[i], dilations[i]))
+            inplanes = planes * 4
+
+    def forward(self, x):  # resnet.py:659-674
+        x = self.maxpool(self.stem(x))
+        outs = []
+        for i in range(4):
+            x = getattr(self, f'layer{i + 1}')(x)
+            outs.append(x)
+        return tuple(outs)
+
+
+class PSPHead(nn.Module):
+    def __init__(self, in_channels=2048, channels=512, pool_scales=(1, 2, 3, 6), num_classes=6):
+        super().__init__()
+        self.psp_modules = nn.ModuleList(
+            nn.Sequential(nn.AdaptiveAvgPool2d(s), ConvModule(in_channels, channels, 1)) for s in pool_scales)
+        self.bottleneck = ConvModule(in_channels + len(pool_scales) * channels, channels, 3, padding=1)
+        self.conv_seg = nn.Conv2d(channels, num_classes, 1)
+        self.dropout = nn.Dropout2d(0.1)
+
+    def forward(self, inputs):
+        x = inputs[3]  # in_index=3
+        outs = [x]
+        for ppm in self.psp_modules:
+            outs.append(F.interpolate(ppm(x), size=x.shape[2:], mode='bilinear', align_corners=False))
+        feats = self.bottleneck(torch.cat(outs, dim=1))
+        return self.conv_seg(self.dropout(feats))
+
+
+class EncoderDecoder(nn.Module):
+    """whole-image inference of the fork: raw logits, no softmax, no argmax (encoder_decoder.py:244-271)."""
+
+    def __init__(self, in_channels=14, num_classes=6):
+        super().__init__()
+        self.backbone = ResNetV1c50D8(in_channels)
+        self.decode_head = PSPHead(num_classes=num_classes)
+
+    def forward(self, img):
+        feats = self.backbone(img)
+        out = self.decode_head(feats)
+        return F.interpolate(out, size=img.shape[2:], mode='bilinear', align_corners=False)
+
+
+def synth_state_dict(in_channels=14, num_classes=6, seed=0):
+    """Seeded random checkpoint: Kaiming-normal convs (fan_out, resnet.py:436-442),
+    BN gamma~U(0.5,1.5) (x0.25 on bn3), beta~N(0,0.1), mean~N(0,0.1), var~U(0.5,1.5); classifier N(0,0.01)."""
+    g = torch.Generator().manual_seed(seed)
+    model = EncoderDecoder(in_channels, num_classes)
+    sd = model.state_dict()
+    out = {}
+    for k, v in sd.items():
+        if k.endswith('num_batches_tracked'):
+            out[k] = v.clone()
+        elif k.endswith('running_mean'):
+            out[k] = torch.randn(v.shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            out[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif v.dim() == 4:
+            if k.startswith('decode_head.conv_seg'):
+                out[k] = torch.randn(v.shape, generator=g) * 0.01
+            else:
+                fan_out = v.shape[0] * v.shape[2] * v.shape[3]
+                out[k] = torch.randn(v.shape, generator=g) * (2.0 / fan_out) ** 0.5
+        elif k.endswith('.weight'):  # BN gamma
+            out[k] = torch.rand(v.shape, generator=g) + 0.5
+            if k.endswith('bn3.weight'):
+                # residual-branch scale kept small so that activations stay O(1) through 16 blocks
+                # (eval-mode BN with random statistics does not normalise); NOT zero, which would
+                # hide bugs in the residual branch.
+                out[k] = out[k] * 0.25
+        elif k.startswith('decode_head.conv_seg') and k.endswith('.bias'):
+            out[k] = torch.randn(v.shape, generator=g) * 0.01
+        else:  # BN beta
+            out[k] = torch.randn(v.shape, generator=g) * 0.1
+    return out
+
+
+def build(state_dict, in_channels=14, num_classes=6):
+    m = EncoderDecoder(in_channels, num_classes)
+    missing = m.load_state_dict({k: v for k, v in state_dict.items() if not k.startswith('auxiliary_head')}, strict=True)
+    return m.eval()
+
+
+def synth_partial_map(C=14, H=720, W=720, seed=1234):
+    """Synthetic partial map: obstacles, explored disc, pose markers, sparse category blobs."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((C, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    r = min(H, W) * (0.25 + 0.15 * rng.random())
+    cy, cx = H / 2 + rng.integers(-H // 8, H // 8 + 1), W / 2 + rng.integers(-W // 8, W // 8 + 1)
+    m[1] = ((yy - cy) ** 2 + (xx - cx) ** 2 < r * r).astype(np.float32)
+    obst = (rng.random((H, W)) < 0.08).astype(np.float32)
+    obst[1:] = np.maximum(obst[1:], obst[:-1])
+    obst[:, 1:] = np.maximum(obst[:, 1:], obst[:, :-1])
+    m[0] = obst * m[1]
+    m[2, H // 2 - 1:H // 2 + 2, W // 2 - 1:W // 2 + 2] = 1.0
+    m[3, H // 2 - 2:H // 2 + 3, W // 2 - 2:W // 2 + 3] = 1.0
+    for c in range(4, C):
+        for _ in range(int(rng.integers(0, 4))):
+            h, w = int(rng.integers(3, max(4, H // 20))), int(rng.integers(3, max(4, W // 20)))
+            y0, x0 = int(rng.integers(0, H - h)), int(rng.integers(0, W - w))
+            m[c, y0:y0 + h, x0:x0 + w] = rng.integers(1, 6) / 5.0
+    return m
+
+
+def run_inference(model, full_map):
+    """nav/agent/prediction.py:112-137: the test pipeline is a numerical identity."""
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(full_map, dtype=np.float32))[None]
+        return [model(x)[0].numpy()]
+
+
+def get_prediction(model, full_map):
+    """nav/agent/prediction.py:155-158 (scipy.special.expit == logistic sigmoid, computed in fp32)."""
+    logits = run_inference(model, full_map)[0]
+    return (1.0 / (1.0 + np.exp(-logits.astype(np.float32)))).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Storage-precision emulation: the same graph with every tensor the CUDA path materialises rounded to
+# bf16 (weights, input, each fused conv+BN(+residual)+ReLU output, pooled bins, resized pyramid levels),
+# fp32 accumulation everywhere.  Lets the bf16 kernels be checked to ~1 bf16 ulp per layer instead of
+# against the looser end-to-end bf16-vs-fp32 tolerance.
+def _r(t, emulate):
+    return t.to(torch.bfloat16).to(torch.float32) if emulate else t
+
+
+def _conv_bn(x, conv, bn, relu, emulate, residual=None):
+    w = _r(conv.weight, emulate)
+    y = F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation)
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    bias = bn.bias - bn.running_mean * scale
+    y = y * scale[None, :, None, None] + bias[None, :, None, None]
+    if residual is not None:
+        y = y + residual
+    if relu:
+        y = F.relu(y)
+    return _r(y, emulate)
+
+
+def forward_folded(model, img, emulate_bf16=False, return_taps=False):
+    """Same network as EncoderDecoder.forward with BN folded into scale/bias (as the CUDA path does)."""
+    e = emulate_bf16
+    with torch.no_grad():
+        bb, head = model.backbone, model.decode_head
+        x = _r(img, e)
+        x = _conv_bn(x, bb.stem[0], bb.stem[1], True, e)
+        x = _conv_bn(x, bb.stem[3], bb.stem[4], True, e)
+        x = _conv_bn(x, bb.stem[6], bb.stem[7], True, e)
+        x = bb.maxpool(x)
+        for i in range(4):
+            for blk in getattr(bb, f'layer{i + 1}'):
+                identity = x
+                if blk.downsample is not None:
+                    identity = _conv_bn(x, blk.downsample[0], blk.downsample[1], False, e)
+                t = _conv_bn(x, blk.conv1, blk.bn1, True, e)
+                t = _conv_bn(t, blk.conv2, blk.bn2, True, e)
+                x = _conv_bn(t, blk.conv3, blk.bn3, True, e, residual=identity)
+        feats4 = x
+        outs = [x]
+        for ppm in head.psp_modules:
+            p = _r(ppm[0](x), e)
+            p = _conv_bn(p, ppm[1].conv, ppm[1].bn, True, e)
+            outs.append(_r(F.interpolate(p, size=x.shape[2:], mode='bilinear', align_corners=False), e))
+        f = _conv_bn(torch.cat(outs, 1), head.bottleneck.conv, head.bottleneck.bn, True, e)
+        logits = F.conv2d(f, _r(head.conv_seg.weight, e), head.conv_seg.bias)
+        out = F.interpolate(logits, size=img.shape[2:], mode='bilinear', align_corners=False)
+    if return_taps:
+        return out, feats4, logits
+    return out

@@ -1,0 +1,107 @@
+"""ctypes binding of libpeanut_b200.so (the C-ABI declared in include/peanut_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+torch is used only for device memory and streams; no torch type crosses the ABI (raw pointers do).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpeanut_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+PN_BF16 = 0
+PN_TF32 = 1
+
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_i64_p = ctypes.POINTER(ctypes.c_int64)
+
+# name -> (restype, argtypes); must list every symbol include/peanut_b200.h declares.
+PROTOTYPES = {
+    "pn_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "pn_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_last_error": (ctypes.c_char_p, []),
+    "pn_abi_version": (ctypes.c_int, []),
+    "pn_set_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, _c_i64_p]),
+    "pn_clear_weights": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_prednet_build": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 6),
+    "pn_prednet_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_prednet_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_prednet_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_prednet_read_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 4 +
+                  [ctypes.c_void_p] * 4 + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile the CUDA sources in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libpeanut_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    """dlopen the library and bind every exported symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(peanut_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("peanut_b200: " + load().pn_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """One pn_ctx: a device, a weight store and the built stage networks."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = ctypes.c_void_p()
+        check(self.lib.pn_create(int(device), ctypes.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pn_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, state_dict):
+        """state_dict: name -> array-like (torch tensor or numpy), passed to the library as fp32."""
+        for name, value in state_dict.items():
+            if hasattr(value, "detach"):
+                value = value.detach().cpu().numpy()
+            arr = np.ascontiguousarray(value, dtype=np.float32)
+            shape = (ctypes.c_int64 * max(arr.ndim, 1))(*arr.shape)
+            check(self.lib.pn_set_weight(self.handle, name.encode(), arr.ctypes.data_as(ctypes.c_void_p), arr.ndim, shape))
+
+    def clear_weights(self):
+        check(self.lib.pn_clear_weights(self.handle))

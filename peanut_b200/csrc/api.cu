@@ -1,0 +1,245 @@
+// C-ABI of libpeanut_b200.so (declared in include/peanut_b200.h).  Every entry point translates
+// C++ exceptions into a status code + thread-local message; no torch types cross this boundary.
+#include <memory>
+#include <mutex>
+
+#include "../../include/peanut_b200.h"
+#include "engine.h"
+#include "prednet.h"
+#include "vec.cuh"
+
+namespace pn {
+
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  WeightStore weights;
+  std::unique_ptr<PredNet> prednet;
+  cudaStream_t stream = nullptr;  // used by the *_host entry points
+};
+
+thread_local std::string g_last_error;
+
+__global__ void set_pred_slots_kernel(PredSlots* slots, const float* in, float* out, int apply_sigmoid) {
+  slots->input = in;
+  slots->output = out;
+  slots->apply_sigmoid = apply_sigmoid;
+}
+
+// NHWC (dt) -> NCHW fp32, first C channels.
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* in, long long ldi, float* out, int B, int C, int HW) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (idx >= total) return;
+  const int hw = static_cast<int>(idx % HW);
+  const long long t = idx / HW;
+  const int c = static_cast<int>(t % C);
+  const int b = static_cast<int>(t / C);
+  out[idx] = to_float(in[(static_cast<long long>(b) * HW + hw) * ldi + c]);
+}
+
+void nhwc_to_nchw(const Tensor& t, int C, float* out, cudaStream_t s) {
+  const int HW = t.H * t.W;
+  const long long total = static_cast<long long>(t.B) * C * HW;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  if (t.dt == kBF16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(t.ptr), t.ld, out, t.B, C, HW);
+  else
+    nhwc_to_nchw_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(t.ptr), t.ld, out, t.B, C, HW);
+}
+
+void check_device(Ctx* c) {
+  PN_REQUIRE(c != nullptr, "null context");
+  PN_CUDA_CHECK(cudaSetDevice(c->device));
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+#define PN_API_BEGIN try {
+#define PN_API_END                        \
+  }                                       \
+  catch (const std::exception& e) {       \
+    g_last_error = e.what();              \
+    return 1;                             \
+  }                                       \
+  catch (...) {                           \
+    g_last_error = "unknown exception";   \
+    return 1;                             \
+  }                                       \
+  return 0;
+
+extern "C" {
+
+const char* pn_last_error(void) { return g_last_error.c_str(); }
+int pn_abi_version(void) { return 1; }
+
+int pn_create(int device, pn_ctx** out) {
+  PN_API_BEGIN
+  PN_REQUIRE(out != nullptr, "pn_create: null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  PN_REQUIRE(e == cudaSuccess && count > 0, "no CUDA device available: peanut_b200 has no CPU fallback");
+  PN_REQUIRE(device >= 0 && device < count, "device index out of range");
+  cudaDeviceProp prop;
+  PN_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  PN_REQUIRE(prop.major == 10, "peanut_b200 kernels are built for sm_100a only (found sm_" +
+                                   std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  PN_CUDA_CHECK(cudaSetDevice(device));
+  auto* c = new Ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  PN_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = reinterpret_cast<pn_ctx*>(c);
+  PN_API_END
+}
+
+int pn_destroy(pn_ctx* ctx) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  if (c) {
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->prednet.reset();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+  }
+  PN_API_END
+}
+
+int pn_set_weight(pn_ctx* ctx, const char* name, const float* data, int ndim, const int64_t* shape) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  PN_REQUIRE(c && name && data && ndim >= 0 && ndim <= 8, "pn_set_weight: bad arguments");
+  HostArray a;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    a.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
+  a.data.assign(data, data + n);
+  c->weights[name] = std::move(a);
+  PN_API_END
+}
+
+int pn_clear_weights(pn_ctx* ctx) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  PN_REQUIRE(c, "null context");
+  c->weights.clear();
+  PN_API_END
+}
+
+int pn_prednet_build(pn_ctx* ctx, int B, int C, int H, int W, int num_classes, int precision) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(B > 0 && C > 0 && H >= 8 && W >= 8 && num_classes > 0, "pn_prednet_build: bad shape");
+  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32, "pn_prednet_build: bad precision");
+  c->prednet.reset();
+  auto net = std::make_unique<PredNet>();
+  net->net.num_sms = c->num_sms;
+  build_prednet(*net, c->weights, B, C, H, W, num_classes, precision == PN_BF16 ? kBF16 : kF32);
+  PN_CUDA_CHECK(cudaDeviceSynchronize());
+  c->prednet = std::move(net);
+  PN_API_END
+}
+
+int pn_prednet_forward(pn_ctx* ctx, const float* map_dev, int apply_sigmoid, float* out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->prednet, "pn_prednet_forward: call pn_prednet_build first");
+  PN_REQUIRE(map_dev && out_dev, "pn_prednet_forward: null buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  set_pred_slots_kernel<<<1, 1, 0, s>>>(c->prednet->slots, map_dev, out_dev, apply_sigmoid);
+  c->prednet->net.run(s);
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
+}
+
+int pn_prednet_forward_host(pn_ctx* ctx, const float* map_host, int apply_sigmoid, float* out_host) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->prednet, "pn_prednet_forward_host: call pn_prednet_build first");
+  PredNet& n = *c->prednet;
+  const size_t in_bytes = static_cast<size_t>(n.B) * n.C * n.H * n.W * sizeof(float);
+  const size_t out_bytes = static_cast<size_t>(n.B) * n.num_classes * n.H * n.W * sizeof(float);
+  if (!n.stage_in) {
+    n.stage_in = static_cast<float*>(n.net.arena.alloc(in_bytes, false));
+    n.stage_out = static_cast<float*>(n.net.arena.alloc(out_bytes, false));
+  }
+  PN_CUDA_CHECK(cudaMemcpyAsync(n.stage_in, map_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  set_pred_slots_kernel<<<1, 1, 0, c->stream>>>(n.slots, n.stage_in, n.stage_out, apply_sigmoid);
+  n.net.run(c->stream);
+  PN_CUDA_CHECK(cudaMemcpyAsync(out_host, n.stage_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PN_API_END
+}
+
+int pn_prednet_num_launches(pn_ctx* ctx) {
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !c->prednet) return -1;
+  return static_cast<int>(c->prednet->net.launches_per_forward) + 1;  // + slot update
+}
+
+int pn_prednet_read_tap(pn_ctx* ctx, int which, float* out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->prednet && out_dev, "pn_prednet_read_tap: not built");
+  PredNet& n = *c->prednet;
+  if (which == 0)
+    nhwc_to_nchw(n.features, 2048, out_dev, static_cast<cudaStream_t>(stream));
+  else if (which == 1)
+    nhwc_to_nchw(n.logits_lowres, n.num_classes, out_dev, static_cast<cudaStream_t>(stream));
+  else
+    PN_REQUIRE(false, "pn_prednet_read_tap: unknown tap");
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
+}
+
+int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,
+              const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
+              int stride, int dil, int pad, int relu, int force_bn, float* y_dev) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(x_dev && w_host && y_dev, "pn_conv2d: null buffer");
+  const DType dt = precision == PN_BF16 ? kBF16 : kF32;
+  Net net;
+  net.num_sms = c->num_sms;
+  net.use_graph = false;
+  struct Slots {
+    const float* x;
+    const float* r;
+  };
+  Slots h{x_dev, residual_dev};
+  Slots* slots = static_cast<Slots*>(net.arena.alloc(sizeof(Slots)));
+  PN_CUDA_CHECK(cudaMemcpy(slots, &h, sizeof(h), cudaMemcpyHostToDevice));
+  Tensor x = net.arena.tensor(B, H, W, pad_channels(Cin, dt), dt);
+  add_nchw_to_nhwc(net, &slots->x, x, Cin);
+  const int Ho = conv_out(H, R, stride, dil, pad), Wo = conv_out(W, S, stride, dil, pad);
+  PN_REQUIRE(Ho > 0 && Wo > 0, "pn_conv2d: empty output");
+  Tensor y = net.arena.tensor(B, Ho, Wo, pad_channels(Cout, dt), dt);
+  Tensor res;
+  if (residual_dev) {
+    res = net.arena.tensor(B, Ho, Wo, pad_channels(Cout, dt), dt);
+    add_nchw_to_nhwc(net, &slots->r, res, Cout);
+  }
+  ConvSpec sp;
+  sp.Cin = Cin, sp.Cout = Cout, sp.R = R, sp.S = S, sp.stride = stride, sp.dil = dil, sp.pad = pad;
+  sp.relu = relu != 0;
+  sp.force_bn = force_bn;
+  add_conv(net, "pn_conv2d", x, y, w_host, scale_host, bias_host, sp, residual_dev ? &res : nullptr);
+  net.run(nullptr);
+  nhwc_to_nchw(y, Cout, y_dev, nullptr);
+  PN_CUDA_CHECK(cudaDeviceSynchronize());
+  PN_API_END
+}
+
+}  // extern "C"

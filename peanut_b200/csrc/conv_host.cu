@@ -1,0 +1,249 @@
+// Host side of the tcgen05 implicit-GEMM convolution: weight packing, TMA descriptor encoding
+// (im2col mode for activations, tiled mode for weights), tile selection and launch recording.
+#include <cmath>
+#include <cstring>
+
+#include "conv_umma.cuh"
+#include "engine.h"
+
+namespace pn {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void* driver_entry(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  PN_CUDA_CHECK(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q));
+  PN_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, std::string("driver entry point not found: ") + name);
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_enum(int sw) {
+  return sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+CUtensorMapDataType dtype_enum(DType dt) {
+  return dt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
+CUtensorMap encode_tiled_2d(DType dt, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                            uint32_t box_inner, uint32_t box_rows, int sw) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&m, dtype_enum(dt), 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+// (C, W, H, N) activation tensor, one box = `pixels` output positions x `channels` channels.
+CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pad, int dil, int R, int S, int stride,
+                          uint32_t box_channels, uint32_t pixels, int sw) {
+  static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
+  CUtensorMap m;
+  const uint64_t es = dtype_size(dt);
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(channels_total), static_cast<cuuint64_t>(in.W),
+                        static_cast<cuuint64_t>(in.H), static_cast<cuuint64_t>(in.B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.ld) * es, static_cast<cuuint64_t>(in.ld) * es * in.W,
+                           static_cast<cuuint64_t>(in.ld) * es * in.W * in.H};
+  // Bounding box of base pixels: [-pad, extent + pad - (taps-1)*dil) in each spatial dimension.
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (S - 1) * dil, pad - (R - 1) * dil};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = fn(&m, dtype_enum(dt), 4, in.ptr, dims, strides, lower, upper, box_channels, pixels, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed with code " + std::to_string(static_cast<int>(r)));
+  // Known driver issue (<= 13.1) for im2col maps over tensors smaller than 128 KiB: bit 21 of the
+  // second descriptor word must be cleared (same workaround CUTLASS applies).
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  const uint64_t span = static_cast<uint64_t>(in.ld) * es * in.W * in.H * in.B;
+  if (drv <= 13010 && span < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  return m;
+}
+
+template <typename T, int BN>
+void launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, size_t smem,
+                 cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    PN_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+    configured = true;
+  }
+  conv_umma_kernel<T, BN><<<grid, kNumThreads, smem, s>>>(ta, tb, p);
+}
+
+template <typename T>
+void launch_conv_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, size_t smem,
+                    cudaStream_t s) {
+  switch (bn) {
+    case 32: launch_conv<T, 32>(ta, tb, p, grid, smem, s); break;
+    case 64: launch_conv<T, 64>(ta, tb, p, grid, smem, s); break;
+    case 128: launch_conv<T, 128>(ta, tb, p, grid, smem, s); break;
+    case 256: launch_conv<T, 256>(ta, tb, p, grid, smem, s); break;
+    default: PN_REQUIRE(false, "unsupported N tile");
+  }
+}
+
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+
+int pad_channels(int c, DType dt) {
+  (void)dt;
+  if (c <= 16) return 16;
+  if (c <= 32) return 32;
+  return round_up(c, 64);
+}
+
+void fold_bn(const WeightStore& w, const std::string& prefix, int C, std::vector<float>& scale,
+             std::vector<float>& bias, float eps) {
+  const HostArray& g = get_weight(w, prefix + ".weight");
+  const HostArray& b = get_weight(w, prefix + ".bias");
+  const HostArray& mu = get_weight(w, prefix + ".running_mean");
+  const HostArray& var = get_weight(w, prefix + ".running_var");
+  PN_REQUIRE(g.numel() == C && b.numel() == C && mu.numel() == C && var.numel() == C, "BN size mismatch at " + prefix);
+  scale.resize(C);
+  bias.resize(C);
+  for (int i = 0; i < C; ++i) {
+    const float inv = 1.0f / std::sqrt(var.data[i] + eps);
+    scale[i] = g.data[i] * inv;
+    bias[i] = b.data[i] - mu.data[i] * scale[i];
+  }
+}
+
+void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor& out, const float* weight,
+              const float* scale, const float* bias, const ConvSpec& sp, const Tensor* residual) {
+  const DType dt = in.dt;
+  const int es = static_cast<int>(dtype_size(dt));
+  const int Ho = conv_out(in.H, sp.R, sp.stride, sp.dil, sp.pad);
+  const int Wo = conv_out(in.W, sp.S, sp.stride, sp.dil, sp.pad);
+  PN_REQUIRE(out.B == in.B && out.H == Ho && out.W == Wo, name + ": output shape mismatch");
+  PN_REQUIRE(in.C >= sp.Cin, name + ": input view has fewer channels than the filter");
+  PN_REQUIRE(out.dt == dt || (sp.out_fp32 && out.dt == kF32), name + ": output dtype mismatch");
+  PN_REQUIRE(reinterpret_cast<uintptr_t>(in.ptr) % 16 == 0 && (in.ld * es) % 16 == 0, name + ": input not 16B aligned");
+  PN_REQUIRE(reinterpret_cast<uintptr_t>(out.ptr) % 16 == 0 && (out.ld * dtype_size(out.dt)) % 16 == 0,
+             name + ": output not 16B aligned");
+
+  // K blocking: one smem row (= swizzle span) holds block_k channels of one filter tap.
+  const int cin_pad = in.C;  // caller pads activations (pad_channels)
+  int sw = cin_pad * es >= 128 ? 128 : cin_pad * es;
+  PN_REQUIRE(sw == 32 || sw == 64 || sw == 128, name + ": unsupported channel padding");
+  const int block_k = sw / es;
+  PN_REQUIRE(cin_pad % block_k == 0, name + ": channels not a multiple of the K block");
+  const int kb_per_tap = cin_pad / block_k;
+  const int taps = sp.R * sp.S;
+  const long long ktot = static_cast<long long>(taps) * cin_pad;
+
+  // N tile: the widest tile that still yields at least ~one wave of CTAs.
+  const int cout32 = round_up(sp.Cout, 32);
+  const long long M = static_cast<long long>(in.B) * Ho * Wo;
+  PN_REQUIRE(M < (1ll << 31), name + ": M too large");
+  const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+  int bn = 32;
+  if (sp.force_bn) {
+    bn = sp.force_bn;
+  } else {
+    for (int cand : {256, 128, 64, 32}) {
+      if (cand > cout32) continue;
+      if (cout32 % cand != 0) continue;
+      bn = cand;
+      const long long tiles = static_cast<long long>(m_tiles) * (cout32 / cand);
+      if (tiles >= net.num_sms || cand == 32) break;
+    }
+  }
+  const int cout_pad = round_up(sp.Cout, bn);
+  const int n_tiles = cout_pad / bn;
+
+  // Pack weights [cout_pad][taps][cin_pad] in the activation dtype.
+  std::vector<float> wp(static_cast<size_t>(cout_pad) * ktot, 0.f);
+  for (int co = 0; co < sp.Cout; ++co)
+    for (int ci = 0; ci < sp.Cin; ++ci)
+      for (int r = 0; r < sp.R; ++r)
+        for (int s = 0; s < sp.S; ++s)
+          wp[(static_cast<size_t>(co) * taps + r * sp.S + s) * cin_pad + ci] =
+              weight[((static_cast<size_t>(co) * sp.Cin + ci) * sp.R + r) * sp.S + s];
+  void* w_dev = nullptr;
+  if (dt == kBF16) {
+    std::vector<uint16_t> wb(wp.size());
+    for (size_t i = 0; i < wp.size(); ++i) wb[i] = f32_to_bf16(wp[i]);
+    w_dev = net.arena.upload(wb);
+  } else {
+    w_dev = net.arena.upload(wp);
+  }
+  std::vector<float> sc(cout_pad, 0.f), bi(cout_pad, 0.f);
+  for (int i = 0; i < sp.Cout; ++i) {
+    sc[i] = scale ? scale[i] : 1.f;
+    bi[i] = bias ? bias[i] : 0.f;
+  }
+  const float* sc_dev = net.arena.upload(sc);
+  const float* bi_dev = net.arena.upload(bi);
+
+  const bool a_tiled = (taps == 1 && sp.stride == 1 && sp.pad == 0);
+  CUtensorMap ta;
+  if (a_tiled) {
+    ta = encode_tiled_2d(dt, in.ptr, cin_pad, M, static_cast<uint64_t>(in.ld) * es, block_k, kBlockM, sw);
+  } else {
+    ta = encode_im2col(dt, in, cin_pad, sp.pad, sp.dil, sp.R, sp.S, sp.stride, block_k, kBlockM, sw);
+  }
+  CUtensorMap tb = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, bn, sw);
+
+  ConvParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(M);
+  p.Ho = Ho, p.Wo = Wo, p.R = sp.R, p.S = sp.S;
+  p.stride = sp.stride, p.dil = sp.dil, p.pad = sp.pad;
+  p.kb_per_tap = kb_per_tap, p.block_k = block_k, p.sw = sw;
+  p.m_tiles = m_tiles, p.n_tiles = n_tiles;
+  p.cout_store = std::min(round_up(sp.Cout, 8), out.C);
+  PN_REQUIRE(p.cout_store >= sp.Cout, name + ": output view too narrow");
+  p.a_tiled = a_tiled ? 1 : 0;
+  p.scale = sc_dev, p.bias = bi_dev;
+  p.residual = residual ? residual->ptr : nullptr;
+  p.ldr = residual ? residual->ld : 0;
+  if (residual) PN_REQUIRE(residual->dt == dt && residual->pixels() == M, name + ": residual mismatch");
+  p.out = out.ptr, p.ldc = out.ld;
+  p.relu = sp.relu ? 1 : 0;
+  p.out_fp32 = (out.dt == kF32) ? 1 : 0;
+
+  const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * sw;
+  const size_t budget = 220 * 1024 - 1024 - 256;
+  int stages = static_cast<int>(budget / stage_bytes);
+  if (stages > 8) stages = 8;
+  const int kblocks = taps * kb_per_tap;
+  if (stages > kblocks + 1) stages = std::max(2, kblocks + 1);
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  const int grid = static_cast<int>(std::min<long long>(tiles, net.num_sms));
+
+  net.add(name, [=](cudaStream_t s) {
+    if (dt == kBF16)
+      launch_conv_bn<__nv_bfloat16>(bn, ta, tb, p, grid, smem, s);
+    else
+      launch_conv_bn<float>(bn, ta, tb, p, grid, smem, s);
+  });
+  net.launches_per_forward += 1;
+}
+
+}  // namespace pn

@@ -1,0 +1,280 @@
+// Implicit-GEMM convolution / GEMM on the sm_100a tensor cores.
+//
+//   D[M, Cout] = epilogue( sum_{r,s,c} A[(n,p,q) -> (n, p*stride - pad + r*dil, q*stride - pad + s*dil, c)] * W[cout, r, s, c] )
+//
+// * activations are NHWC (channel stride 1); the A operand is fetched by TMA in im2col mode
+//   (one 128-pixel x BLOCK_K-channel box per filter tap and channel block, hardware zero-fill for the halo),
+//   or in plain tiled 2-D mode for matrices;
+// * weights are packed [Cout_pad][R*S*Cin_pad] (K-major) and fetched by tiled 2-D TMA;
+// * tcgen05.mma (M=128, N=BN, K=32 bytes) accumulates in TMEM, two accumulator stages so that the
+//   epilogue of tile i overlaps the main loop of tile i+1; the kernel is persistent (grid = #SMs);
+// * the epilogue fuses folded BatchNorm (per-channel scale/bias), residual add and ReLU and writes NHWC.
+//
+// Replaces the cuDNN conv + separate BN + ReLU kernels the reference reaches through
+// mmcv ConvModule / mmseg Bottleneck (prediction/mmseg/models/backbones/resnet.py:267-307) and
+// detectron2's BottleneckBlock.
+#pragma once
+#include "ptx.cuh"
+
+namespace pn {
+
+struct ConvParams {
+  int M;           // number of output pixels = B * Ho * Wo (GEMM rows)
+  int Ho, Wo;      // output spatial size
+  int R, S;        // filter taps
+  int stride, dil, pad;
+  int kb_per_tap;  // Cin_pad / BLOCK_K
+  int block_k;     // elements per K block (sw / sizeof(T))
+  int sw;          // bytes per smem row == TMA swizzle span: 32, 64 or 128
+  int stages;      // smem pipeline depth
+  int m_tiles, n_tiles;
+  int cout_store;  // channels actually written per pixel (multiple of 8)
+  int a_tiled;     // 1: A is a plain [M, K] matrix fetched with tiled 2-D TMA
+  const float* scale;  // [n_tiles * BN]
+  const float* bias;   // [n_tiles * BN]
+  const void* residual;  // optional, same dtype as the activations, row stride ldr
+  long long ldr;
+  void* out;
+  long long ldc;  // output row stride in elements
+  int relu;
+  int out_fp32;  // write fp32 regardless of the activation dtype
+};
+
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+
+template <typename T>
+struct ElemTraits;
+template <>
+struct ElemTraits<__nv_bfloat16> {
+  static constexpr uint32_t kFormat = 1;
+};
+template <>
+struct ElemTraits<float> {
+  static constexpr uint32_t kFormat = 2;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x A tile][stages x B tile][barriers][tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kBlockM * p.sw;
+  const uint32_t b_bytes = BN * p.sw;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.stages * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tfull_bar = bars + 2 * p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int taps = p.R * p.S;
+  const int kblocks = taps * p.kb_per_tap;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int m0 = m_tile * kBlockM;
+        const int q = m0 % p.Wo;
+        const int t = m0 / p.Wo;
+        const int pp = t % p.Ho;
+        const int img = t / p.Ho;
+        const int w0 = q * p.stride - p.pad;
+        const int h0 = pp * p.stride - p.pad;
+        int kb_global = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            for (int kb = 0; kb < p.kb_per_tap; ++kb, ++kb_global) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              if (p.a_tiled) {
+                tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, m0);
+              } else {
+                tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0,
+                                   img, static_cast<uint16_t>(s * p.dil), static_cast<uint16_t>(r * p.dil));
+              }
+              tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one elected lane)
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(ElemTraits<T>::kFormat, BN);
+      const int ksteps = p.sw / 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc(smem_u32(smem_a + stage * a_bytes), p.sw);
+          const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + stage * b_bytes), p.sw);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t accum = (kb | k) ? 1u : 0u;
+            if constexpr (ElemTraits<T>::kFormat == 1) {
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            } else {
+              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: TMEM -> regs -> BN/residual/ReLU -> NHWC
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const long long m = static_cast<long long>(m_tile) * kBlockM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chunk * 32, v);
+        tmem_ld_wait();
+        const int n0 = n_tile * BN + chunk * 32;
+        if (row_ok && n0 < p.cout_store) {
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            y[j] = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
+          }
+          if (p.residual != nullptr) {
+            const T* rp = reinterpret_cast<const T*>(p.residual) + m * p.ldr + n0;
+            if constexpr (sizeof(T) == 2) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (n0 + g * 8 + 8 <= p.cout_store) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
+                  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                    const float2 f2 = __bfloat1622float2(b2);
+                    y[g * 8 + 2 * e] += f2.x;
+                    y[g * 8 + 2 * e + 1] += f2.y;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (n0 + g * 4 + 4 <= p.cout_store) {
+                  const float4 rv = *reinterpret_cast<const float4*>(rp + g * 4);
+                  y[g * 4] += rv.x;
+                  y[g * 4 + 1] += rv.y;
+                  y[g * 4 + 2] += rv.z;
+                  y[g * 4 + 3] += rv.w;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          if (sizeof(T) == 2 && !p.out_fp32) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + g * 8 + 8 <= p.cout_store) {
+                uint4 o;
+                o.x = pack_bf16(y[g * 8], y[g * 8 + 1]);
+                o.y = pack_bf16(y[g * 8 + 2], y[g * 8 + 3]);
+                o.z = pack_bf16(y[g * 8 + 4], y[g * 8 + 5]);
+                o.w = pack_bf16(y[g * 8 + 6], y[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + g * 8) = o;
+              }
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (n0 + g * 4 + 4 <= p.cout_store) {
+                *reinterpret_cast<float4*>(op + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace pn

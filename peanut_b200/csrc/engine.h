@@ -1,0 +1,163 @@
+// Host-side runtime shared by the three perception stages: device arena, named fp32 weight store,
+// NHWC tensor views and the list of recorded kernel launches ("ops") that make up one forward pass.
+// Nothing here is exported; the C-ABI lives in api.cu / include/peanut_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pn {
+
+enum DType : int { kBF16 = 0, kF32 = 1 };
+inline size_t dtype_size(DType d) { return d == kBF16 ? 2 : 4; }
+
+#define PN_CUDA_CHECK(expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                               ":" + std::to_string(__LINE__) + ")");                               \
+  } while (0)
+
+#define PN_REQUIRE(cond, msg)                                                        \
+  do {                                                                               \
+    if (!(cond)) throw std::runtime_error(std::string("peanut_b200: ") + (msg));     \
+  } while (0)
+
+// NHWC view: element (b, y, x, c) lives at ptr + ((b*H + y)*W + x)*ld + c.
+struct Tensor {
+  void* ptr = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  long long ld = 0;
+  DType dt = kBF16;
+  long long pixels() const { return static_cast<long long>(B) * H * W; }
+  size_t bytes() const { return static_cast<size_t>(pixels()) * ld * dtype_size(dt); }
+  // A view on channels [c0, c0 + c) of the same pixels.
+  Tensor channels(int c0, int c) const {
+    Tensor t = *this;
+    t.ptr = static_cast<char*>(ptr) + static_cast<size_t>(c0) * dtype_size(dt);
+    t.C = c;
+    return t;
+  }
+};
+
+struct HostArray {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// Owns every device allocation of one network instance.
+class Arena {
+ public:
+  ~Arena() { release(); }
+  void* alloc(size_t bytes, bool zero = true) {
+    void* p = nullptr;
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    PN_CUDA_CHECK(cudaMalloc(&p, bytes));
+    if (zero) PN_CUDA_CHECK(cudaMemset(p, 0, bytes));
+    ptrs_.push_back(p);
+    total_ += bytes;
+    return p;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& h) {
+    T* d = static_cast<T*>(alloc(h.size() * sizeof(T), false));
+    PN_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+  Tensor tensor(int B, int H, int W, int C, DType dt) {
+    Tensor t;
+    t.B = B, t.H = H, t.W = W, t.C = C, t.ld = C, t.dt = dt;
+    t.ptr = alloc(t.bytes());
+    return t;
+  }
+  void release() {
+    for (void* p : ptrs_) cudaFree(p);
+    ptrs_.clear();
+    total_ = 0;
+  }
+  size_t total() const { return total_; }
+
+ private:
+  std::vector<void*> ptrs_;
+  size_t total_ = 0;
+};
+
+using WeightStore = std::map<std::string, HostArray>;
+
+// One recorded forward pass: a flat list of launches on a caller-supplied stream,
+// optionally frozen into a CUDA graph after the first run.
+struct Net {
+  Arena arena;
+  std::vector<std::function<void(cudaStream_t)>> ops;
+  std::vector<std::string> op_names;
+  DType dt = kBF16;
+  int num_sms = 148;
+  long long launches_per_forward = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  int warm_runs = 0;
+  bool use_graph = true;
+
+  void add(const std::string& name, std::function<void(cudaStream_t)> f) {
+    ops.push_back(std::move(f));
+    op_names.push_back(name);
+  }
+  void run_eager(cudaStream_t s) {
+    for (auto& f : ops) f(s);
+  }
+  void run(cudaStream_t s);
+  ~Net();
+};
+
+inline const HostArray& get_weight(const WeightStore& w, const std::string& name) {
+  auto it = w.find(name);
+  PN_REQUIRE(it != w.end(), "missing weight '" + name + "'");
+  return it->second;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Convolution (conv_host.cu)
+struct ConvSpec {
+  int Cin = 0, Cout = 0, R = 1, S = 1, stride = 1, dil = 1, pad = 0;
+  bool relu = false;
+  bool out_fp32 = false;
+  int force_bn = 0;  // test hook: force the N tile
+};
+// weight: fp32 [Cout][Cin][R][S]; scale / bias: fp32 [Cout] (folded BN or plain bias with scale 1).
+// `out` must already describe the destination view (B, Ho, Wo, C >= Cout rounded to 8, ld).
+void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor& out, const float* weight,
+              const float* scale, const float* bias, const ConvSpec& spec, const Tensor* residual = nullptr);
+// Folds BatchNorm running statistics into (scale, bias): y = x*scale + bias, eps as in nn.BatchNorm2d.
+void fold_bn(const WeightStore& w, const std::string& bn_prefix, int C, std::vector<float>& scale,
+             std::vector<float>& bias, float eps = 1e-5f);
+inline int conv_out(int in, int k, int stride, int dil, int pad) {
+  return (in + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+}
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// Channel padding rule for activation tensors of dtype dt: multiple of 16 up to 64, then multiple of 64 (bf16);
+// keeps every K block a whole TMA swizzle row.
+int pad_channels(int c, DType dt);
+
+// ---------------------------------------------------------------------------------------------
+// Layout / pooling / resize kernels (ops.cu)
+void add_nchw_to_nhwc(Net& net, const float* const* src_slot, const Tensor& out, int C);  // fp32 NCHW -> NHWC dt, zero pad
+void add_maxpool3x3s2(Net& net, const Tensor& in, const Tensor& out);
+void add_ppm_pool(Net& net, const Tensor& in, const std::vector<int>& scales, const std::vector<Tensor>& outs);
+void add_bilinear_into(Net& net, const Tensor& in, const Tensor& out);  // align_corners=False, NHWC -> NHWC view
+void add_upsample_logits(Net& net, const Tensor& logits, int C, int Hout, int Wout, float* const* dst_slot,
+                         const int* sigmoid_slot);  // NHWC fp32 -> NCHW fp32 (+sigmoid)
+
+}  // namespace pn

@@ -1,0 +1,90 @@
+"""Parity of the tcgen05 implicit-GEMM convolution (pn_conv2d) against torch.nn.functional.conv2d.
+
+bf16 path: inputs/weights are pre-rounded to bf16 so both sides multiply identical operands; the only
+differences left are fp32 accumulation order and the final bf16 rounding of the stored output
+(relative 2^-8) -> tolerance 1e-2 relative to the output scale.  tf32 path: 10-bit mantissa operands.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from peanut_b200 import _lib
+from tests.helpers import bf16_round, conv2d_cabi
+
+pytestmark = pytest.mark.gpu
+
+# (B, Cin, H, W, Cout, k, stride, dil, pad, force_bn)
+CASES = [
+    (1, 64, 16, 16, 64, 1, 1, 1, 0, 0),      # 1x1, tiled-A path, K = one block
+    (1, 256, 20, 24, 128, 1, 1, 1, 0, 0),    # 1x1, several K blocks, M tail (480 rows)
+    (2, 64, 15, 17, 64, 3, 1, 1, 1, 0),      # 3x3 pad 1, im2col, odd sizes, tile crosses images
+    (1, 128, 31, 29, 128, 3, 2, 1, 1, 0),    # 3x3 stride 2 (layer2.0.conv2)
+    (1, 256, 23, 23, 256, 3, 1, 2, 2, 0),    # dilation 2 (layer3)
+    (1, 512, 19, 19, 512, 3, 1, 4, 4, 0),    # dilation 4 (layer4)
+    (1, 256, 24, 24, 512, 1, 2, 1, 0, 0),    # 1x1 stride 2 downsample (im2col with stride)
+    (1, 14, 40, 40, 32, 3, 2, 1, 1, 0),      # stem.0: 14 -> pad 16 channels, 32-byte swizzle rows
+    (1, 32, 33, 35, 64, 3, 1, 1, 1, 0),      # stem.6: 32 channels, 64-byte rows
+    (1, 3, 64, 48, 64, 7, 2, 1, 3, 0),       # Mask-RCNN stem 7x7 s2 p3
+    (1, 512, 12, 12, 6, 1, 1, 1, 0, 0),      # classifier: Cout 6 -> N tile 32, 8 stored channels
+    (1, 128, 30, 30, 256, 3, 1, 1, 1, 256),  # N tile 256
+    (1, 128, 30, 30, 256, 3, 1, 1, 1, 64),   # N tile 64
+    (3, 2048, 6, 6, 512, 1, 1, 1, 0, 0),     # PPM 1x1 on pooled bins, long K
+    (1, 1024, 9, 9, 512, 3, 1, 1, 1, 0),     # long K loop (144 blocks) > pipeline depth
+    (4, 64, 48, 48, 256, 1, 1, 1, 0, 0),     # many tiles per CTA? (72 m-tiles x n) persistent loop
+    (8, 256, 40, 40, 256, 3, 1, 1, 1, 128),  # 100 m-tiles x 2 n-tiles > 148 CTAs: multi-tile persistence
+]
+
+
+def _run(ctx, case, precision, with_res=True):
+    B, Cin, H, W, Cout, k, stride, dil, pad, bn = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn((B, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    if precision == _lib.PN_BF16:
+        x, w = bf16_round(x), bf16_round(w)
+    xd = x.cuda()
+    ref = F.conv2d(xd.double(), w.cuda().double(), stride=stride, padding=pad, dilation=dil)
+    ref = ref * scale.cuda().double()[None, :, None, None] + bias.cuda().double()[None, :, None, None]
+    res = None
+    if with_res:
+        res = torch.randn(ref.shape, generator=g)
+        if precision == _lib.PN_BF16:
+            res = bf16_round(res)
+        res = res.cuda()
+        ref = ref + res.double()
+    ref = torch.relu(ref).float()
+    y = conv2d_cabi(ctx, xd, w, scale, bias, res, stride=stride, dil=dil, pad=pad, relu=True, force_bn=bn,
+                    precision=precision)
+    torch.cuda.synchronize()
+    return y, ref
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_bf16(ctx, case):
+    y, ref = _run(ctx, case, _lib.PN_BF16)
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= 1e-2 * scale, f"max abs err {err} vs scale {scale}"
+    # mean error far below the bf16 output rounding bound => no systematically wrong taps / channels
+    assert (y - ref).abs().mean().item() <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("case", CASES[:12], ids=[str(c) for c in CASES[:12]])
+def test_conv_tf32(ctx, case):
+    y, ref = _run(ctx, case, _lib.PN_TF32)
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= 3e-3 * scale, f"max abs err {err} vs scale {scale}"
+
+
+def test_conv_no_epilogue_extras(ctx):
+    """scale/bias/residual all absent, no ReLU: negative values must survive."""
+    g = torch.Generator().manual_seed(7)
+    x = bf16_round(torch.randn((1, 64, 10, 10), generator=g))
+    w = bf16_round(torch.randn((64, 64, 3, 3), generator=g) / 24.0)
+    y = conv2d_cabi(ctx, x.cuda(), w, pad=1)
+    ref = F.conv2d(x.cuda(), w.cuda(), padding=1)
+    assert (y - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (y < 0).any()

@@ -62,10 +62,17 @@ int pn_prednet_num_launches(pn_ctx* ctx);
  * [B,2048,H/8,W/8], 1 = low-resolution logits [B,num_classes,H/8,W/8]. */
 int pn_prednet_read_tap(pn_ctx* ctx, int which, float* out_dev, void* stream);
 
+/* Per-launch device time of one forward pass (CUDA events around every recorded launch, eager mode,
+ * averaged over `iters` passes after one warm-up).  ms_out[max_ops] receives milliseconds per op,
+ * names_out a '\n'-separated list of op names.  Measurement aid for bench.py / profiles/. */
+int pn_prednet_num_ops(pn_ctx* ctx);
+int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char* names_out, int names_bytes);
+
 /* ---- Single fused convolution (conv + per-channel scale/bias + optional residual + ReLU), used by the
  * parity tests of the tensor-core kernel against torch.nn.functional.conv2d.
  * x_dev [B,Cin,H,W], w_host [Cout,Cin,R,S], scale_host/bias_host [Cout] or NULL,
- * residual_dev [B,Cout,Ho,Wo] or NULL, y_dev [B,Cout,Ho,Wo]; force_bn: 0 = auto N tile, else 32/64/128/256. */
+ * residual_dev [B,Cout,Ho,Wo] or NULL, y_dev [B,Cout,Ho,Wo]; force_bn: 0 = auto N tile, else 32/64/128/256;
+ * OR-ing 0x1000 forces the direct-store epilogue instead of the TMA-staged one (both are parity-tested). */
 int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,
               const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
               int stride, int dil, int pad, int relu, int force_bn, float* y_dev);

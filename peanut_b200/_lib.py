@@ -32,6 +32,8 @@ PROTOTYPES = {
     "pn_prednet_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_prednet_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "pn_prednet_read_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_prednet_num_ops": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_prednet_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     "pn_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                   [ctypes.c_void_p] * 4 + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
 }

@@ -1,5 +1,6 @@
 // C-ABI of libpeanut_b200.so (declared in include/peanut_b200.h).  Every entry point translates
 // C++ exceptions into a status code + thread-local message; no torch types cross this boundary.
+#include <cstring>
 #include <memory>
 #include <mutex>
 
@@ -203,6 +204,61 @@ int pn_prednet_read_tap(pn_ctx* ctx, int which, float* out_dev, void* stream) {
   PN_API_END
 }
 
+int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char* names_out, int names_bytes) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->prednet && ms_out && iters > 0, "pn_prednet_profile: not built");
+  Net& net = c->prednet->net;
+  const int n = static_cast<int>(net.ops.size());
+  PN_REQUIRE(max_ops >= n, "pn_prednet_profile: ms_out too small");
+  PredNet& pnn = *c->prednet;
+  const size_t in_bytes = static_cast<size_t>(pnn.B) * pnn.C * pnn.H * pnn.W * sizeof(float);
+  const size_t out_bytes = static_cast<size_t>(pnn.B) * pnn.num_classes * pnn.H * pnn.W * sizeof(float);
+  if (!pnn.stage_in) {
+    pnn.stage_in = static_cast<float*>(net.arena.alloc(in_bytes, true));
+    pnn.stage_out = static_cast<float*>(net.arena.alloc(out_bytes, false));
+  }
+  set_pred_slots_kernel<<<1, 1, 0, c->stream>>>(pnn.slots, pnn.stage_in, pnn.stage_out, 0);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) PN_CUDA_CHECK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  for (int it = 0; it < iters + 1; ++it) {
+    PN_CUDA_CHECK(cudaEventRecord(ev[0], c->stream));
+    for (int i = 0; i < n; ++i) {
+      net.ops[i](c->stream);
+      PN_CUDA_CHECK(cudaEventRecord(ev[i + 1], c->stream));
+    }
+    PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (it == 0) continue;  // warm-up
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      PN_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  std::string names;
+  for (int i = 0; i < n; ++i) {
+    ms_out[i] = static_cast<float>(acc[i] / iters);
+    names += net.op_names[i];
+    names += '\n';
+  }
+  if (names_out && names_bytes > 0) {
+    const size_t k = std::min(names.size(), static_cast<size_t>(names_bytes - 1));
+    memcpy(names_out, names.data(), k);
+    names_out[k] = 0;
+  }
+  return n > 0 ? 0 : 0;
+  PN_API_END
+}
+
+int pn_prednet_num_ops(pn_ctx* ctx) {
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !c->prednet) return -1;
+  return static_cast<int>(c->prednet->net.ops.size());
+}
+
 int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,
               const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
               int stride, int dil, int pad, int relu, int force_bn, float* y_dev) {
@@ -234,7 +290,8 @@ int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, in
   ConvSpec sp;
   sp.Cin = Cin, sp.Cout = Cout, sp.R = R, sp.S = S, sp.stride = stride, sp.dil = dil, sp.pad = pad;
   sp.relu = relu != 0;
-  sp.force_bn = force_bn;
+  sp.force_bn = force_bn & 0xfff;
+  sp.force_direct_epilogue = (force_bn & 0x1000) != 0;
   add_conv(net, "pn_conv2d", x, y, w_host, scale_host, bias_host, sp, residual_dev ? &res : nullptr);
   net.run(nullptr);
   nhwc_to_nchw(y, Cout, y_dev, nullptr);

@@ -75,26 +75,28 @@ CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pa
   return m;
 }
 
+struct ConvMaps {
+  CUtensorMap a, b, out, res;
+};
+
 template <typename T, int BN>
-void launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, size_t smem,
-                 cudaStream_t s) {
+void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     PN_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     configured = true;
   }
-  conv_umma_kernel<T, BN><<<grid, kNumThreads, smem, s>>>(ta, tb, p);
+  conv_umma_kernel<T, BN><<<grid, kNumThreads, smem, s>>>(tm.a, tm.b, tm.out, tm.res, p);
 }
 
 template <typename T>
-void launch_conv_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int grid, size_t smem,
-                    cudaStream_t s) {
+void launch_conv_bn(int bn, const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
   switch (bn) {
-    case 32: launch_conv<T, 32>(ta, tb, p, grid, smem, s); break;
-    case 64: launch_conv<T, 64>(ta, tb, p, grid, smem, s); break;
-    case 128: launch_conv<T, 128>(ta, tb, p, grid, smem, s); break;
-    case 256: launch_conv<T, 256>(ta, tb, p, grid, smem, s); break;
+    case 32: launch_conv<T, 32>(tm, p, grid, smem, s); break;
+    case 64: launch_conv<T, 64>(tm, p, grid, smem, s); break;
+    case 128: launch_conv<T, 128>(tm, p, grid, smem, s); break;
+    case 256: launch_conv<T, 256>(tm, p, grid, smem, s); break;
     default: PN_REQUIRE(false, "unsupported N tile");
   }
 }
@@ -189,6 +191,13 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     for (size_t i = 0; i < wp.size(); ++i) wb[i] = f32_to_bf16(wp[i]);
     w_dev = net.arena.upload(wb);
   } else {
+    // tf32 path: round weights to the 10-bit mantissa (nearest, ties away) the tensor core would otherwise truncate to
+    for (float& v : wp) {
+      uint32_t u;
+      std::memcpy(&u, &v, 4);
+      if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+      std::memcpy(&v, &u, 4);
+    }
     w_dev = net.arena.upload(wp);
   }
   std::vector<float> sc(cout_pad, 0.f), bi(cout_pad, 0.f);
@@ -200,13 +209,15 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   const float* bi_dev = net.arena.upload(bi);
 
   const bool a_tiled = (taps == 1 && sp.stride == 1 && sp.pad == 0);
-  CUtensorMap ta;
+  ConvMaps tm;
   if (a_tiled) {
-    ta = encode_tiled_2d(dt, in.ptr, cin_pad, M, static_cast<uint64_t>(in.ld) * es, block_k, kBlockM, sw);
+    tm.a = encode_tiled_2d(dt, in.ptr, cin_pad, M, static_cast<uint64_t>(in.ld) * es, block_k, kBlockM, sw);
   } else {
-    ta = encode_im2col(dt, in, cin_pad, sp.pad, sp.dil, sp.R, sp.S, sp.stride, block_k, kBlockM, sw);
+    tm.a = encode_im2col(dt, in, cin_pad, sp.pad, sp.dil, sp.R, sp.S, sp.stride, block_k, kBlockM, sw);
   }
-  CUtensorMap tb = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, bn, sw);
+  tm.b = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, bn, sw);
+  tm.out = tm.b;
+  tm.res = tm.b;
 
   ConvParams p;
   std::memset(&p, 0, sizeof(p));
@@ -225,23 +236,61 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.out = out.ptr, p.ldc = out.ld;
   p.relu = sp.relu ? 1 : 0;
   p.out_fp32 = (out.dt == kF32) ? 1 : 0;
+  p.round_tf32 = (dt == kF32 && !sp.out_fp32) ? 1 : 0;
+
+  // Epilogue mode: smem-staged TMA stores (+ TMA residual prefetch) whenever a stored row chunk is at
+  // least 64 bytes and the output has the activation dtype; otherwise direct per-thread stores.
+  size_t epi_bytes = 0;
+  {
+    const int store_bytes = p.cout_store * es;
+    int cb = 0;
+    if (out.dt == dt && !sp.force_direct_epilogue) {
+      if (store_bytes >= 128 && bn * es >= 128) cb = 128;
+      else if (store_bytes >= 64 && bn * es >= 64 && es == 2) cb = 64;
+    }
+    if (cb) {
+      p.epi_tma = 1;
+      p.cb = cb;
+      p.res_bufs = residual ? 3 : 0;
+      tm.out = encode_tiled_2d(dt, out.ptr, p.cout_store, M, static_cast<uint64_t>(out.ld) * es, cb / es, kBlockM, cb);
+      if (residual)
+        tm.res = encode_tiled_2d(dt, residual->ptr, p.cout_store, M, static_cast<uint64_t>(residual->ld) * es, cb / es,
+                                 kBlockM, cb);
+      p.out_bufs = 2;
+      epi_bytes = static_cast<size_t>(p.out_bufs + p.res_bufs) * kBlockM * cb;
+    }
+  }
 
   const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * sw;
-  const size_t budget = 220 * 1024 - 1024 - 256;
-  int stages = static_cast<int>(budget / stage_bytes);
-  if (stages > 8) stages = 8;
   const int kblocks = taps * kb_per_tap;
+  size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 2 * bn * sizeof(float) + 256 /*barriers*/;
+  size_t budget = 227 * 1024 - fixed_bytes;
+  int stages = static_cast<int>(budget / stage_bytes);
+  if (p.epi_tma && kblocks >= 32) {
+    // K-heavy layer: the epilogue is a small fraction of the tile, so trade the second output staging
+    // buffer for a deeper operand pipeline when that buys a stage.
+    const size_t fixed1 = fixed_bytes - static_cast<size_t>(kBlockM) * p.cb;
+    const int stages1 = static_cast<int>((227 * 1024 - fixed1) / stage_bytes);
+    if (stages1 > stages && stages < 6) {
+      p.out_bufs = 1;
+      fixed_bytes = fixed1;
+      budget = 227 * 1024 - fixed_bytes;
+      stages = stages1;
+    }
+  }
+  if (stages > 8) stages = 8;
   if (stages > kblocks + 1) stages = std::max(2, kblocks + 1);
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+  PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
+  const size_t smem = fixed_bytes + stages * stage_bytes;
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   const int grid = static_cast<int>(std::min<long long>(tiles, net.num_sms));
 
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
-      launch_conv_bn<__nv_bfloat16>(bn, ta, tb, p, grid, smem, s);
+      launch_conv_bn<__nv_bfloat16>(bn, tm, p, grid, smem, s);
     else
-      launch_conv_bn<float>(bn, ta, tb, p, grid, smem, s);
+      launch_conv_bn<float>(bn, tm, p, grid, smem, s);
   });
   net.launches_per_forward += 1;
 }

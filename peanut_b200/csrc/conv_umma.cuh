@@ -9,6 +9,13 @@
 // * tcgen05.mma (M=128, N=BN, K=32 bytes) accumulates in TMEM, two accumulator stages so that the
 //   epilogue of tile i overlaps the main loop of tile i+1; the kernel is persistent (grid = #SMs);
 // * the epilogue fuses folded BatchNorm (per-channel scale/bias), residual add and ReLU and writes NHWC.
+//   Fast path: the residual tile is prefetched by TMA into shared memory by a dedicated warp (it does not
+//   depend on the accumulators, so it runs ahead of the MMAs), results are staged in swizzled shared
+//   memory and written back with TMA bulk stores (full 128-byte lines, M/N tails clipped by hardware).
+//   Fallback path (narrow or mixed-precision outputs): direct 16-byte global stores per thread.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (one per TMEM lane quarter),
+// 6 = residual prefetcher.
 //
 // Replaces the cuDNN conv + separate BN + ReLU kernels the reference reaches through
 // mmcv ConvModule / mmseg Bottleneck (prediction/mmseg/models/backbones/resnet.py:267-307) and
@@ -38,10 +45,15 @@ struct ConvParams {
   long long ldc;  // output row stride in elements
   int relu;
   int out_fp32;  // write fp32 regardless of the activation dtype
+  int round_tf32;  // fp32 activations: round stored values to tf32 (nearest) so the next MMA's truncation is exact
+  int epi_tma;   // 1: smem-staged epilogue with TMA residual loads / TMA stores
+  int cb;        // epilogue chunk row bytes (= swizzle span of the out/residual maps): 32, 64 or 128
+  int res_bufs;  // residual staging depth (0 when no residual)
+  int out_bufs;  // output staging depth: 2, or 1 for K-heavy layers where a deeper A/B pipeline matters more
 };
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+constexpr int kNumThreads = 224;
 
 template <typename T>
 struct ElemTraits;
@@ -58,24 +70,41 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// Byte offset of 16-byte unit j of row r inside a TMA-swizzled tile whose rows are cb bytes.
+__device__ __forceinline__ uint32_t swz_off(uint32_t r, uint32_t j, uint32_t cb) {
+  uint32_t off = r * cb + (j << 4);
+  return off ^ (((off >> 7) & ((cb >> 4) - 1)) << 4);
+}
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x A tile][stages x B tile][barriers][tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = kBlockM * p.sw;
   const uint32_t b_bytes = BN * p.sw;
+  const uint32_t chunk_bytes = p.epi_tma ? kBlockM * p.cb : 0;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + p.stages * a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_bytes);
+  uint8_t* smem_b = smem_a + p.stages * a_bytes;
+  uint8_t* smem_out = smem_b + p.stages * b_bytes;
+  uint8_t* smem_res = smem_out + p.out_bufs * chunk_bytes;
+  float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * chunk_bytes);
+  float* smem_bias = smem_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rempty_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,6 +113,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.epi_tma) tma_prefetch_desc(&tmap_out);
+    if (p.epi_tma && p.residual) tma_prefetch_desc(&tmap_res);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -91,6 +122,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&rfull_bar[i], 1);
+      mbar_init(&rempty_bar[i], 4);
     }
     fence_barrier_init();
   }
@@ -106,6 +141,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int taps = p.R * p.S;
   const int kblocks = taps * p.kb_per_tap;
+  const int cols_per_chunk = p.epi_tma ? p.cb / static_cast<int>(sizeof(T)) : 32;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -180,9 +216,140 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------ epilogue: TMEM -> regs -> BN/residual/ReLU -> NHWC
+  } else if (warp == 6) {
+    // ------------------------------------------------------------ residual prefetcher (TMA epilogue only)
+    if (p.epi_tma && p.residual != nullptr && elect_one()) {
+      uint32_t g = 0;  // running chunk counter, same sequence as the epilogue warps
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        for (int n0 = n_tile * BN; n0 < n_tile * BN + BN && n0 < p.cout_store; n0 += cols_per_chunk, ++g) {
+          const uint32_t rb = g % p.res_bufs;
+          const uint32_t ph = (g / p.res_bufs) & 1;
+          mbar_wait(&rempty_bar[rb], ph ^ 1);
+          mbar_arrive_expect_tx(&rfull_bar[rb], chunk_bytes);
+          tma_load_2d(&tmap_res, &rfull_bar[rb], smem_res + rb * chunk_bytes, n0, m_tile * kBlockM);
+        }
+      }
+    }
+  } else if (p.epi_tma) {
+    // ------------------------------------------------------------ epilogue, fast path
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const uint32_t row = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127
+    const bool issuer = (et == 0);
+    constexpr int kUnits = 32 * sizeof(T) / 16;  // 16-byte units per 32 columns
+    uint32_t g = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      // per-tile scale/bias -> smem (previous tile's readers are all past their last chunk barrier)
+      for (int i = et; i < BN; i += 128) {
+        smem_scale[i] = __ldg(p.scale + n_tile * BN + i);
+        smem_bias[i] = __ldg(p.bias + n_tile * BN + i);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      for (int n0 = n_tile * BN; n0 < n_tile * BN + BN && n0 < p.cout_store; n0 += cols_per_chunk, ++g) {
+        uint8_t* obuf = smem_out + (p.out_bufs == 2 ? (g & 1) : 0) * chunk_bytes;
+        if (issuer) {  // the store that last read this buffer has drained
+          if (p.out_bufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        named_bar_sync(1, 128);
+        const uint8_t* rbuf = nullptr;
+        uint32_t rb = 0;
+        if (p.residual != nullptr) {
+          rb = g % p.res_bufs;
+          mbar_wait(&rfull_bar[rb], (g / p.res_bufs) & 1);
+          rbuf = smem_res + rb * chunk_bytes;
+        }
+        const int nl0 = n0 - n_tile * BN;  // column offset inside the tile
+#pragma unroll 1
+        for (int sub = 0; sub < cols_per_chunk / 32; ++sub) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + nl0 + sub * 32, v);
+          tmem_ld_wait();
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(smem_scale + nl0 + sub * 32 + j);
+            const float4 bi = *reinterpret_cast<const float4*>(smem_bias + nl0 + sub * 32 + j);
+            y[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+            y[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+            y[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+            y[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+          }
+          if (rbuf != nullptr) {
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + swz_off(row, sub * kUnits + u, p.cb));
+              if constexpr (sizeof(T) == 2) {
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                  y[u * 8 + 2 * e] += f2.x;
+                  y[u * 8 + 2 * e + 1] += f2.y;
+                }
+              } else {
+                y[u * 4] += __uint_as_float(rv.x);
+                y[u * 4 + 1] += __uint_as_float(rv.y);
+                y[u * 4 + 2] += __uint_as_float(rv.z);
+                y[u * 4 + 3] += __uint_as_float(rv.w);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < kUnits; ++u) {
+            uint4 o;
+            if constexpr (sizeof(T) == 2) {
+              o.x = pack_bf16(y[u * 8], y[u * 8 + 1]);
+              o.y = pack_bf16(y[u * 8 + 2], y[u * 8 + 3]);
+              o.z = pack_bf16(y[u * 8 + 4], y[u * 8 + 5]);
+              o.w = pack_bf16(y[u * 8 + 6], y[u * 8 + 7]);
+            } else {
+              if (p.round_tf32) {
+                o.x = __float_as_uint(round_tf32(y[u * 4]));
+                o.y = __float_as_uint(round_tf32(y[u * 4 + 1]));
+                o.z = __float_as_uint(round_tf32(y[u * 4 + 2]));
+                o.w = __float_as_uint(round_tf32(y[u * 4 + 3]));
+              } else {
+                o.x = __float_as_uint(y[u * 4]);
+                o.y = __float_as_uint(y[u * 4 + 1]);
+                o.z = __float_as_uint(y[u * 4 + 2]);
+                o.w = __float_as_uint(y[u * 4 + 3]);
+              }
+            }
+            *reinterpret_cast<uint4*>(obuf + swz_off(row, sub * kUnits + u, p.cb)) = o;
+          }
+        }
+        fence_proxy_async();  // make the st.shared above visible to the TMA (async proxy)
+        if (rbuf != nullptr) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rempty_bar[rb]);
+        }
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_2d(&tmap_out, obuf, n0, m_tile * kBlockM);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if (issuer) tma_store_wait_all();
+  } else {
+    // ------------------------------------------------------------ epilogue, direct path: TMEM -> regs -> global
+    const int quarter = warp & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -215,8 +382,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                    const float2 f2 = __bfloat1622float2(b2);
+                    const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
                     y[g * 8 + 2 * e] += f2.x;
                     y[g * 8 + 2 * e + 1] += f2.y;
                   }
@@ -253,6 +419,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           } else {
+            if (p.round_tf32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] = round_tf32(y[j]);
+            }
             float* op = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {

@@ -135,6 +135,7 @@ struct ConvSpec {
   bool relu = false;
   bool out_fp32 = false;
   int force_bn = 0;  // test hook: force the N tile
+  bool force_direct_epilogue = false;  // test hook: bypass the TMA-staged epilogue
 };
 // weight: fp32 [Cout][Cin][R][S]; scale / bias: fp32 [Cout] (folded BN or plain bias with scale 1).
 // `out` must already describe the destination view (B, Ho, Wo, C >= Cout rounded to 8, ld).

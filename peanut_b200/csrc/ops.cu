@@ -22,6 +22,11 @@ __global__ void nchw_to_nhwc_kernel(const float* const* src_slot, T* dst, int B,
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
       v[j] = c < C ? __ldg(src + (static_cast<long long>(b) * C + c) * HW + hw) : 0.f;
+      if (sizeof(T) == 4) {  // fp32 activations feed tf32 MMAs: round-to-nearest here, truncation there is then exact
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[j]));
+        v[j] = __uint_as_float(r);
+      }
     }
     store8(o + c0, v);
   }

@@ -118,6 +118,14 @@ class Segmentor:
                                                         int(bool(apply_sigmoid)), out_host.data_ptr()))
         return out_host
 
+    def profile(self, iters=5):
+        """[(op name, milliseconds)] per recorded launch of the currently built network."""
+        n = int(self.ctx.lib.pn_prednet_num_ops(self.ctx.handle))
+        ms = (ctypes.c_float * n)()
+        names = ctypes.create_string_buffer(64 * n)
+        _lib.check(self.ctx.lib.pn_prednet_profile(self.ctx.handle, iters, ms, n, names, len(names)))
+        return list(zip(names.value.decode().strip().split("\n"), [float(v) for v in ms]))
+
     def read_tap(self, which):
         B, C, H, W = self._built
         d = lambda v: (v - 1) // 2 + 1  # one stride-2 stage (3x3 pad 1 / maxpool 3x3 pad 1)

@@ -32,6 +32,10 @@ CASES = [
     (1, 1024, 9, 9, 512, 3, 1, 1, 1, 0),     # long K loop (144 blocks) > pipeline depth
     (4, 64, 48, 48, 256, 1, 1, 1, 0, 0),     # many tiles per CTA? (72 m-tiles x n) persistent loop
     (8, 256, 40, 40, 256, 3, 1, 1, 1, 128),  # 100 m-tiles x 2 n-tiles > 148 CTAs: multi-tile persistence
+    (2, 64, 15, 17, 64, 3, 1, 1, 1, 0x1000),       # direct-store epilogue (fallback path)
+    (1, 256, 24, 24, 512, 1, 2, 1, 0, 0x1000 | 128),
+    (1, 64, 36, 36, 48, 1, 1, 1, 0, 0),      # Cout 48: partial 128-byte chunk clipped by the TMA store
+    (6, 512, 30, 30, 2048, 1, 1, 1, 0, 0),   # conv3-like: many chunks per tile, residual ring wraps
 ]
 
 

@@ -68,6 +68,38 @@ int pn_prednet_read_tap(pn_ctx* ctx, int which, float* out_dev, void* stream);
 int pn_prednet_num_ops(pn_ctx* ctx);
 int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char* names_out, int names_bytes);
 
+/* ---- Stage B: Semantic_Mapping ("Sem_Map_Module"), batched over environments.
+ * Replaces Semantic_Mapping.forward, nav/agent/mapping.py:52-179 (call sites nav/agent/agent_state.py:114-115,
+ * 273-274).  The configuration mirrors the argparse flags the module reads (nav/arguments.py:44-51, 58-60, 74-84). */
+typedef struct pn_semmap_cfg {
+  int frame_height;        /* 120 */
+  int frame_width;         /* 160 */
+  int map_resolution;      /* 5 (cm per cell) */
+  int map_size_cm;         /* 4800 */
+  int global_downscaling;  /* 2  -> local map of 480 x 480 cells */
+  int vision_range;        /* 100 */
+  int du_scale;            /* 1 (only value supported) */
+  int num_sem_categories;  /* 10 */
+  float hfov;              /* 79 */
+  float camera_height;     /* 0.88 (m) */
+  float cat_pred_threshold; /* 5.0 */
+  float exp_pred_threshold; /* 1.0 */
+  float map_pred_threshold; /* 0.1 */
+} pn_semmap_cfg;
+
+int pn_semmap_build(pn_ctx* ctx, int num_envs, const pn_semmap_cfg* cfg);
+/* obs [E, 4+S, h, w] (channel 3 = depth in cm, 4.. = semantic masks), pose_delta [E,3] (dx m, dy m, dtheta rad),
+ * maps_last [E, 4+S, n, n] - dense when maps_last_strides is NULL, else a strided view with element strides
+ * {env, channel, row} (the reference passes a window of full_map, agent_state.py:206-208) -, poses_inout [E,3] (x m, y m, theta deg; UPDATED IN PLACE like the reference mutates
+ * poses_last), fp_map_out [E, vr, vr] (may be NULL), map_out [E, 4+S, n, n] (must not alias maps_last). */
+int pn_semmap_forward(pn_ctx* ctx, const float* obs_dev, const float* pose_delta_dev, const float* maps_last_dev,
+                      const int64_t* maps_last_strides, float* poses_inout_dev, float* fp_map_out_dev,
+                      float* map_out_dev, void* stream);
+/* Parity tap: ego map [E, 2+S, vr, vr] (obstacle, explored, categories) before resampling, and the per-env
+ * stair-mask decision (mapping.py:94).  Either pointer may be NULL. */
+int pn_semmap_read_ego(pn_ctx* ctx, float* ego_out_dev, int* stair_flags_out_dev, void* stream);
+int pn_semmap_num_launches(pn_ctx* ctx);
+
 /* ---- Single fused convolution (conv + per-channel scale/bias + optional residual + ReLU), used by the
  * parity tests of the tensor-core kernel against torch.nn.functional.conv2d.
  * x_dev [B,Cin,H,W], w_host [Cout,Cin,R,S], scale_host/bias_host [Cout] or NULL,

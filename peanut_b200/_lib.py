@@ -34,9 +34,24 @@ PROTOTYPES = {
     "pn_prednet_read_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "pn_prednet_num_ops": (ctypes.c_int, [ctypes.c_void_p]),
     "pn_prednet_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    "pn_semmap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
+    "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "pn_semmap_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "pn_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                   [ctypes.c_void_p] * 4 + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
 }
+
+
+
+class SemMapCfg(ctypes.Structure):
+    """struct pn_semmap_cfg"""
+    _fields_ = [("frame_height", ctypes.c_int), ("frame_width", ctypes.c_int), ("map_resolution", ctypes.c_int),
+                ("map_size_cm", ctypes.c_int), ("global_downscaling", ctypes.c_int), ("vision_range", ctypes.c_int),
+                ("du_scale", ctypes.c_int), ("num_sem_categories", ctypes.c_int), ("hfov", ctypes.c_float),
+                ("camera_height", ctypes.c_float), ("cat_pred_threshold", ctypes.c_float),
+                ("exp_pred_threshold", ctypes.c_float), ("map_pred_threshold", ctypes.c_float)]
+
 
 _lib = None
 

@@ -1,5 +1,6 @@
 // C-ABI of libpeanut_b200.so (declared in include/peanut_b200.h).  Every entry point translates
 // C++ exceptions into a status code + thread-local message; no torch types cross this boundary.
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -7,6 +8,7 @@
 #include "../../include/peanut_b200.h"
 #include "engine.h"
 #include "prednet.h"
+#include "semmap.h"
 #include "vec.cuh"
 
 namespace pn {
@@ -16,6 +18,7 @@ struct Ctx {
   int num_sms = 148;
   WeightStore weights;
   std::unique_ptr<PredNet> prednet;
+  std::unique_ptr<SemMap> semmap;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
 };
 
@@ -105,6 +108,7 @@ int pn_destroy(pn_ctx* ctx) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->prednet.reset();
+    c->semmap.reset();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
   }
@@ -202,6 +206,89 @@ int pn_prednet_read_tap(pn_ctx* ctx, int which, float* out_dev, void* stream) {
     PN_REQUIRE(false, "pn_prednet_read_tap: unknown tap");
   PN_CUDA_CHECK(cudaGetLastError());
   PN_API_END
+}
+
+int pn_semmap_build(pn_ctx* ctx, int num_envs, const pn_semmap_cfg* cfg) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(cfg != nullptr && num_envs > 0, "pn_semmap_build: bad arguments");
+  PN_REQUIRE(cfg->du_scale == 1, "pn_semmap_build: du_scale != 1 is not supported (reference default is 1)");
+  PN_REQUIRE(cfg->map_resolution > 0 && cfg->vision_range > 0 && cfg->global_downscaling > 0, "pn_semmap_build: bad geometry");
+  // Constants exactly as Semantic_Mapping.__init__ / forward compute them (mapping.py:12-50, 66-72, 102-103, 127-130)
+  SemMapCfg g{};
+  g.h = cfg->frame_height, g.w = cfg->frame_width;
+  g.channels = 4 + cfg->num_sem_categories;
+  g.nf = 1 + cfg->num_sem_categories;
+  g.ego_channels = 2 + cfg->num_sem_categories;
+  g.vr = cfg->vision_range;
+  const int res = cfg->map_resolution;
+  const int max_h = static_cast<int>(360.0 / res), min_h = static_cast<int>(-40.0 / res);
+  g.nz = max_h - min_h;
+  const double agent_height = static_cast<double>(cfg->camera_height) * 100.0;
+  g.min_z = static_cast<int>(25.0 / res - min_h);
+  g.max_z = static_cast<int>((agent_height + 1) / res - min_h);
+  g.map_cells = (cfg->map_size_cm / cfg->global_downscaling) / res;
+  if (cfg->num_sem_categories <= 16) {
+    g.special_f[0] = 1 + 5, g.special_f[1] = 1 + 2, g.special_f[2] = -1;
+  } else {
+    g.special_f[0] = 1 + 3, g.special_f[1] = 1 + 9, g.special_f[2] = 1 + 14;
+  }
+  g.xc = static_cast<float>((g.w - 1.0) / 2.0);
+  g.zc = static_cast<float>((g.h - 1.0) / 2.0);
+  g.f = static_cast<float>((g.w / 2.0) / std::tan(static_cast<double>(cfg->hfov) / 2.0 * 3.14159265358979323846 / 180.0));
+  g.agent_height = static_cast<float>(agent_height);
+  g.shift_x = static_cast<float>(g.vr * res / 2);
+  g.res = static_cast<float>(res);
+  g.half_vr = static_cast<float>(g.vr / 2);
+  g.vr_f = static_cast<float>(g.vr);
+  g.z_mid = static_cast<float>(std::floor((max_h + min_h) / 2.0));
+  g.nz_f = static_cast<float>(g.nz);
+  g.map_thr = cfg->map_pred_threshold, g.exp_thr = cfg->exp_pred_threshold, g.cat_thr = cfg->cat_pred_threshold;
+  PN_REQUIRE(g.map_cells >= g.vr && g.map_cells % 2 == 0, "pn_semmap_build: local map smaller than the vision range");
+  auto sm = std::make_unique<SemMap>();
+  sm->init(g, num_envs);
+  PN_CUDA_CHECK(cudaDeviceSynchronize());
+  c->semmap = std::move(sm);
+  PN_API_END
+}
+
+int pn_semmap_forward(pn_ctx* ctx, const float* obs_dev, const float* pose_delta_dev, const float* maps_last_dev,
+                      const int64_t* maps_last_strides, float* poses_inout_dev, float* fp_map_out_dev,
+                      float* map_out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->semmap, "pn_semmap_forward: call pn_semmap_build first");
+  PN_REQUIRE(obs_dev && pose_delta_dev && maps_last_dev && poses_inout_dev && map_out_dev, "pn_semmap_forward: null buffer");
+  PN_REQUIRE(maps_last_dev != map_out_dev, "pn_semmap_forward: map_out must not alias maps_last");
+  const SemMapCfg& g = c->semmap->c;
+  const long long plane = static_cast<long long>(g.map_cells) * g.map_cells;
+  long long se = plane * g.channels, sp = plane, sr = g.map_cells;
+  if (maps_last_strides) se = maps_last_strides[0], sp = maps_last_strides[1], sr = maps_last_strides[2];
+  c->semmap->forward(obs_dev, pose_delta_dev, maps_last_dev, se, sp, sr, poses_inout_dev, fp_map_out_dev, map_out_dev,
+                     static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
+int pn_semmap_read_ego(pn_ctx* ctx, float* ego_out_dev, int* stair_flags_out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->semmap, "pn_semmap_read_ego: not built");
+  SemMap& m = *c->semmap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ego_out_dev)
+    PN_CUDA_CHECK(cudaMemcpyAsync(ego_out_dev, m.ego, static_cast<size_t>(m.E) * m.c.ego_channels * m.c.vr * m.c.vr * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (stair_flags_out_dev)
+    PN_CUDA_CHECK(cudaMemcpyAsync(stair_flags_out_dev, m.stair_flag, static_cast<size_t>(m.E) * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  PN_API_END
+}
+
+int pn_semmap_num_launches(pn_ctx* ctx) {
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !c->semmap) return -1;
+  return SemMap::kLaunches;
 }
 
 int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char* names_out, int names_bytes) {

@@ -62,11 +62,72 @@ int pn_prednet_num_launches(pn_ctx* ctx);
  * [B,2048,H/8,W/8], 1 = low-resolution logits [B,num_classes,H/8,W/8]. */
 int pn_prednet_read_tap(pn_ctx* ctx, int which, float* out_dev, void* stream);
 
-/* Per-launch device time of one forward pass (CUDA events around every recorded launch, eager mode,
- * averaged over `iters` passes after one warm-up).  ms_out[max_ops] receives milliseconds per op,
+/* Algorithmic FLOPs (2*MAC over conv/FC, unpadded) of one forward pass of the built network. */
+int pn_prednet_flops(pn_ctx* ctx, double* flops_out);
+
+/* Per-launch device time of one forward pass of a built network (CUDA events around every recorded launch,
+ * eager mode, averaged over `iters` passes after one warm-up; run one regular forward first so that the
+ * per-call buffers are set).  ms_out[max_ops] receives milliseconds per op, flops_out[max_ops] (may be NULL) the
+ * algorithmic FLOPs of each op (0 for non-GEMM ops; mask-head ops are counted at full capacity),
  * names_out a '\n'-separated list of op names.  Measurement aid for bench.py / profiles/. */
-int pn_prednet_num_ops(pn_ctx* ctx);
-int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char* names_out, int names_bytes);
+enum pn_net { PN_NET_PREDNET = 0, PN_NET_MASKRCNN = 1 };
+int pn_net_num_ops(pn_ctx* ctx, int which);
+int pn_net_profile(pn_ctx* ctx, int which, int iters, float* ms_out, double* flops_out, int max_ops, char* names_out,
+                   int names_bytes);
+
+/* ---- Stage A: Mask-RCNN R101-FPN RGB -> per-category mask stack.
+ * Replaces SemanticPredMaskRCNN.get_prediction, nav/agent/utils/segmentation.py:41-62 (call site
+ * nav/agent/agent_helper.py:220-225), i.e. detectron2's DefaultPredictor + the per-instance accumulation loop.
+ * The configuration mirrors the keys of nav/agent/utils/COCO-InstSeg/mask_rcnn_R_101_cat9.yaml that shape
+ * inference (NULL = the reference's values). */
+typedef struct pn_maskrcnn_cfg {
+  int min_size_test;        /* 800   INPUT.MIN_SIZE_TEST            yaml:30  */
+  int max_size_test;        /* 1333  INPUT.MAX_SIZE_TEST            yaml:28  */
+  int rpn_pre_nms_topk;     /* 1000  RPN.PRE_NMS_TOPK_TEST          yaml:251 */
+  int rpn_post_nms_topk;    /* 1000  RPN.POST_NMS_TOPK_TEST         yaml:249 */
+  float rpn_nms_thresh;     /* 0.7   RPN.NMS_THRESH                 yaml:247 */
+  int num_classes;          /* 9     ROI_HEADS.NUM_CLASSES          yaml:193 */
+  float box_nms_thresh;     /* 0.5   ROI_HEADS.NMS_THRESH_TEST      yaml:192 */
+  int detections_per_image; /* 100   TEST.DETECTIONS_PER_IMAGE      yaml:312 */
+  float mask_threshold;     /* 0.5   paste_masks_in_image threshold          */
+} pn_maskrcnn_cfg;
+
+/* B frames of H x W per forward (reference: 1 x 480 x 640). */
+int pn_maskrcnn_build(pn_ctx* ctx, int B, int H, int W, int precision, const pn_maskrcnn_cfg* cfg);
+/* rgb [B,H,W,3] uint8 RGB (the flip to BGR of segmentation.py:44 happens inside), goal_cat [B] int32 or NULL,
+ * score_thresh = ROI_HEADS.SCORE_THRESH_TEST (segmentation.py:33 sets it to args.sem_pred_prob_thr),
+ * sem_pred_prob_thr / goal_thr = the gates of segmentation.py:54-58,
+ * sem_out [B,H,W,num_classes+1] fp32: per-category sum of instance masks (last channel always 0). */
+int pn_maskrcnn_forward(pn_ctx* ctx, const uint8_t* rgb_dev, const int* goal_cat_dev, float score_thresh,
+                        float sem_pred_prob_thr, float goal_thr, float* sem_out_dev, void* stream);
+int pn_maskrcnn_forward_host(pn_ctx* ctx, const uint8_t* rgb_host, const int* goal_cat_host, float score_thresh,
+                             float sem_pred_prob_thr, float goal_thr, float* sem_out_host);
+int pn_maskrcnn_num_launches(pn_ctx* ctx);
+/* Network input geometry: resized_hw = ResizeShortestEdge output, padded_hw = padded to a multiple of 32. */
+int pn_maskrcnn_input_size(pn_ctx* ctx, int* resized_hw, int* padded_hw);
+/* Parity aids.  Stages, in order: preprocess, backbone, fpn, rpn_head, rpn_proposals, box_head, detections,
+ * mask_head, paste ("end" = past the last).  pn_maskrcnn_set_call stores the per-call pointers / thresholds,
+ * pn_maskrcnn_run_stages runs [first_stage, end_stage) eagerly, pn_maskrcnn_tap copies a named intermediate out
+ * (write = 0) or overwrites it (write = 1): NHWC activations ("input", "res2".."res5", "p2".."p6", "box_pooled",
+ * "mask_pooled") travel as fp32 NCHW with `channels` channels; raw buffers ("resized_u8", "rpn_head.p2".."p6",
+ * "prop_boxes", "prop_scores", "prop_img", "prop_count", "box_out", "det_boxes", "det_scores", "det_classes",
+ * "det_count", "mask_logits") as stored. */
+int pn_maskrcnn_set_call(pn_ctx* ctx, const uint8_t* rgb_dev, const int* goal_cat_dev, float score_thresh,
+                         float sem_pred_prob_thr, float goal_thr, float* sem_out_dev, void* stream);
+int pn_maskrcnn_run_stages(pn_ctx* ctx, const char* first_stage, const char* end_stage, void* stream);
+int pn_maskrcnn_tap(pn_ctx* ctx, const char* name, int write, int channels, void* buf_dev, int64_t buf_bytes, void* stream);
+/* Host-only: the fixed-point coefficient tables of Pillow's bilinear resize (what DefaultPredictor's
+ * ResizeShortestEdge applies to the uint8 frame).  bounds_out [out_size][2] = (first input index, tap count),
+ * coeffs_out [out_size][*ksize_out] 22-bit fixed point; *ksize_out: in = row width of coeffs_out, out = taps. */
+int pn_pil_bilinear_coeffs(int in_size, int out_size, int* bounds_out, int* coeffs_out, int* ksize_out);
+
+/* ---- Glue between stages A and B: Agent_Helper._preprocess_obs / _preprocess_depth
+ * (nav/agent/agent_helper.py:175-217).  depth [E,H,W] fp32 as the simulator emits it (0 = invalid, 1 = max range),
+ * rgb [E,H,W,3] uint8 (may be NULL: channels 0-2 are unused by the mapper), sem [E,H,W,num_sem] fp32 (stage A output)
+ * -> obs [E, 4+num_sem, frame_height, frame_width] (channel 3 = depth in cm, [ds/2::ds] subsampling). */
+int pn_make_obs(pn_ctx* ctx, const float* depth_dev, const uint8_t* rgb_dev, const float* sem_dev, int E, int H, int W,
+                int frame_height, int frame_width, int num_sem, float min_depth, float max_depth, float* obs_out_dev,
+                void* stream);
 
 /* ---- Stage B: Semantic_Mapping ("Sem_Map_Module"), batched over environments.
  * Replaces Semantic_Mapping.forward, nav/agent/mapping.py:52-179 (call sites nav/agent/agent_state.py:114-115,

@@ -32,8 +32,25 @@ PROTOTYPES = {
     "pn_prednet_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_prednet_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "pn_prednet_read_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
-    "pn_prednet_num_ops": (ctypes.c_int, [ctypes.c_void_p]),
-    "pn_prednet_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    "pn_prednet_flops": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_net_num_ops": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "pn_net_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_int]),
+    "pn_maskrcnn_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "pn_maskrcnn_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float,
+                                           ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_maskrcnn_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float,
+                                                ctypes.c_float, ctypes.c_void_p]),
+    "pn_maskrcnn_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_maskrcnn_input_size": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_maskrcnn_set_call": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float,
+                                            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_maskrcnn_run_stages": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p]),
+    "pn_maskrcnn_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_void_p]),
+    "pn_pil_bilinear_coeffs": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_make_obs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 +
+                    [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "pn_semmap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
     "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),
@@ -51,6 +68,30 @@ class SemMapCfg(ctypes.Structure):
                 ("du_scale", ctypes.c_int), ("num_sem_categories", ctypes.c_int), ("hfov", ctypes.c_float),
                 ("camera_height", ctypes.c_float), ("cat_pred_threshold", ctypes.c_float),
                 ("exp_pred_threshold", ctypes.c_float), ("map_pred_threshold", ctypes.c_float)]
+
+
+class MaskRcnnCfg(ctypes.Structure):
+    """struct pn_maskrcnn_cfg"""
+    _fields_ = [("min_size_test", ctypes.c_int), ("max_size_test", ctypes.c_int), ("rpn_pre_nms_topk", ctypes.c_int),
+                ("rpn_post_nms_topk", ctypes.c_int), ("rpn_nms_thresh", ctypes.c_float), ("num_classes", ctypes.c_int),
+                ("box_nms_thresh", ctypes.c_float), ("detections_per_image", ctypes.c_int), ("mask_threshold", ctypes.c_float)]
+
+
+PN_NET_PREDNET = 0
+PN_NET_MASKRCNN = 1
+
+
+def net_profile(ctx, which, iters=5):
+    """[(op name, milliseconds, algorithmic FLOPs)] per recorded launch of a built network."""
+    lib = ctx.lib
+    n = int(lib.pn_net_num_ops(ctx.handle, which))
+    if n < 0:
+        raise RuntimeError("peanut_b200: network not built")
+    ms = (ctypes.c_float * n)()
+    fl = (ctypes.c_double * n)()
+    names = ctypes.create_string_buffer(96 * n)
+    check(lib.pn_net_profile(ctx.handle, which, iters, ms, fl, n, names, len(names)))
+    return list(zip(names.value.decode().strip().split("\n"), [float(v) for v in ms], [float(v) for v in fl]))
 
 
 _lib = None

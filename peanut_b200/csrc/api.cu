@@ -7,6 +7,7 @@
 
 #include "../../include/peanut_b200.h"
 #include "engine.h"
+#include "maskrcnn.h"
 #include "prednet.h"
 #include "semmap.h"
 #include "vec.cuh"
@@ -19,6 +20,7 @@ struct Ctx {
   WeightStore weights;
   std::unique_ptr<PredNet> prednet;
   std::unique_ptr<SemMap> semmap;
+  std::unique_ptr<MaskRcnn> maskrcnn;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
 };
 
@@ -52,6 +54,36 @@ void nhwc_to_nchw(const Tensor& t, int C, float* out, cudaStream_t s) {
     nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(t.ptr), t.ld, out, t.B, C, HW);
   else
     nhwc_to_nchw_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(t.ptr), t.ld, out, t.B, C, HW);
+}
+
+// NCHW fp32 -> NHWC (dt) first C channels of an existing tensor (tap injection).
+template <typename T>
+__global__ void nchw_to_nhwc_direct_kernel(const float* in, T* out, long long ldo, int B, int C, int HW, int round_tf32) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const long long t = idx / C;
+  const int hw = static_cast<int>(t % HW);
+  const int b = static_cast<int>(t / HW);
+  float v = in[(static_cast<long long>(b) * C + c) * HW + hw];
+  if (round_tf32) {
+    uint32_t q;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v));
+    v = __uint_as_float(q);
+  }
+  out[(static_cast<long long>(b) * HW + hw) * ldo + c] = from_float<T>(v);
+}
+
+void nchw_to_nhwc_direct(const float* in, const Tensor& t, int C, cudaStream_t s) {
+  const int HW = t.H * t.W;
+  const long long total = static_cast<long long>(t.B) * C * HW;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  if (t.dt == kBF16)
+    nchw_to_nhwc_direct_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(in, static_cast<__nv_bfloat16*>(t.ptr), t.ld, t.B, C, HW, 0);
+  else
+    nchw_to_nhwc_direct_kernel<float><<<blocks, threads, 0, s>>>(in, static_cast<float*>(t.ptr), t.ld, t.B, C, HW, 1);
 }
 
 void check_device(Ctx* c) {
@@ -109,6 +141,7 @@ int pn_destroy(pn_ctx* ctx) {
     cudaDeviceSynchronize();
     c->prednet.reset();
     c->semmap.reset();
+    c->maskrcnn.reset();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
   }
@@ -183,6 +216,14 @@ int pn_prednet_forward_host(pn_ctx* ctx, const float* map_host, int apply_sigmoi
   n.net.run(c->stream);
   PN_CUDA_CHECK(cudaMemcpyAsync(out_host, n.stage_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PN_API_END
+}
+
+int pn_prednet_flops(pn_ctx* ctx, double* flops_out) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  PN_REQUIRE(c && c->prednet && flops_out, "pn_prednet_flops: not built");
+  *flops_out = c->prednet->net.total_flops();
   PN_API_END
 }
 
@@ -291,22 +332,29 @@ int pn_semmap_num_launches(pn_ctx* ctx) {
   return SemMap::kLaunches;
 }
 
-int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char* names_out, int names_bytes) {
+static Net* select_net(Ctx* c, int which) {
+  if (which == PN_NET_PREDNET) return c->prednet ? &c->prednet->net : nullptr;
+  if (which == PN_NET_MASKRCNN) return c->maskrcnn ? &c->maskrcnn->net : nullptr;
+  return nullptr;
+}
+
+int pn_net_num_ops(pn_ctx* ctx, int which) {
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  Net* net = c ? select_net(c, which) : nullptr;
+  return net ? static_cast<int>(net->ops.size()) : -1;
+}
+
+int pn_net_profile(pn_ctx* ctx, int which, int iters, float* ms_out, double* flops_out, int max_ops, char* names_out,
+                   int names_bytes) {
   PN_API_BEGIN
   auto* c = reinterpret_cast<Ctx*>(ctx);
   check_device(c);
-  PN_REQUIRE(c->prednet && ms_out && iters > 0, "pn_prednet_profile: not built");
-  Net& net = c->prednet->net;
+  Net* netp = select_net(c, which);
+  PN_REQUIRE(netp && ms_out && iters > 0, "pn_net_profile: network not built");
+  Net& net = *netp;
   const int n = static_cast<int>(net.ops.size());
-  PN_REQUIRE(max_ops >= n, "pn_prednet_profile: ms_out too small");
-  PredNet& pnn = *c->prednet;
-  const size_t in_bytes = static_cast<size_t>(pnn.B) * pnn.C * pnn.H * pnn.W * sizeof(float);
-  const size_t out_bytes = static_cast<size_t>(pnn.B) * pnn.num_classes * pnn.H * pnn.W * sizeof(float);
-  if (!pnn.stage_in) {
-    pnn.stage_in = static_cast<float*>(net.arena.alloc(in_bytes, true));
-    pnn.stage_out = static_cast<float*>(net.arena.alloc(out_bytes, false));
-  }
-  set_pred_slots_kernel<<<1, 1, 0, c->stream>>>(pnn.slots, pnn.stage_in, pnn.stage_out, 0);
+  PN_REQUIRE(max_ops >= n, "pn_net_profile: ms_out too small");
+  // the per-call slots must already point at valid buffers: run one regular forward before profiling
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) PN_CUDA_CHECK(cudaEventCreate(&e));
   std::vector<double> acc(n, 0.0);
@@ -328,6 +376,7 @@ int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char*
   std::string names;
   for (int i = 0; i < n; ++i) {
     ms_out[i] = static_cast<float>(acc[i] / iters);
+    if (flops_out) flops_out[i] = net.op_flops[i];
     names += net.op_names[i];
     names += '\n';
   }
@@ -336,14 +385,177 @@ int pn_prednet_profile(pn_ctx* ctx, int iters, float* ms_out, int max_ops, char*
     memcpy(names_out, names.data(), k);
     names_out[k] = 0;
   }
-  return n > 0 ? 0 : 0;
   PN_API_END
 }
 
-int pn_prednet_num_ops(pn_ctx* ctx) {
+// ------------------------------------------------------------------------------------------------- stage A
+int pn_maskrcnn_build(pn_ctx* ctx, int B, int H, int W, int precision, const pn_maskrcnn_cfg* cfg) {
+  PN_API_BEGIN
   auto* c = reinterpret_cast<Ctx*>(ctx);
-  if (!c || !c->prednet) return -1;
-  return static_cast<int>(c->prednet->net.ops.size());
+  check_device(c);
+  PN_REQUIRE(B > 0 && H > 0 && W > 0, "pn_maskrcnn_build: bad shape");
+  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32, "pn_maskrcnn_build: bad precision");
+  MrcnnCfg g;
+  g.B = B, g.H = H, g.W = W;
+  if (cfg) {
+    g.min_size = cfg->min_size_test, g.max_size = cfg->max_size_test;
+    g.pre_nms_topk = cfg->rpn_pre_nms_topk, g.post_nms_topk = cfg->rpn_post_nms_topk, g.rpn_nms = cfg->rpn_nms_thresh;
+    g.num_classes = cfg->num_classes, g.box_nms = cfg->box_nms_thresh, g.detections = cfg->detections_per_image;
+    g.mask_thresh = cfg->mask_threshold;
+  }
+  c->maskrcnn.reset();
+  auto net = std::make_unique<MaskRcnn>();
+  net->net.num_sms = c->num_sms;
+  build_maskrcnn(*net, c->weights, g, precision == PN_BF16 ? kBF16 : kF32);
+  PN_CUDA_CHECK(cudaDeviceSynchronize());
+  c->maskrcnn = std::move(net);
+  PN_API_END
+}
+
+static void set_mrcnn_slots(MaskRcnn& m, const uint8_t* rgb, const int* goal, float score_thresh, float sem_thr, float goal_thr,
+                            float* sem_out, cudaStream_t s) {
+  MrcnnSlots h{rgb, sem_out, goal, score_thresh, sem_thr, goal_thr};
+  // small pageable copy: the driver stages it at call time, so `h` may die when we return
+  PN_CUDA_CHECK(cudaMemcpyAsync(m.slots, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+}
+
+int pn_maskrcnn_forward(pn_ctx* ctx, const uint8_t* rgb_dev, const int* goal_cat_dev, float score_thresh,
+                        float sem_pred_prob_thr, float goal_thr, float* sem_out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->maskrcnn, "pn_maskrcnn_forward: call pn_maskrcnn_build first");
+  PN_REQUIRE(rgb_dev && sem_out_dev, "pn_maskrcnn_forward: null buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  set_mrcnn_slots(*c->maskrcnn, rgb_dev, goal_cat_dev, score_thresh, sem_pred_prob_thr, goal_thr, sem_out_dev, s);
+  c->maskrcnn->net.run(s);
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
+}
+
+int pn_maskrcnn_forward_host(pn_ctx* ctx, const uint8_t* rgb_host, const int* goal_cat_host, float score_thresh,
+                             float sem_pred_prob_thr, float goal_thr, float* sem_out_host) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->maskrcnn, "pn_maskrcnn_forward_host: call pn_maskrcnn_build first");
+  MaskRcnn& m = *c->maskrcnn;
+  const size_t in_bytes = static_cast<size_t>(m.cfg.B) * m.cfg.H * m.cfg.W * 3;
+  const size_t out_bytes = static_cast<size_t>(m.cfg.B) * m.cfg.H * m.cfg.W * (m.cfg.num_classes + 1) * sizeof(float);
+  if (!m.stage_rgb) {
+    m.stage_rgb = static_cast<uint8_t*>(m.net.arena.alloc(in_bytes + m.cfg.B * sizeof(int), false));
+    m.stage_sem = static_cast<float*>(m.net.arena.alloc(out_bytes, false));
+  }
+  int* goal_dev = nullptr;
+  PN_CUDA_CHECK(cudaMemcpyAsync(m.stage_rgb, rgb_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (goal_cat_host) {
+    goal_dev = reinterpret_cast<int*>(m.stage_rgb + ((in_bytes + 3) & ~size_t(3)));
+    PN_CUDA_CHECK(cudaMemcpyAsync(goal_dev, goal_cat_host, m.cfg.B * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  set_mrcnn_slots(m, m.stage_rgb, goal_dev, score_thresh, sem_pred_prob_thr, goal_thr, m.stage_sem, c->stream);
+  m.net.run(c->stream);
+  PN_CUDA_CHECK(cudaMemcpyAsync(sem_out_host, m.stage_sem, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PN_API_END
+}
+
+int pn_maskrcnn_num_launches(pn_ctx* ctx) {
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !c->maskrcnn) return -1;
+  return static_cast<int>(c->maskrcnn->net.launches_per_forward);
+}
+
+int pn_maskrcnn_input_size(pn_ctx* ctx, int* resized_hw, int* padded_hw) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  PN_REQUIRE(c && c->maskrcnn, "pn_maskrcnn_input_size: not built");
+  if (resized_hw) resized_hw[0] = c->maskrcnn->Hn, resized_hw[1] = c->maskrcnn->Wn;
+  if (padded_hw) padded_hw[0] = c->maskrcnn->Hp, padded_hw[1] = c->maskrcnn->Wp;
+  PN_API_END
+}
+
+int pn_maskrcnn_run_stages(pn_ctx* ctx, const char* first_stage, const char* end_stage, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->maskrcnn && first_stage && end_stage, "pn_maskrcnn_run_stages: not built");
+  Net& net = c->maskrcnn->net;
+  const int a = net.stage_begin(first_stage), b = net.stage_begin(end_stage);
+  PN_REQUIRE(a <= b, "pn_maskrcnn_run_stages: stages out of order");
+  net.run_range(a, b, static_cast<cudaStream_t>(stream));
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
+}
+
+int pn_maskrcnn_set_call(pn_ctx* ctx, const uint8_t* rgb_dev, const int* goal_cat_dev, float score_thresh,
+                         float sem_pred_prob_thr, float goal_thr, float* sem_out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->maskrcnn, "pn_maskrcnn_set_call: not built");
+  set_mrcnn_slots(*c->maskrcnn, rgb_dev, goal_cat_dev, score_thresh, sem_pred_prob_thr, goal_thr, sem_out_dev,
+                  static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
+int pn_maskrcnn_tap(pn_ctx* ctx, const char* name, int write, int channels, void* buf_dev, int64_t buf_bytes, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(c->maskrcnn && name && buf_dev, "pn_maskrcnn_tap: not built");
+  MaskRcnn& m = *c->maskrcnn;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const std::string key(name);
+  if (key == "resized_u8") {
+    const size_t bytes = static_cast<size_t>(m.cfg.B) * m.Hn * m.Wn * 3;
+    PN_REQUIRE(!write && static_cast<size_t>(buf_bytes) >= bytes, "pn_maskrcnn_tap: resized_u8 is read-only / buffer too small");
+    PN_CUDA_CHECK(cudaMemcpyAsync(buf_dev, m.resized_u8, bytes, cudaMemcpyDeviceToDevice, s));
+  } else if (m.net.taps.count(key)) {
+    const Tensor& t = m.net.taps[key];
+    PN_REQUIRE(channels > 0 && channels <= t.C, "pn_maskrcnn_tap: bad channel count");
+    const size_t bytes = static_cast<size_t>(t.pixels()) * channels * sizeof(float);
+    PN_REQUIRE(static_cast<size_t>(buf_bytes) >= bytes, "pn_maskrcnn_tap: buffer too small");
+    if (write) nchw_to_nhwc_direct(static_cast<const float*>(buf_dev), t, channels, s);
+    else nhwc_to_nchw(t, channels, static_cast<float*>(buf_dev), s);
+  } else if (m.net.raw_taps.count(key)) {
+    auto& rt = m.net.raw_taps[key];
+    const size_t bytes = std::min(rt.second, static_cast<size_t>(buf_bytes));
+    if (write) PN_CUDA_CHECK(cudaMemcpyAsync(rt.first, buf_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    else PN_CUDA_CHECK(cudaMemcpyAsync(buf_dev, rt.first, bytes, cudaMemcpyDeviceToDevice, s));
+  } else {
+    PN_REQUIRE(false, "pn_maskrcnn_tap: unknown tap '" + key + "'");
+  }
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
+}
+
+int pn_pil_bilinear_coeffs(int in_size, int out_size, int* bounds_out, int* coeffs_out, int* ksize_out) {
+  PN_API_BEGIN
+  PN_REQUIRE(in_size > 0 && out_size > 0 && bounds_out && coeffs_out && ksize_out, "pn_pil_bilinear_coeffs: bad arguments");
+  std::vector<int> b, k;
+  int ks = 0;
+  pil_bilinear_coeffs(in_size, out_size, b, k, ks);
+  PN_REQUIRE(ks <= *ksize_out, "pn_pil_bilinear_coeffs: coefficient buffer too narrow (pass its width in *ksize_out)");
+  std::copy(b.begin(), b.end(), bounds_out);
+  for (int i = 0; i < out_size; ++i)
+    for (int j = 0; j < ks; ++j) coeffs_out[i * (*ksize_out) + j] = k[i * ks + j];
+  *ksize_out = ks;
+  PN_API_END
+}
+
+int pn_make_obs(pn_ctx* ctx, const float* depth_dev, const uint8_t* rgb_dev, const float* sem_dev, int E, int H, int W,
+                int frame_height, int frame_width, int num_sem, float min_depth, float max_depth, float* obs_out_dev,
+                void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(depth_dev && sem_dev && obs_out_dev && E > 0, "pn_make_obs: null buffer");
+  PN_REQUIRE(frame_width > 0 && W % frame_width == 0 && H / (W / frame_width) == frame_height, "pn_make_obs: frame size must divide the camera size");
+  const int ds = W / frame_width;
+  launch_make_obs(depth_dev, rgb_dev, sem_dev, E, H, W, ds, frame_height, frame_width, num_sem, min_depth, max_depth, obs_out_dev,
+                  static_cast<cudaStream_t>(stream));
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
 }
 
 int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,

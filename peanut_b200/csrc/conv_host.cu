@@ -237,6 +237,8 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.relu = sp.relu ? 1 : 0;
   p.out_fp32 = (out.dt == kF32) ? 1 : 0;
   p.round_tf32 = (dt == kF32 && !sp.out_fp32) ? 1 : 0;
+  p.m_limit = sp.m_limit;
+  p.m_limit_rows = sp.m_limit_rows;
 
   // Epilogue mode: smem-staged TMA stores (+ TMA residual prefetch) whenever a stored row chunk is at
   // least 64 bytes and the output has the activation dtype; otherwise direct per-thread stores.
@@ -286,12 +288,13 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   const int grid = static_cast<int>(std::min<long long>(tiles, net.num_sms));
 
+  const double flops = 2.0 * static_cast<double>(M) * sp.Cout * sp.Cin * taps;
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
       launch_conv_bn<__nv_bfloat16>(bn, tm, p, grid, smem, s);
     else
       launch_conv_bn<float>(bn, tm, p, grid, smem, s);
-  });
+  }, flops);
   net.launches_per_forward += 1;
 }
 

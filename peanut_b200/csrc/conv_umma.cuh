@@ -50,6 +50,8 @@ struct ConvParams {
   int cb;        // epilogue chunk row bytes (= swizzle span of the out/residual maps): 32, 64 or 128
   int res_bufs;  // residual staging depth (0 when no residual)
   int out_bufs;  // output staging depth: 2, or 1 for K-heavy layers where a deeper A/B pipeline matters more
+  const int* m_limit;  // optional device-side count of valid row groups (ROIs); rows = *m_limit * m_limit_rows
+  int m_limit_rows;
 };
 
 constexpr int kBlockM = 128;
@@ -138,7 +140,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  int m_tiles_live = p.m_tiles;
+  if (p.m_limit != nullptr) {
+    const long long rows = static_cast<long long>(__ldg(p.m_limit)) * p.m_limit_rows;
+    const int t = static_cast<int>((rows + kBlockM - 1) / kBlockM);
+    m_tiles_live = t < p.m_tiles ? t : p.m_tiles;
+  }
+  const int num_tiles = m_tiles_live * p.n_tiles;
   const int taps = p.R * p.S;
   const int kblocks = taps * p.kb_per_tap;
   const int cols_per_chunk = p.epi_tma ? p.cb / static_cast<int>(sizeof(T)) : 32;

@@ -1,0 +1,727 @@
+// Mask-RCNN control flow on the device (no host synchronisation anywhere): FPN top-down add, RPN top-k +
+// box decoding + per-level NMS + cross-level merge, ROIAlign, box-head post-processing (softmax, score
+// filter, per-class NMS, top-100), and the mask paste + per-category accumulation of
+// SemanticPredMaskRCNN.get_prediction (nav/agent/utils/segmentation.py:47-62).
+//
+// Semantics follow detectron2 0.6 as configured by nav/agent/utils/COCO-InstSeg/mask_rcnn_R_101_cat9.yaml
+// (restated in oracle/maskrcnn.py, which cites the yaml lines).  This translation unit is compiled with
+// -fmad=false so that box decoding, IoU, ROIAlign and paste arithmetic round after every multiply and add
+// like the reference's separate torch ops.
+#include <cfloat>
+#include <cmath>
+
+#include "maskrcnn.h"
+#include "vec.cuh"
+
+namespace pn {
+
+namespace {
+
+constexpr float kScaleClamp = 4.135166556742356f;  // log(1000 / 16)
+
+__device__ __forceinline__ uint32_t fkey(float f) {  // order-preserving float -> uint32
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Box2BoxTransform.apply_deltas for one box.
+__device__ __forceinline__ void decode_box(const float a[4], float dx, float dy, float dw, float dh, float wx, float wy,
+                                           float ww, float wh, float out[4]) {
+  const float width = a[2] - a[0], height = a[3] - a[1];
+  const float cx = a[0] + 0.5f * width, cy = a[1] + 0.5f * height;
+  dx = dx / wx, dy = dy / wy, dw = dw / ww, dh = dh / wh;
+  dw = fminf(dw, kScaleClamp), dh = fminf(dh, kScaleClamp);
+  const float pcx = dx * width + cx, pcy = dy * height + cy;
+  const float pw = expf(dw) * width, ph = expf(dh) * height;
+  out[0] = pcx - 0.5f * pw, out[1] = pcy - 0.5f * ph, out[2] = pcx + 0.5f * pw, out[3] = pcy + 0.5f * ph;
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float area_a = (a.z - a.x) * (a.w - a.y), area_b = (b.z - b.x) * (b.w - b.y);
+  const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f), h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
+  const float inter = w * h;
+  return inter / (area_a + area_b - inter) > thr;
+}
+
+// Block-wide exclusive scan of one flag per thread (blockDim.x == 1024); returns rank, writes total.
+__device__ __forceinline__ int block_scan_flag(bool flag, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int in_warp = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_sums[wid] = __popc(bal);
+  __syncthreads();
+  if (wid == 0) {
+    int v = warp_sums[lane], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    warp_sums[lane] = x - v;  // exclusive
+    if (lane == 31) warp_sums[32] = x;
+  }
+  __syncthreads();
+  const int r = warp_sums[wid] + in_warp;
+  total = warp_sums[32];
+  __syncthreads();
+  return r;
+}
+
+// In-place bitonic sort, descending, of n (power of two) 64-bit keys in shared memory.
+__device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], b = keys[l];
+          const bool desc = (i & k) == 0;
+          if ((a < b) == desc) keys[i] = b, keys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FPN: lat += nearest-neighbour x2 upsampling of prev (F.interpolate(scale_factor=2, mode="nearest")).
+template <typename T>
+__global__ void k_upsample2x_add(const T* __restrict__ prev, long long ldp, int h, int w, T* __restrict__ lat, long long ldl,
+                                 int B, int H, int W, int C8, int round_tf32) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * C8;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % C8);
+  long long t = idx / C8;
+  const int x = static_cast<int>(t % W);
+  t /= W;
+  const int y = static_cast<int>(t % H);
+  const int b = static_cast<int>(t / H);
+  const int ys = min(y >> 1, h - 1), xs = min(x >> 1, w - 1);
+  float a[8], p[8];
+  T* lp = lat + ((static_cast<long long>(b) * H + y) * W + x) * ldl + cg * 8;
+  load8(lp, a);
+  load8(prev + ((static_cast<long long>(b) * h + ys) * w + xs) * ldp + cg * 8, p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = a[j] + p[j];
+    if (round_tf32) {
+      uint32_t q;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(a[j]));
+      a[j] = __uint_as_float(q);
+    }
+  }
+  store8(lp, a);
+}
+
+template <typename T>
+__global__ void k_subsample2(const T* __restrict__ in, long long ldi, int H, int W, T* __restrict__ out, long long ldo, int B,
+                             int Ho, int Wo, int C8) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % C8);
+  long long t = idx / C8;
+  const int x = static_cast<int>(t % Wo);
+  t /= Wo;
+  const int y = static_cast<int>(t % Ho);
+  const int b = static_cast<int>(t / Ho);
+  float v[8];
+  load8(in + ((static_cast<long long>(b) * H + 2 * y) * W + 2 * x) * ldi + cg * 8, v);
+  store8(out + ((static_cast<long long>(b) * Ho + y) * Wo + x) * ldo + cg * 8, v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RPN per (level, image): exact top-k by 4-pass radix select (ties -> lower index), sort, decode, clip,
+// drop empty / non-finite, greedy NMS via a shared-memory suppression bit matrix.  block = 1024 threads.
+struct RpnSmem {
+  unsigned long long keys[kRpnCap];
+  float4 box[kRpnCap];
+  float score[kRpnCap];
+  uint32_t hist[256];
+  int warp_sums[33];
+  uint32_t prefix, rank, cnt_eq;
+  int ncand, nvalid, nkept;
+  int kept[kRpnCap];
+};
+
+__global__ void __launch_bounds__(1024, 1) k_rpn_select_nms(RpnMeta meta, float* __restrict__ lvl_boxes,
+                                                            float* __restrict__ lvl_scores, int* __restrict__ lvl_count) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  RpnSmem& S = *reinterpret_cast<RpnSmem*>(smem_raw);
+  uint32_t* mask = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(RpnSmem) + 15) & ~size_t(15)));  // [kRpnCap][32]
+  const int L = blockIdx.x, b = blockIdx.y;
+  const RpnLevel& lv = meta.lv[L];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int npix = lv.H * lv.W;
+  const int n = npix * kAnchors;
+  const int k = min(n, meta.pre_topk);
+  const float* head = lv.head + static_cast<size_t>(b) * npix * kRpnHeadC;
+  auto logit_at = [&](int i) { return head[static_cast<size_t>(i / kAnchors) * kRpnHeadC + (i % kAnchors)]; };
+
+  // ---- radix select of the k-th largest key
+  if (tid == 0) S.prefix = 0, S.rank = static_cast<uint32_t>(k - 1), S.ncand = 0;
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) S.hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = S.prefix;
+    const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int base = 0; base < n; base += 1024) {
+      const int i = base + tid;
+      uint32_t key = 0;
+      bool part = false;
+      if (i < n) {
+        key = fkey(logit_at(i));
+        part = (key & pmask) == prefix;
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, part);
+      if (part) {
+        const uint32_t bin = (key >> shift) & 255u;
+        const unsigned peers = __match_any_sync(act, bin);
+        if (lane == __ffs(peers) - 1) atomicAdd(&S.hist[bin], static_cast<uint32_t>(__popc(peers)));
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // bins in descending order: lane owns bins [255 - 8*lane - 7, 255 - 8*lane]
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c[j] = S.hist[255 - (lane * 8 + j)], sum += c[j];
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      uint32_t before = incl - sum;  // elements in bins above this lane's
+      const uint32_t r = S.rank;
+      if (r >= before && r < incl) {
+        uint32_t rr = r - before;
+        int j = 0;
+        while (rr >= c[j]) rr -= c[j], ++j;
+        S.rank = rr;
+        S.prefix = prefix | (static_cast<uint32_t>(255 - (lane * 8 + j)) << shift);
+        S.cnt_eq = c[j];
+      }
+    }
+    __syncthreads();
+  }
+  const uint32_t T = S.prefix;
+  const int need_eq = static_cast<int>(S.rank) + 1, cnt_eq = static_cast<int>(S.cnt_eq);
+  __syncthreads();
+  // ---- collect the k winners as (key, ~index) composites
+  int eq_seen = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const uint32_t key = i < n ? fkey(logit_at(i)) : 0u;
+    const bool gt = i < n && key > T;
+    bool eq = i < n && key == T;
+    if (need_eq < cnt_eq) {  // block-uniform: ties must be taken in index order
+      int tot;
+      const int r = block_scan_flag(eq, S.warp_sums, tot);
+      eq = eq && (eq_seen + r < need_eq);
+      eq_seen += tot;
+    }
+    if (gt || eq) {
+      const int slot = atomicAdd(&S.ncand, 1);
+      S.keys[slot] = (static_cast<unsigned long long>(key) << 32) | (0xffffffffu - static_cast<uint32_t>(i));
+    }
+  }
+  __syncthreads();
+  for (int i = S.ncand + tid; i < kRpnCap; i += 1024) S.keys[i] = 0ull;
+  __syncthreads();
+  bitonic_desc(S.keys, kRpnCap);
+
+  // ---- decode, clip, validity
+  bool valid = false;
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sc = 0.f;
+  if (tid < k) {
+    const unsigned long long kk = S.keys[tid];
+    const int i = static_cast<int>(0xffffffffu - static_cast<uint32_t>(kk & 0xffffffffull));
+    const int pix = i / kAnchors, a = i - pix * kAnchors;
+    const int y = pix / lv.W, x = pix - y * lv.W;
+    const float sx = static_cast<float>(x * lv.stride), sy = static_cast<float>(y * lv.stride);
+    const float anchor[4] = {sx + lv.base[a][0], sy + lv.base[a][1], sx + lv.base[a][2], sy + lv.base[a][3]};
+    const float* d = head + static_cast<size_t>(pix) * kRpnHeadC + kAnchors + a * 4;
+    float o[4];
+    decode_box(anchor, d[0], d[1], d[2], d[3], 1.f, 1.f, 1.f, 1.f, o);
+    sc = fkey_inv(static_cast<uint32_t>(kk >> 32));
+    valid = isfinite(o[0]) && isfinite(o[1]) && isfinite(o[2]) && isfinite(o[3]) && isfinite(sc);
+    bx = make_float4(clampf(o[0], 0.f, meta.img_w), clampf(o[1], 0.f, meta.img_h), clampf(o[2], 0.f, meta.img_w),
+                     clampf(o[3], 0.f, meta.img_h));
+    valid = valid && (bx.z - bx.x > 0.f) && (bx.w - bx.y > 0.f);
+  }
+  int m;
+  const int pos = block_scan_flag(valid, S.warp_sums, m);
+  if (valid) S.box[pos] = bx, S.score[pos] = sc;
+  __syncthreads();
+
+  // ---- suppression bit matrix: bit jj of mask[i][j] <=> box 32j+jj (later in score order) overlaps box i
+  const int nw = (m + 31) >> 5;
+  for (int p = tid; p < m * nw; p += 1024) {
+    const int i = p / nw, j = p - i * nw;
+    uint32_t bits = 0;
+    if (j >= (i >> 5)) {
+      const float4 a = S.box[i];
+      const int c0 = j << 5;
+      const int cend = min(32, m - c0);
+      for (int jj = 0; jj < cend; ++jj) {
+        const int c = c0 + jj;
+        if (c > i && iou_gt(a, S.box[c], meta.nms_thr)) bits |= 1u << jj;
+      }
+    }
+    mask[i * 32 + j] = bits;
+  }
+  __syncthreads();
+  // ---- greedy sweep by one warp: lane l owns word l of the `removed` bit vector
+  if (tid < 32) {
+    uint32_t removed = 0;
+    int nkept = 0;
+    for (int c = 0; c < nw; ++c) {
+      uint32_t rem = __shfl_sync(0xffffffffu, removed, c);
+      const int i_lane = (c << 5) + lane;
+      const uint32_t intra = i_lane < m ? mask[i_lane * 32 + c] : 0u;
+      uint32_t kept_bits = 0;
+      const int cend = min(32, m - (c << 5));
+      for (int j = 0; j < cend; ++j) {
+        const uint32_t row = __shfl_sync(0xffffffffu, intra, j);
+        if (!((rem >> j) & 1u)) {
+          kept_bits |= 1u << j;
+          rem |= row;
+        }
+      }
+      // fold the rows of the kept boxes into every word
+      uint32_t kb = kept_bits;
+      while (kb) {
+        const int j = __ffs(kb) - 1;
+        kb &= kb - 1;
+        if (lane < nw) removed |= mask[((c << 5) + j) * 32 + lane];
+      }
+      if ((kept_bits >> lane) & 1u) S.kept[nkept + __popc(kept_bits & ((1u << lane) - 1u))] = i_lane;
+      nkept += __popc(kept_bits);
+    }
+    if (lane == 0) S.nkept = nkept;
+  }
+  __syncthreads();
+  const int nk = S.nkept;
+  float* ob = lvl_boxes + (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap * 4;
+  float* os = lvl_scores + (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap;
+  for (int i = tid; i < nk; i += 1024) {
+    const int src = S.kept[i];
+    const float4 v = S.box[src];
+    ob[i * 4] = v.x, ob[i * 4 + 1] = v.y, ob[i * 4 + 2] = v.z, ob[i * 4 + 3] = v.w;
+    os[i] = S.score[src];
+  }
+  if (tid == 0) lvl_count[b * kRpnLevels + L] = nk;
+}
+
+// Cross-level merge: keep = batched_nms(...)[:post_topk] orders all survivors by score (stable: level, then
+// rank).  Every level list is already sorted, so the global rank is a sum of binary searches.
+__global__ void __launch_bounds__(1024) k_rpn_merge(int post_topk, const float* __restrict__ lvl_boxes,
+                                                    const float* __restrict__ lvl_scores, const int* __restrict__ lvl_count,
+                                                    float* __restrict__ prop_boxes, float* __restrict__ prop_scores,
+                                                    int* __restrict__ prop_img, int* __restrict__ prop_count) {
+  const int b = blockIdx.x;
+  __shared__ int cnt[kRpnLevels];
+  if (threadIdx.x < kRpnLevels) cnt[threadIdx.x] = lvl_count[b * kRpnLevels + threadIdx.x];
+  __syncthreads();
+  int total = 0;
+  for (int l = 0; l < kRpnLevels; ++l) total += cnt[l];
+  const int nout = min(total, post_topk);
+  for (int e = threadIdx.x; e < kRpnLevels * kRpnCap; e += blockDim.x) {
+    const int L = e / kRpnCap, r = e - L * kRpnCap;
+    if (r >= cnt[L]) continue;
+    const float s = lvl_scores[(static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap + r];
+    int rank = r;
+    for (int l2 = 0; l2 < kRpnLevels; ++l2) {
+      if (l2 == L) continue;
+      const float* sc = lvl_scores + (static_cast<size_t>(b) * kRpnLevels + l2) * kRpnCap;
+      // number of entries of level l2 ordered before (s, L): score > s, or == s when l2 < L
+      int lo = 0, hi = cnt[l2];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float v = sc[mid];
+        const bool before = (l2 < L) ? (v >= s) : (v > s);
+        if (before) lo = mid + 1;
+        else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < post_topk) {
+      const float* src = lvl_boxes + ((static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap + r) * 4;
+      float* dst = prop_boxes + (static_cast<size_t>(b) * post_topk + rank) * 4;
+      dst[0] = src[0], dst[1] = src[1], dst[2] = src[2], dst[3] = src[3];
+      prop_scores[static_cast<size_t>(b) * post_topk + rank] = s;
+      prop_img[static_cast<size_t>(b) * post_topk + rank] = b;
+    }
+  }
+  for (int r = nout + threadIdx.x; r < post_topk; r += blockDim.x) prop_img[static_cast<size_t>(b) * post_topk + r] = -1;
+  if (threadIdx.x == 0) prop_count[b] = nout;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ROIAlignV2 (aligned=True, sampling_ratio=0) with detectron2's level assignment.  One CTA per ROI, one warp
+// per output bin (round robin), one lane per 8 channels (256 channels).
+template <typename T>
+__global__ void __launch_bounds__(256) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
+                                                   int S, T* __restrict__ out, long long ldo) {
+  const int r = blockIdx.x;
+  const int b = img[r];
+  if (b < 0) return;
+  const float x1 = boxes[r * 4], y1 = boxes[r * 4 + 1], x2 = boxes[r * 4 + 2], y2 = boxes[r * 4 + 3];
+  const float size = sqrtf((x2 - x1) * (y2 - y1));
+  float lvf = floorf(4.f + log2f(size / 224.f + 1e-8f));
+  lvf = fminf(fmaxf(lvf, 2.f), 5.f);
+  const PyramidLevel lv = pyr.lv[static_cast<int>(lvf) - 2];
+  const T* feat = static_cast<const T*>(lv.ptr) + static_cast<size_t>(b) * lv.H * lv.W * lv.ld;
+  const float rsw = x1 * lv.scale - 0.5f, rsh = y1 * lv.scale - 0.5f;
+  const float rew = x2 * lv.scale - 0.5f, reh = y2 * lv.scale - 0.5f;
+  const float rw = rew - rsw, rh = reh - rsh;
+  const float bin_h = rh / static_cast<float>(S), bin_w = rw / static_cast<float>(S);
+  const int gh = static_cast<int>(ceilf(rh / static_cast<float>(S)));
+  const int gw = static_cast<int>(ceilf(rw / static_cast<float>(S)));
+  const float count = static_cast<float>(max(gh * gw, 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float fh = static_cast<float>(lv.H), fw = static_cast<float>(lv.W);
+  for (int bin = warp; bin < S * S; bin += 8) {
+    const int ph = bin / S, pw = bin - ph * S;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int iy = 0; iy < gh; ++iy) {
+      float y = rsh + static_cast<float>(ph) * bin_h + (static_cast<float>(iy) + .5f) * bin_h / static_cast<float>(gh);
+      for (int ix = 0; ix < gw; ++ix) {
+        float x = rsw + static_cast<float>(pw) * bin_w + (static_cast<float>(ix) + .5f) * bin_w / static_cast<float>(gw);
+        float yy = y;
+        if (yy < -1.0f || yy > fh || x < -1.0f || x > fw) continue;
+        if (yy <= 0.f) yy = 0.f;
+        if (x <= 0.f) x = 0.f;
+        int yl = static_cast<int>(yy), xl = static_cast<int>(x), yh, xh;
+        if (yl >= lv.H - 1) yh = yl = lv.H - 1, yy = static_cast<float>(yl);
+        else yh = yl + 1;
+        if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
+        else xh = xl + 1;
+        const float ly = yy - static_cast<float>(yl), lx = x - static_cast<float>(xl);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+        float v1[8], v2[8], v3[8], v4[8];
+        load8(feat + (static_cast<size_t>(yl) * lv.W + xl) * lv.ld + lane * 8, v1);
+        load8(feat + (static_cast<size_t>(yl) * lv.W + xh) * lv.ld + lane * 8, v2);
+        load8(feat + (static_cast<size_t>(yh) * lv.W + xl) * lv.ld + lane * 8, v3);
+        load8(feat + (static_cast<size_t>(yh) * lv.W + xh) * lv.ld + lane * 8, v4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (((w1 * v1[j] + w2 * v2[j]) + w3 * v3[j]) + w4 * v4[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = acc[j] / count;
+      if (sizeof(T) == 4) {
+        uint32_t q;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(acc[j]));
+        acc[j] = __uint_as_float(q);
+      }
+    }
+    store8(out + (static_cast<size_t>(r) * S * S + bin) * ldo + lane * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fast_rcnn_inference_single_image: softmax, score filter, class-wise decode + clip, per-class NMS in score
+// order, first `detections` survivors.  One CTA per image; dynamic smem = candidate keys.
+__global__ void __launch_bounds__(1024, 1) k_detections(const MrcnnSlots* __restrict__ slots, int K, int post_topk, int max_det,
+                                                        float nms_thr, float img_h, float img_w,
+                                                        const float* __restrict__ box_out, int ldb,
+                                                        const float* __restrict__ prop_boxes, const int* __restrict__ prop_count,
+                                                        float* __restrict__ det_boxes, float* __restrict__ det_scores,
+                                                        int* __restrict__ det_classes, int* __restrict__ det_count, int cap) {
+  extern __shared__ __align__(16) unsigned long long dkeys[];  // [cap]
+  __shared__ int s_n;
+  __shared__ float4 kbox[128];
+  __shared__ int kcls[128];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float thr = slots->score_thresh;
+  const int R = prop_count[b];
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int r = tid; r < R; r += blockDim.x) {
+    const float* row = box_out + (static_cast<size_t>(b) * post_topk + r) * ldb;
+    float mx = row[0];
+    for (int c = 1; c <= K; ++c) mx = fmaxf(mx, row[c]);
+    float e[16], sum = 0.f;
+    for (int c = 0; c <= K; ++c) e[c] = expf(row[c] - mx), sum += e[c];
+    bool finite_row = isfinite(sum);
+    for (int c = 0; c < K && finite_row; ++c) {
+      const float p = e[c] / sum;
+      if (p > thr) {
+        const int slot = atomicAdd(&s_n, 1);
+        if (slot < cap)
+          dkeys[slot] = (static_cast<unsigned long long>(fkey(p)) << 32) | (0xffffffffu - static_cast<uint32_t>(r * K + c));
+      }
+    }
+  }
+  __syncthreads();
+  const int n = min(s_n, cap);
+  int npow = 1;
+  while (npow < n) npow <<= 1;
+  for (int i = n + tid; i < npow; i += blockDim.x) dkeys[i] = 0ull;
+  __syncthreads();
+  if (npow > 1) bitonic_desc(dkeys, npow);
+  // greedy per-class NMS by warp 0, candidates in score order
+  if (tid < 32) {
+    const int lane = tid;
+    int nk = 0;
+    for (int c = 0; c < n && nk < max_det; ++c) {
+      const unsigned long long kk = dkeys[c];
+      const int flat = static_cast<int>(0xffffffffu - static_cast<uint32_t>(kk & 0xffffffffull));
+      const int r = flat / K, cls = flat - r * K;
+      const float* row = box_out + (static_cast<size_t>(b) * post_topk + r) * ldb;
+      const float* pb = prop_boxes + (static_cast<size_t>(b) * post_topk + r) * 4;
+      const float anchor[4] = {pb[0], pb[1], pb[2], pb[3]};
+      const float* d = row + (K + 1) + cls * 4;
+      float o[4];
+      decode_box(anchor, d[0], d[1], d[2], d[3], 10.f, 10.f, 5.f, 5.f, o);
+      const bool finite_box = isfinite(o[0]) && isfinite(o[1]) && isfinite(o[2]) && isfinite(o[3]);
+      const float4 bx = make_float4(clampf(o[0], 0.f, img_w), clampf(o[1], 0.f, img_h), clampf(o[2], 0.f, img_w),
+                                    clampf(o[3], 0.f, img_h));
+      bool hit = false;
+      for (int j = lane; j < nk; j += 32)
+        if (kcls[j] == cls && iou_gt(kbox[j], bx, nms_thr)) hit = true;
+      // (valid_mask of the reference drops whole rows with a non-finite box of ANY class; a non-finite
+      // decoded box here can only come from non-finite deltas, which also poison that row's other classes)
+      if (!__any_sync(0xffffffffu, hit) && finite_box) {
+        if (lane == 0) {
+          kbox[nk] = bx, kcls[nk] = cls;
+          float* ob = det_boxes + (static_cast<size_t>(b) * max_det + nk) * 4;
+          ob[0] = bx.x, ob[1] = bx.y, ob[2] = bx.z, ob[3] = bx.w;
+          det_scores[static_cast<size_t>(b) * max_det + nk] = fkey_inv(static_cast<uint32_t>(kk >> 32));
+          det_classes[static_cast<size_t>(b) * max_det + nk] = cls;
+        }
+        ++nk;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) det_count[b] = nk;
+  }
+}
+
+// Batch-compacted ROI list for the mask head + per-image offsets.  One block.
+__global__ void k_compact_dets(int B, int max_det, const float* __restrict__ det_boxes, const int* __restrict__ det_classes,
+                               const int* __restrict__ det_count, float* __restrict__ mroi_boxes, int* __restrict__ mroi_img,
+                               int* __restrict__ mroi_cls, int* __restrict__ mroi_total) {
+  __shared__ int start[1025];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) start[b] = acc, acc += det_count[b];
+    start[B] = acc;
+    mroi_total[0] = acc;
+    for (int b = 0; b <= B; ++b) mroi_total[1 + b] = start[b];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < B * max_det; e += blockDim.x) {
+    const int b = e / max_det, i = e - b * max_det;
+    if (i < det_count[b]) {
+      const int dst = start[b] + i;
+      for (int q = 0; q < 4; ++q) mroi_boxes[dst * 4 + q] = det_boxes[e * 4 + q];
+      mroi_img[dst] = b;
+      mroi_cls[dst] = det_classes[e];
+    }
+    if (e >= start[B]) mroi_img[e] = -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// detector_postprocess + paste_masks_in_image + the accumulation loop of segmentation.py:47-62, one thread
+// per output pixel: for every detection of the frame that passes the score gates, the 28x28 mask
+// probabilities are bilinearly sampled (grid_sample, align_corners=False, zero padding) at the pixel centre
+// mapped into the detection's box; >= threshold adds 1 to the class channel.
+__global__ void __launch_bounds__(256) k_paste_accumulate(const MrcnnSlots* __restrict__ slots, int H, int W, int K, int max_det,
+                                                          float sx, float sy, float mask_thr, const float* __restrict__ det_scores,
+                                                          const int* __restrict__ det_count, const int* __restrict__ mroi_total,
+                                                          const float* __restrict__ mroi_boxes, const int* __restrict__ mroi_cls,
+                                                          const float* __restrict__ mask_logits) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  __shared__ float4 sbox[128];
+  __shared__ int scls[128];
+  __shared__ int sroi[128];
+  __shared__ int s_n;
+  const int n_det = det_count[b];
+  const int start = mroi_total[1 + b];
+  if (threadIdx.x == 0) {
+    // gates + rescale to the camera frame + clip + drop empty (serial: n_det <= 100, negligible)
+    const float sem_thr = slots->sem_thr, goal_thr = slots->goal_thr;
+    const int goal = slots->goal_cat ? slots->goal_cat[b] : -1;
+    int n = 0;
+    for (int i = 0; i < n_det; ++i) {
+      const int cls = mroi_cls[start + i];
+      const float score = det_scores[static_cast<size_t>(b) * max_det + i];
+      const float* pb = mroi_boxes + static_cast<size_t>(start + i) * 4;
+      float4 bx = make_float4(pb[0] * sx, pb[1] * sy, pb[2] * sx, pb[3] * sy);
+      bx.x = clampf(bx.x, 0.f, static_cast<float>(W)), bx.z = clampf(bx.z, 0.f, static_cast<float>(W));
+      bx.y = clampf(bx.y, 0.f, static_cast<float>(H)), bx.w = clampf(bx.w, 0.f, static_cast<float>(H));
+      if (!((bx.z - bx.x) > 0.f && (bx.w - bx.y) > 0.f)) continue;
+      if (cls < 0 || cls >= K) continue;
+      if (score < sem_thr) continue;
+      if (cls == goal && score < goal_thr) continue;
+      sbox[n] = bx, scls[n] = cls, sroi[n] = start + i;
+      ++n;
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  if (x >= W) return;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  const int n = s_n;
+  const float px = static_cast<float>(x) + 0.5f, py = static_cast<float>(y) + 0.5f;
+  for (int i = 0; i < n; ++i) {
+    const float4 bx = sbox[i];
+    const float gx = (px - bx.x) / (bx.z - bx.x) * 2.f - 1.f;
+    const float gy = (py - bx.y) / (bx.w - bx.y) * 2.f - 1.f;
+    const float ix = (gx + 1.f) * 14.f - 0.5f, iy = (gy + 1.f) * 14.f - 0.5f;  // ((g + 1) * 28 - 1) / 2
+    if (!(ix > -1.f && ix < 28.f && iy > -1.f && iy < 28.f)) continue;
+    const float xw = floorf(ix), yn = floorf(iy);
+    const float w = ix - xw, e = 1.f - w, nn = iy - yn, s = 1.f - nn;
+    const float wnw = s * e, wne = s * w, wsw = nn * e, wse = nn * w;
+    const int X0 = static_cast<int>(xw), Y0 = static_cast<int>(yn);
+    const int cls = scls[i];
+    const float* ml = mask_logits + static_cast<size_t>(sroi[i]) * (14 * 14 * 4) * 16 + cls;
+    auto prob = [&](int Y, int X) -> float {
+      if (X < 0 || X >= 28 || Y < 0 || Y >= 28) return 0.f;
+      const int row = (((Y >> 1) * 14) + (X >> 1)) * 4 + ((Y & 1) << 1) + (X & 1);
+      return 1.f / (1.f + expf(-ml[static_cast<size_t>(row) * 16]));
+    };
+    const float v = ((prob(Y0, X0) * wnw + prob(Y0, X0 + 1) * wne) + prob(Y0 + 1, X0) * wsw) + prob(Y0 + 1, X0 + 1) * wse;
+    if (v >= mask_thr) acc[cls] += 1.f;
+  }
+  float* o = slots->sem_out + ((static_cast<size_t>(b) * H + y) * W + x) * (K + 1);
+  for (int c = 0; c <= K; ++c) o[c] = c < K ? acc[c] : 0.f;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+void add_upsample2x_add(Net& net, const Tensor& prev, const Tensor& lat) {
+  PN_REQUIRE(prev.C == lat.C && prev.C % 8 == 0 && prev.dt == lat.dt && prev.B == lat.B, "upsample_add: shape");
+  PN_REQUIRE(lat.H == 2 * prev.H && lat.W == 2 * prev.W, "upsample_add: the fine level must be exactly 2x the coarse one");
+  const int C8 = lat.C / 8;
+  const long long total = lat.pixels() * C8;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  Tensor p = prev, l = lat;
+  net.add("fpn_upsample_add", [=](cudaStream_t s) {
+    if (l.dt == kBF16)
+      k_upsample2x_add<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(p.ptr), p.ld, p.H, p.W, static_cast<__nv_bfloat16*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 0);
+    else
+      k_upsample2x_add<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(p.ptr), p.ld, p.H, p.W, static_cast<float*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 1);
+  });
+  net.launches_per_forward += 1;
+}
+
+void add_subsample2(Net& net, const Tensor& in, const Tensor& out) {
+  PN_REQUIRE(out.H == (in.H - 1) / 2 + 1 && out.W == (in.W - 1) / 2 + 1 && in.C == out.C && in.C % 8 == 0, "subsample2: shape");
+  const int C8 = in.C / 8;
+  const long long total = out.pixels() * C8;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  Tensor i = in, o = out;
+  net.add("fpn_p6_subsample", [=](cudaStream_t s) {
+    if (i.dt == kBF16)
+      k_subsample2<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(i.ptr), i.ld, i.H, i.W, static_cast<__nv_bfloat16*>(o.ptr), o.ld, o.B, o.H, o.W, C8);
+    else
+      k_subsample2<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(i.ptr), i.ld, i.H, i.W, static_cast<float*>(o.ptr), o.ld, o.B, o.H, o.W, C8);
+  });
+  net.launches_per_forward += 1;
+}
+
+void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
+  PN_REQUIRE(meta.pre_topk <= kRpnCap && meta.post_topk >= 1, "rpn: pre_nms_topk exceeds the per-level capacity");
+  const size_t smem = ((sizeof(RpnSmem) + 15) & ~size_t(15)) + static_cast<size_t>(kRpnCap) * 32 * sizeof(uint32_t);
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_rpn_select_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int B = m.cfg.B;
+  float* lb = m.lvl_boxes;
+  float* ls = m.lvl_scores;
+  int* lc = m.lvl_count;
+  net.add("rpn_select_nms", [=](cudaStream_t s) { k_rpn_select_nms<<<dim3(kRpnLevels, B), 1024, smem, s>>>(meta, lb, ls, lc); });
+  float* pb = m.prop_boxes;
+  float* ps = m.prop_scores;
+  int* pi = m.prop_img;
+  int* pc = m.prop_count;
+  const int post = meta.post_topk;
+  net.add("rpn_merge", [=](cudaStream_t s) { k_rpn_merge<<<B, 1024, 0, s>>>(post, lb, ls, lc, pb, ps, pi, pc); });
+  net.launches_per_forward += 2;
+}
+
+void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr, DType dt, const float* boxes, const int* img,
+                   int nrois, int S, const Tensor& out) {
+  PN_REQUIRE(out.C == 256 && out.dt == dt, "roi_align: 256-channel pyramid expected");
+  Tensor o = out;
+  net.add(name, [=](cudaStream_t s) {
+    if (dt == kBF16)
+      k_roi_align<__nv_bfloat16><<<nrois, 256, 0, s>>>(pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
+    else
+      k_roi_align<float><<<nrois, 256, 0, s>>>(pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
+  });
+  net.launches_per_forward += 1;
+}
+
+void add_detections(Net& net, MaskRcnn& m) {
+  const MrcnnCfg c = m.cfg;
+  PN_REQUIRE(c.num_classes + 1 <= 16 && c.detections <= 128, "detections: at most 15 classes / 128 detections");
+  int cap = 1;
+  while (cap < c.post_nms_topk * c.num_classes) cap <<= 1;
+  const size_t smem = static_cast<size_t>(cap) * sizeof(unsigned long long);
+  PN_REQUIRE(smem <= 200 * 1024, "detections: candidate list does not fit shared memory");
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_detections, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const MrcnnSlots* slots = m.slots;
+  const float img_h = static_cast<float>(m.Hn), img_w = static_cast<float>(m.Wn);
+  const float* box_out = m.box_out;
+  const float* pb = m.prop_boxes;
+  const int* pc = m.prop_count;
+  float* db = m.det_boxes;
+  float* ds = m.det_scores;
+  int* dc = m.det_classes;
+  int* dn = m.det_count;
+  net.add("detections", [=](cudaStream_t s) {
+    k_detections<<<c.B, 1024, smem, s>>>(slots, c.num_classes, c.post_nms_topk, c.detections, c.box_nms, img_h, img_w, box_out,
+                                         64, pb, pc, db, ds, dc, dn, cap);
+  });
+  float* mb = m.mroi_boxes;
+  int* mi = m.mroi_img;
+  int* mc = m.mroi_cls;
+  int* mt = m.mroi_total;
+  PN_REQUIRE(c.B <= 1024, "detections: batch too large");
+  net.add("compact_dets", [=](cudaStream_t s) { k_compact_dets<<<1, 256, 0, s>>>(c.B, c.detections, db, dc, dn, mb, mi, mc, mt); });
+  net.launches_per_forward += 2;
+}
+
+void add_paste_accumulate(Net& net, MaskRcnn& m) {
+  const MrcnnCfg c = m.cfg;
+  const MrcnnSlots* slots = m.slots;
+  // boxes[:, 0::2] *= scale_x with the python float cast to fp32 (detector_postprocess)
+  const float sx = static_cast<float>(static_cast<double>(c.W) / m.Wn), sy = static_cast<float>(static_cast<double>(c.H) / m.Hn);
+  const float* ds = m.det_scores;
+  const int* dn = m.det_count;
+  const int* mt = m.mroi_total;
+  const float* mb = m.mroi_boxes;
+  const int* mc = m.mroi_cls;
+  const float* ml = m.mask_logits;
+  net.add("paste_accumulate", [=](cudaStream_t s) {
+    k_paste_accumulate<<<dim3((c.W + 255) / 256, c.H, c.B), 256, 0, s>>>(slots, c.H, c.W, c.num_classes, c.detections, sx, sy,
+                                                                       c.mask_thresh, ds, dn, mt, mb, mc, ml);
+  });
+  net.launches_per_forward += 1;
+}
+
+}  // namespace pn

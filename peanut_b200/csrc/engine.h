@@ -103,6 +103,10 @@ struct Net {
   Arena arena;
   std::vector<std::function<void(cudaStream_t)>> ops;
   std::vector<std::string> op_names;
+  std::vector<double> op_flops;                 // algorithmic FLOPs (2*MAC, unpadded) of each op; 0 for non-GEMM ops
+  std::vector<std::pair<std::string, int>> stages;  // (name, index of the stage's first op), in order
+  std::map<std::string, Tensor> taps;           // named NHWC activations (parity taps)
+  std::map<std::string, std::pair<void*, size_t>> raw_taps;  // named raw device buffers (pointer, bytes)
   DType dt = kBF16;
   int num_sms = 148;
   long long launches_per_forward = 0;
@@ -111,12 +115,29 @@ struct Net {
   int warm_runs = 0;
   bool use_graph = true;
 
-  void add(const std::string& name, std::function<void(cudaStream_t)> f) {
+  void add(const std::string& name, std::function<void(cudaStream_t)> f, double flops = 0.0) {
     ops.push_back(std::move(f));
     op_names.push_back(name);
+    op_flops.push_back(flops);
+  }
+  void stage(const std::string& name) { stages.emplace_back(name, static_cast<int>(ops.size())); }
+  // Index of the first op of `name`; ops.size() for the pseudo-stage "end".
+  int stage_begin(const std::string& name) const {
+    if (name == "end") return static_cast<int>(ops.size());
+    for (auto& st : stages)
+      if (st.first == name) return st.second;
+    throw std::runtime_error("peanut_b200: unknown stage '" + name + "'");
+  }
+  double total_flops() const {
+    double t = 0;
+    for (double f : op_flops) t += f;
+    return t;
   }
   void run_eager(cudaStream_t s) {
     for (auto& f : ops) f(s);
+  }
+  void run_range(int first, int last, cudaStream_t s) {
+    for (int i = first; i < last; ++i) ops[i](s);
   }
   void run(cudaStream_t s);
   ~Net();
@@ -136,6 +157,10 @@ struct ConvSpec {
   bool out_fp32 = false;
   int force_bn = 0;  // test hook: force the N tile
   bool force_direct_epilogue = false;  // test hook: bypass the TMA-staged epilogue
+  // Dynamic row limit: when set, only the first (*m_limit) * m_limit_rows GEMM rows are computed (device-side
+  // count of valid ROIs x rows per ROI); tiles beyond are skipped by every warp role.
+  const int* m_limit = nullptr;
+  int m_limit_rows = 1;
 };
 // weight: fp32 [Cout][Cin][R][S]; scale / bias: fp32 [Cout] (folded BN or plain bias with scale 1).
 // `out` must already describe the destination view (B, Ho, Wo, C >= Cout rounded to 8, ld).

@@ -1,0 +1,203 @@
+// Frame pre-processing kernels either side of the networks (all HBM/latency-bound, integer or elementwise):
+//
+//   * Mask-RCNN input: detectron2's DefaultPredictor resizes the uint8 BGR frame with PIL bilinear
+//     (ResizeShortestEdge, nav/agent/utils/COCO-InstSeg/mask_rcnn_R_101_cat9.yaml:28,30), then
+//     GeneralizedRCNN.preprocess_image subtracts PIXEL_MEAN (yaml:82-89) and zero-pads to a multiple of 32.
+//     PIL resizes uint8 images in 22-bit fixed point, horizontal pass first, with a uint8 round trip
+//     between the passes; the kernel below replays exactly that integer arithmetic (bit-exact), so the
+//     coefficient tables are computed on the host in double precision like Pillow's precompute_coeffs.
+//   * Mapper observation ("N2" glue): Agent_Helper._preprocess_obs / _preprocess_depth
+//     (nav/agent/agent_helper.py:175-217) - per-column invalid-depth fill, too-far masking, cm conversion,
+//     [2::4, 2::4] subsampling of depth / semantic masks / rgb and channel concatenation.
+#include <cmath>
+
+#include "maskrcnn.h"
+#include "vec.cuh"
+
+namespace pn {
+
+// ---------------------------------------------------------------------------------------------------
+// Pillow Resample.c: precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (support 1).
+void pil_bilinear_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk, int& ksize) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 1.0 * filterscale;
+  ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  bounds.assign(static_cast<size_t>(out_size) * 2, 0);
+  kk.assign(static_cast<size_t>(out_size) * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    for (int x = xmax; x < ksize; ++x) k[x] = 0.0;
+    for (int x = 0; x < ksize; ++x) {
+      const double v = k[x] * static_cast<double>(1 << 22);
+      kk[static_cast<size_t>(xx) * ksize + x] = v < 0 ? static_cast<int>(-0.5 + v) : static_cast<int>(0.5 + v);
+    }
+    bounds[xx * 2] = xmin;
+    bounds[xx * 2 + 1] = xmax;
+  }
+}
+
+namespace {
+
+__device__ __forceinline__ int clip8(int v) {
+  v >>= 22;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// One thread per output pixel (all 3 channels).  hb/hk, vb/vk: bounds + coefficients of the two passes.
+template <typename T>
+__global__ void k_resize_normalize(const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, int Hp, int Wp,
+                                   int Cpad, const int* __restrict__ hb, const int* __restrict__ hk, int hks,
+                                   const int* __restrict__ vb, const int* __restrict__ vk, int vks, float3 mean_bgr,
+                                   float3 std_bgr, T* __restrict__ out, uint8_t* __restrict__ resized_u8) {
+  const uint8_t* rgb = *rgb_slot;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Hp * Wp;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % Wp);
+  const long long t = idx / Wp;
+  const int y = static_cast<int>(t % Hp);
+  const int b = static_cast<int>(t / Hp);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (y < Hn && x < Wn) {
+    const int x0 = hb[2 * x], xn = hb[2 * x + 1];
+    const int y0 = vb[2 * y], yn = vb[2 * y + 1];
+    int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int j = 0; j < yn; ++j) {
+      const uint8_t* row = rgb + (static_cast<size_t>(b) * H + (y0 + j)) * W * 3;
+      int h[3] = {1 << 21, 1 << 21, 1 << 21};
+      for (int i = 0; i < xn; ++i) {
+        const int k = hk[x * hks + i];
+        const uint8_t* px = row + (x0 + i) * 3;
+        h[0] += px[0] * k, h[1] += px[1] * k, h[2] += px[2] * k;
+      }
+      const int kv = vk[y * vks + j];
+      acc[0] += clip8(h[0]) * kv, acc[1] += clip8(h[1]) * kv, acc[2] += clip8(h[2]) * kv;
+    }
+    const int r = clip8(acc[0]), g = clip8(acc[1]), bl = clip8(acc[2]);
+    if (resized_u8 != nullptr) {
+      uint8_t* o = resized_u8 + ((static_cast<size_t>(b) * Hn + y) * Wn + x) * 3;
+      o[0] = static_cast<uint8_t>(bl), o[1] = static_cast<uint8_t>(g), o[2] = static_cast<uint8_t>(r);
+    }
+    v[0] = (static_cast<float>(bl) - mean_bgr.x) / std_bgr.x;
+    v[1] = (static_cast<float>(g) - mean_bgr.y) / std_bgr.y;
+    v[2] = (static_cast<float>(r) - mean_bgr.z) / std_bgr.z;
+    if (sizeof(T) == 4) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        uint32_t q;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v[j]));
+        v[j] = __uint_as_float(q);
+      }
+    }
+  }
+  T* o = out + idx * Cpad;
+  store8(o, v);
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 8; c0 < Cpad; c0 += 8) store8(o + c0, z);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Mapper observation.  One warp per (env, subsampled column); lanes stride over the 480 rows of the full
+// column for the invalid-pixel statistics, then over the 120 subsampled rows for the output.
+__global__ void k_make_obs(const float* __restrict__ depth_all, const uint8_t* __restrict__ rgb_all,
+                           const float* __restrict__ sem_all, int E, int H, int W, int ds, int h, int w, int nsem, float min_d,
+                           float max_d, float* __restrict__ obs) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= E * w) return;
+  const int e = gw / w, xs = gw - e * w;
+  const int x = ds / 2 + xs * ds;
+  const float* depth = depth_all + static_cast<size_t>(e) * H * W;
+  const uint8_t* rgb = rgb_all ? rgb_all + static_cast<size_t>(e) * H * W * 3 : nullptr;
+  const float* sem = sem_all + static_cast<size_t>(e) * H * W * nsem;
+  // column statistics over ALL rows (agent_helper.py:200-206)
+  int n_invalid = 0;
+  float col_max = -INFINITY;
+  for (int y = lane; y < H; y += 32) {
+    const float d = depth[static_cast<size_t>(y) * W + x];
+    n_invalid += (d == 0.f);
+    col_max = fmaxf(col_max, d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_invalid += __shfl_xor_sync(0xffffffffu, n_invalid, o);
+    col_max = fmaxf(col_max, __shfl_xor_sync(0xffffffffu, col_max, o));
+  }
+  // np.mean(invalid) > 0.9 in float64
+  const bool mostly_invalid = static_cast<double>(n_invalid) / static_cast<double>(H) > 0.9;
+  const int C = 4 + nsem;
+  float* o = obs + static_cast<size_t>(e) * C * h * w;
+  for (int ys = lane; ys < h; ys += 32) {
+    const int y = ds / 2 + ys * ds;
+    float d = depth[static_cast<size_t>(y) * W + x];
+    if (d == 0.f) d = mostly_invalid ? col_max : 100.0f;
+    if (d > 0.99f) d = 0.f;
+    if (d == 0.f) d = 100.0f;
+    d = min_d * 100.0f + d * (max_d - min_d) * 100.0f;
+    const size_t pix = static_cast<size_t>(ys) * w + xs;
+    const size_t src = static_cast<size_t>(y) * W + x;
+    for (int c = 0; c < 3; ++c) o[static_cast<size_t>(c) * h * w + pix] = rgb ? static_cast<float>(rgb[src * 3 + c]) : 0.f;
+    o[static_cast<size_t>(3) * h * w + pix] = d;
+    for (int c = 0; c < nsem; ++c) o[static_cast<size_t>(4 + c) * h * w + pix] = sem[src * nsem + c];
+  }
+}
+
+}  // namespace
+
+void add_resize_normalize(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
+                          uint8_t* resized_u8, const float mean_bgr[3], const float std_bgr[3]) {
+  PN_REQUIRE(out.ld == out.C && out.C % 8 == 0 && out.C >= 8, "resize_normalize: output must be dense, >= 8 channels");
+  std::vector<int> hb, hk, vb, vk;
+  int hks = 0, vks = 0;
+  pil_bilinear_coeffs(W, Wn, hb, hk, hks);
+  pil_bilinear_coeffs(H, Hn, vb, vk, vks);
+  const int* d_hb = net.arena.upload(hb);
+  const int* d_hk = net.arena.upload(hk);
+  const int* d_vb = net.arena.upload(vb);
+  const int* d_vk = net.arena.upload(vk);
+  const float3 mean = make_float3(mean_bgr[0], mean_bgr[1], mean_bgr[2]);
+  const float3 inv = make_float3(std_bgr[0], std_bgr[1], std_bgr[2]);
+  const long long total = out.pixels();
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  Tensor o = out;
+  net.add("resize_normalize", [=](cudaStream_t s) {
+    if (o.dt == kBF16)
+      k_resize_normalize<__nv_bfloat16><<<blocks, threads, 0, s>>>(rgb_slot, B, H, W, Hn, Wn, o.H, o.W, o.C, d_hb, d_hk, hks, d_vb, d_vk, vks, mean, inv, static_cast<__nv_bfloat16*>(o.ptr), resized_u8);
+    else
+      k_resize_normalize<float><<<blocks, threads, 0, s>>>(rgb_slot, B, H, W, Hn, Wn, o.H, o.W, o.C, d_hb, d_hk, hks, d_vb, d_vk, vks, mean, inv, static_cast<float*>(o.ptr), resized_u8);
+  });
+  net.launches_per_forward += 1;
+}
+
+void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, int E, int H, int W, int ds, int h, int w,
+                     int nsem, float min_d, float max_d, float* obs, cudaStream_t s) {
+  const int warps = E * w;
+  const int threads = 128;
+  const int blocks = (warps * 32 + threads - 1) / threads;
+  k_make_obs<<<blocks, threads, 0, s>>>(depth, rgb, sem, E, H, W, ds, h, w, nsem, min_d, max_d, obs);
+}
+
+}  // namespace pn

@@ -1,0 +1,109 @@
+"""One perception step for E independent environments on one GPU: RGB-D frame + partial map -> (per-category masks,
+updated local map + pose, predicted semantic map).
+
+This is the batched composition of the three reference call sites that ``PEANUT_Agent.act`` walks every step
+(SURVEY.md §3.1): ``SemanticPredMaskRCNN.get_prediction`` (nav/agent/agent_helper.py:220-225),
+``Agent_Helper._preprocess_obs`` (agent_helper.py:175-195), ``Semantic_Mapping.forward``
+(nav/agent/agent_state.py:273-274) and ``PEANUT_Prediction_Model.get_prediction`` (agent_state.py:355-361).  The
+reference runs them for one environment with >= 3 host->device and >= 6 device->host synchronising copies per step;
+here everything between the input copy and the result copy stays on the device, on one stream, for E
+environments at once (the environments are independent: no cross-env state).
+"""
+import ctypes
+import types
+
+import torch
+
+from . import _lib
+from .mapping import Semantic_Mapping
+from .prediction import Segmentor, _default_cfg
+from .segmentation import MaskRCNN
+
+
+def default_args(**kw):
+    """The argparse defaults of nav/arguments.py that shape the path (lines 40-81, 104)."""
+    a = dict(env_frame_width=640, env_frame_height=480, frame_width=160, frame_height=120, min_depth=0.5, max_depth=5.0,
+             map_resolution=5, map_size_cm=4800, global_downscaling=2, vision_range=100, hfov=79.0, du_scale=1,
+             cat_pred_threshold=5.0, exp_pred_threshold=1.0, map_pred_threshold=0.1, num_sem_categories=10,
+             camera_height=0.88, sem_pred_prob_thr=0.95, goal_thr=0.985, sem_gpu_id=0)
+    a.update(kw)
+    return types.SimpleNamespace(**a)
+
+
+class PerceptionPipeline:
+    def __init__(self, seg_weights, pred_weights, num_envs=1, device="cuda:0", precision="bf16", map_shape=(24, 240, 240),
+                 num_pred_classes=6, args=None):
+        self.args = args or default_args()
+        a = self.args
+        dev = torch.device(device)
+        self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
+        a.device = self.device
+        self.E = int(num_envs)
+        self.map_shape = tuple(map_shape)
+        self.num_pred_classes = num_pred_classes
+        self.seg = MaskRCNN(seg_weights, device=self.device, precision=precision, batch=self.E, height=a.env_frame_height,
+                            width=a.env_frame_width)
+        self.mapper = Semantic_Mapping(a, num_envs=self.E)
+        self.pred = Segmentor(_default_cfg(map_shape[0], num_pred_classes), pred_weights, self.device, precision=precision)
+        self.pred._ensure_built(self.E, *self.map_shape)
+        nsem = a.num_sem_categories
+        E, H, W = self.E, a.env_frame_height, a.env_frame_width
+        d = self.device
+        self.sem = torch.zeros((E, H, W, nsem), dtype=torch.float32, device=d)
+        self.obs = torch.zeros((E, 4 + nsem, a.frame_height, a.frame_width), dtype=torch.float32, device=d)
+        self.pred_out = torch.zeros((E, num_pred_classes) + self.map_shape[1:], dtype=torch.float32, device=d)
+        # staging for the host entry point
+        self._dev_in = None
+        self._host_out = None
+        if self.seg.n_cats + 1 != nsem:
+            raise ValueError("num_sem_categories must equal the segmentation classes + 1")
+
+    def launches_per_step(self):
+        """Kernel launches one step enqueues (graph nodes of the two networks + mapper + glue)."""
+        return self.seg.num_launches() + 1 + int(self.mapper.ctx.lib.pn_semmap_num_launches(self.mapper.ctx.handle)) + \
+            self.pred.num_launches()
+
+    def step_device(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat=None):
+        """All CUDA tensors: rgb uint8 [E,H,W,3]; depth float32 [E,H,W] (simulator units, 0 = invalid);
+        pose_delta [E,3]; local_map [E,4+S,n,n]; poses [E,3] (updated in place); partial_map [E,C,Hm,Wm].
+        Returns (sem [E,H,W,S], fp_map [E,vr,vr], new_local_map [E,4+S,n,n], poses, pred_map [E,K,Hm,Wm]);
+        no host synchronisation."""
+        a = self.args
+        self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        lib = self.seg.ctx.lib
+        _lib.check(lib.pn_make_obs(self.seg.ctx.handle, depth.data_ptr(), rgb.data_ptr(), self.sem.data_ptr(), self.E,
+                                   a.env_frame_height, a.env_frame_width, a.frame_height, a.frame_width,
+                                   a.num_sem_categories, a.min_depth, a.max_depth, self.obs.data_ptr(),
+                                   ctypes.c_void_p(stream)))
+        fp, new_map, poses = self.mapper.forward_batch(self.obs, pose_delta, local_map, poses)
+        pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
+        return self.sem, fp, new_map, poses, pred
+
+    def step_host(self, rgb_h, depth_h, pose_delta_h, partial_map_h, local_map, poses):
+        """End-to-end step as a caller with HOST observations sees it: pinned host inputs are copied to the device,
+        the step runs, and the step's result (predicted map, pose, egocentric obstacle map) is copied back.
+        The local map and poses are device-resident state, as in the reference (agent_state.py:53-60).
+        Returns (pred_map_host, poses_host, fp_map_host, new_local_map_device)."""
+        d = self.device
+        if self._dev_in is None:
+            self._dev_in = (torch.empty_like(rgb_h, device=d), torch.empty_like(depth_h, device=d),
+                            torch.empty_like(pose_delta_h, device=d), torch.empty_like(partial_map_h, device=d))
+            self._host_out = (torch.empty(self.pred_out.shape, dtype=torch.float32).pin_memory(),
+                              torch.empty((self.E, 3), dtype=torch.float32).pin_memory(),
+                              torch.empty((self.E, self.args.vision_range, self.args.vision_range), dtype=torch.float32).pin_memory())
+        for dst, src in zip(self._dev_in, (rgb_h, depth_h, pose_delta_h, partial_map_h)):
+            dst.copy_(src, non_blocking=True)
+        rgb, depth, delta, pmap = self._dev_in
+        _, fp, new_map, poses, pred = self.step_device(rgb, depth, delta, local_map, poses, pmap)
+        self._host_out[0].copy_(pred, non_blocking=True)
+        self._host_out[1].copy_(poses, non_blocking=True)
+        self._host_out[2].copy_(fp, non_blocking=True)
+        torch.cuda.current_stream(d).synchronize()
+        return self._host_out[0], self._host_out[1], self._host_out[2], new_map
+
+    def h2d_bytes(self, rgb_h, depth_h, pose_delta_h, partial_map_h):
+        return sum(t.numel() * t.element_size() for t in (rgb_h, depth_h, pose_delta_h, partial_map_h))
+
+    def d2h_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self._host_out) if self._host_out else 0

@@ -119,12 +119,14 @@ class Segmentor:
         return out_host
 
     def profile(self, iters=5):
-        """[(op name, milliseconds)] per recorded launch of the currently built network."""
-        n = int(self.ctx.lib.pn_prednet_num_ops(self.ctx.handle))
-        ms = (ctypes.c_float * n)()
-        names = ctypes.create_string_buffer(64 * n)
-        _lib.check(self.ctx.lib.pn_prednet_profile(self.ctx.handle, iters, ms, n, names, len(names)))
-        return list(zip(names.value.decode().strip().split("\n"), [float(v) for v in ms]))
+        """[(op name, milliseconds, FLOPs)] per recorded launch of the currently built network."""
+        return _lib.net_profile(self.ctx, _lib.PN_NET_PREDNET, iters)
+
+    def flops(self):
+        """Algorithmic FLOPs of one forward of the currently built network (2*MAC over conv layers)."""
+        out = ctypes.c_double()
+        _lib.check(self.ctx.lib.pn_prednet_flops(self.ctx.handle, ctypes.byref(out)))
+        return float(out.value)
 
     def read_tap(self, which):
         B, C, H, W = self._built

@@ -1,0 +1,275 @@
+"""Stage A parity on the GPU: CUDA Mask-RCNN (through the C-ABI and the reference-facing shim) against the CPU
+oracle (oracle/maskrcnn.py) on the same seeded weights and frames, stage by stage.
+
+The discrete stages (top-k, NMS, score filter, paste threshold) are checked EXACTLY by feeding them the oracle's
+own inputs through the parity taps; the tensor-core stages are checked within stated floating-point tolerances:
+  * tf32 path vs fp32 oracle: 5e-3 of the tensor's range per stage (10-bit operand mantissas, ~100 layers);
+  * bf16 path vs the bf16-storage emulation of the oracle: 4e-2 of the range.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import maskrcnn as O
+from peanut_b200 import segmentation as S
+
+pytestmark = pytest.mark.gpu
+
+H, W = 240, 320          # small camera frame for the stage tests (the e2e test uses the reference's 480 x 640)
+MIN_SIZE, MAX_SIZE = 400, 667
+THR = 0.3                # SCORE_THRESH_TEST for random weights (0.95 leaves too few detections to test NMS)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return O.synth_weights(0)
+
+
+@pytest.fixture(scope="module")
+def frame():
+    return O.synth_rgb(3, H, W)
+
+
+@pytest.fixture(scope="module")
+def ocfg():
+    return O.Cfg(min_size=MIN_SIZE, max_size=MAX_SIZE, score_thresh=THR)
+
+
+@pytest.fixture(scope="module")
+def otaps(weights, frame, ocfg):
+    taps = {}
+    taps["result"] = O.forward(frame, weights, ocfg, taps=taps)
+    return taps
+
+
+def _engine(weights, precision, batch=1, h=H, w=W, min_size=MIN_SIZE, max_size=MAX_SIZE):
+    return S.MaskRCNN(weights, precision=precision, batch=batch, height=h, width=w,
+                      cfg=S.default_cfg(min_size_test=min_size, max_size_test=max_size))
+
+
+@pytest.fixture(scope="module")
+def eng_tf32(weights, frame):
+    e = _engine(weights, "tf32")
+    e._rgb = torch.from_numpy(frame)[None].cuda()
+    e._out = torch.zeros((1, H, W, 10), device="cuda")
+    e.set_call(e._rgb, e._out, score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR)
+    return e
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+def test_resize_is_pil_exact_and_input_normalised(eng_tf32, frame, ocfg, otaps):
+    e = eng_tf32
+    e.run_stages("preprocess", "backbone")
+    (hn, wn), (hp, wp) = e.input_size()
+    assert (hn, wn) == O.resized_shape(H, W, ocfg) and (hp, wp) == tuple(otaps["input"].shape[2:])
+    from PIL import Image
+    ref = np.asarray(Image.fromarray(np.ascontiguousarray(frame[:, :, ::-1])).resize((wn, hn), Image.BILINEAR))
+    got = e.read_tap("resized_u8", (1, hn, wn, 3), torch.uint8).cpu().numpy()[0]
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} resized pixels differ from PIL"
+    x = e.read_tap("input", (1, 3, hp, wp)).cpu()
+    # stored as tf32 (10-bit mantissa, round to nearest): |err| <= 2^-11 * 128
+    assert (x - otaps["input"]).abs().max().item() <= 0.0626
+    assert (x[:, :, hn:, :] == 0).all() and (x[:, :, :, wn:] == 0).all()
+
+
+def test_backbone_fpn_rpn_head_tf32(eng_tf32, otaps):
+    e = eng_tf32
+    e.run_stages("preprocess", "rpn_proposals")
+    for k, c in (("res2", 256), ("res3", 512), ("res4", 1024), ("res5", 2048)):
+        ref = otaps["feats"][k]
+        got = e.read_tap(k, tuple(ref.shape)).cpu()
+        assert _rel(got, ref) <= 5e-3, k
+    for k in ("p2", "p3", "p4", "p5", "p6"):
+        ref = otaps["pyr"][k]
+        got = e.read_tap(k, tuple(ref.shape)).cpu()
+        assert _rel(got, ref) <= 5e-3, k
+    for l, (obj, dlt) in enumerate(otaps["rpn"]):
+        _, _, h, w = obj.shape
+        got = e.read_tap(f"rpn_head.p{l + 2}", (1, h, w, 16)).cpu()
+        ref = torch.cat((obj, dlt), 1).permute(0, 2, 3, 1)
+        assert (got[..., :15] - ref).abs().max().item() <= 5e-3 * ref.abs().max().item(), f"rpn head p{l + 2}"
+
+
+def _inject_rpn_heads(e, otaps):
+    for l, (obj, dlt) in enumerate(otaps["rpn"]):
+        buf = torch.zeros((1, obj.shape[2], obj.shape[3], 16))
+        buf[..., :15] = torch.cat((obj, dlt), 1).permute(0, 2, 3, 1)
+        e.write_tap(f"rpn_head.p{l + 2}", buf)
+
+
+def test_rpn_proposals_exact_given_oracle_head(eng_tf32, otaps):
+    """top-k per level, decode, clip, per-level NMS 0.7, merge to 1000: same survivors in the same order."""
+    e = eng_tf32
+    e.run_stages("preprocess", "rpn_proposals")
+    _inject_rpn_heads(e, otaps)
+    e.run_stages("rpn_proposals", "box_head")
+    n = int(e.read_tap("prop_count", (1,), torch.int32).item())
+    ref_b, ref_s = otaps["proposals"], otaps["proposal_logits"]
+    assert n == ref_b.shape[0]
+    got_s = e.read_tap("prop_scores", (1000,)).cpu()[:n]
+    got_b = e.read_tap("prop_boxes", (1000, 4)).cpu()[:n]
+    assert torch.equal(got_s, ref_s), "proposal scores (the selected anchors) differ"
+    assert (got_b - ref_b).abs().max().item() <= 2e-3
+    img = e.read_tap("prop_img", (1000,), torch.int32).cpu()
+    assert (img[:n] == 0).all() and (img[n:] == -1).all()
+
+
+def test_roi_align_and_box_head(eng_tf32, otaps, weights):
+    e = eng_tf32
+    e.run_stages("preprocess", "rpn_proposals")
+    _inject_rpn_heads(e, otaps)
+    e.run_stages("rpn_proposals", "detections")
+    n = otaps["proposals"].shape[0]
+    pyr = {k: e.read_tap(k, tuple(otaps["pyr"][k].shape)).cpu() for k in ("p2", "p3", "p4", "p5")}
+    boxes = e.read_tap("prop_boxes", (1000, 4)).cpu()[:n]
+    ref_pool = O.roi_pool(pyr, boxes, 7)
+    got_pool = e.read_tap("box_pooled", (1000, 256, 7, 7)).cpu()[:n]
+    # same inputs, same fp32 op order; the stored result is rounded to tf32 (2^-11 relative)
+    assert (got_pool - ref_pool).abs().max().item() <= 6e-4 * ref_pool.abs().max().item()
+    cls_ref, dlt_ref = O.box_head(got_pool, weights)
+    out = e.read_tap("box_out", (1000, 64)).cpu()[:n]
+    assert (out[:, :10] - cls_ref).abs().max().item() <= 5e-3 * cls_ref.abs().max().item()
+    assert (out[:, 10:46] - dlt_ref).abs().max().item() <= 5e-3 * dlt_ref.abs().max().item()
+
+
+def _inject_box_head(e, otaps):
+    n = otaps["proposals"].shape[0]
+    pb = torch.zeros((1000, 4))
+    pb[:n] = otaps["proposals"]
+    e.write_tap("prop_boxes", pb)
+    e.write_tap("prop_count", torch.tensor([n], dtype=torch.int32))
+    out = torch.zeros((1000, 64))
+    out[:n, :10] = otaps["cls_logits"]
+    out[:n, 10:46] = otaps["deltas"]
+    e.write_tap("box_out", out)
+    return n
+
+
+def test_detections_exact_given_oracle_head(eng_tf32, otaps):
+    """softmax, score filter, class-wise decode, per-class NMS 0.5, top 100: same detections in the same order."""
+    e = eng_tf32
+    e.run_stages("preprocess", "rpn_proposals")
+    _inject_box_head(e, otaps)
+    e.run_stages("detections", "mask_head")
+    nd = int(e.read_tap("det_count", (1,), torch.int32).item())
+    assert nd == otaps["det_boxes"].shape[0] and nd > 10
+    cls = e.read_tap("det_classes", (100,), torch.int32).cpu()[:nd].long()
+    sc = e.read_tap("det_scores", (100,)).cpu()[:nd]
+    bx = e.read_tap("det_boxes", (100, 4)).cpu()[:nd]
+    assert torch.equal(cls, otaps["det_classes"])
+    assert (sc - otaps["det_scores"]).abs().max().item() <= 1e-6
+    assert (bx - otaps["det_boxes"]).abs().max().item() <= 2e-3
+    assert len(set(cls.tolist())) >= 2, "synthetic weights should exercise more than one class"
+
+
+def test_mask_head_and_paste(eng_tf32, otaps, weights, ocfg):
+    e = eng_tf32
+    e.run_stages("preprocess", "rpn_proposals")
+    _inject_box_head(e, otaps)
+    e.run_stages("detections", "end")
+    nd = otaps["det_boxes"].shape[0]
+    pyr = {k: e.read_tap(k, tuple(otaps["pyr"][k].shape)).cpu() for k in ("p2", "p3", "p4", "p5")}
+    det_boxes = e.read_tap("det_boxes", (100, 4)).cpu()[:nd]
+    det_scores = e.read_tap("det_scores", (100,)).cpu()[:nd]
+    classes = otaps["det_classes"]
+    ref_pool = O.roi_pool(pyr, det_boxes, 14)
+    got_pool = e.read_tap("mask_pooled", (100, 256, 14, 14)).cpu()[:nd]
+    assert (got_pool - ref_pool).abs().max().item() <= 6e-4 * ref_pool.abs().max().item()
+    # mask logits: [roi, py, px, dy, dx, 16] -> [roi, 9, 28, 28]
+    raw = e.read_tap("mask_logits", (100, 14, 14, 2, 2, 16)).cpu()[:nd]
+    got_logits = raw.permute(0, 5, 1, 3, 2, 4).reshape(nd, 16, 28, 28)[:, :9]
+    ref_probs = O.mask_head(got_pool, classes, weights)
+    got_probs = got_logits[torch.arange(nd), classes].sigmoid()
+    assert (got_probs - ref_probs).abs().max().item() <= 5e-3
+    # paste + accumulate: exact given the device's own mask probabilities and boxes
+    b, s, c, masks = O.postprocess(det_boxes, det_scores, classes, got_probs, otaps["image_size"], H, W, ocfg)
+    ref_sem = O.accumulate(masks, s, c, 9, THR, THR, None, H, W)
+    got_sem = e._out.cpu()[0]
+    diff = (got_sem != ref_sem)
+    assert diff.float().mean().item() <= 1e-5, f"{int(diff.sum())} of {diff.numel()} cells differ"
+    assert (got_sem[..., 9] == 0).all() and got_sem.sum() > 0
+
+
+def test_bf16_features_vs_emulated_oracle(weights, frame, ocfg):
+    e = _engine(weights, "bf16")
+    rgb = torch.from_numpy(frame)[None].cuda()
+    out = torch.zeros((1, H, W, 10), device="cuda")
+    e.set_call(rgb, out, score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR)
+    e.run_stages("preprocess", "rpn_proposals")
+    with torch.no_grad():
+        x, _ = O.preprocess(frame, ocfg)
+        feats = O.backbone(x, weights, emulate_bf16=True)
+        pyr = O.fpn(feats, weights, emulate_bf16=True)
+    for k in ("res2", "res3", "res4", "res5"):
+        assert _rel(e.read_tap(k, tuple(feats[k].shape)).cpu(), feats[k]) <= 4e-2, k
+    for k in ("p2", "p3", "p4", "p5", "p6"):
+        assert _rel(e.read_tap(k, tuple(pyr[k].shape)).cpu(), pyr[k]) <= 4e-2, k
+
+
+def _match(boxes_a, cls_a, boxes_b, cls_b, iou_thr=0.9):
+    from torchvision.ops import box_iou
+    if boxes_a.numel() == 0 or boxes_b.numel() == 0:
+        return 0
+    iou = box_iou(boxes_a, boxes_b)
+    iou[cls_a[:, None] != cls_b[None, :]] = 0
+    return int((iou.max(1).values >= iou_thr).sum())
+
+
+def test_end_to_end_reference_frame_tf32(weights):
+    """480 x 640 frame through the whole pipeline at the reference's geometry (800 x 1067 -> 800 x 1088)."""
+    frame = O.synth_rgb(11)
+    cfg = O.Cfg(score_thresh=THR)
+    taps = {}
+    ref = O.forward(frame, weights, cfg, taps=taps)
+    e = _engine(weights, "tf32", h=480, w=640, min_size=800, max_size=1333)
+    assert e.input_size() == ((800, 1067), (800, 1088))
+    sem = e.forward_device(torch.from_numpy(frame)[None].cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR)
+    torch.cuda.synchronize()
+    nd = int(e.read_tap("det_count", (1,), torch.int32).item())
+    bx = e.read_tap("det_boxes", (100, 4)).cpu()[:nd]
+    cl = e.read_tap("det_classes", (100,), torch.int32).cpu()[:nd].long()
+    n_ref = taps["det_boxes"].shape[0]
+    assert n_ref > 0
+    matched = _match(taps["det_boxes"], taps["det_classes"], bx, cl)
+    assert matched >= 0.8 * n_ref, f"only {matched} of {n_ref} oracle detections found"
+    ref_sem = O.accumulate(ref["masks"], ref["scores"], ref["classes"], 9, THR, THR, None, 480, 640)
+    agree = ((sem.cpu()[0] > 0) == (ref_sem > 0)).float().mean().item()
+    assert agree >= 0.97, f"category-mask agreement {agree}"
+
+
+def test_reference_api_and_goal_gate(weights):
+    frame = O.synth_rgb(11)
+    args = types.SimpleNamespace(sem_pred_prob_thr=THR, goal_thr=0.9999999, seg_model_wts=None, sem_gpu_id=0)
+    model = S.SemanticPredMaskRCNN(args, state_dict=weights, precision="bf16")
+    assert model.n_cats == 9
+    sem, bgr = model.get_prediction(frame)
+    assert sem.shape == (480, 640, 10) and sem.dtype == np.float32 and sem.flags.writeable
+    assert np.array_equal(bgr, frame[:, :, ::-1])
+    assert (sem == np.round(sem)).all() and sem.min() >= 0 and sem.sum() > 0
+    present = [c for c in range(9) if sem[:, :, c].sum() > 0]
+    goal = present[0]
+    sem_g, _ = model.get_prediction(frame, goal_cat=goal)   # goal_thr ~ 1 removes (nearly) every goal-class instance
+    assert sem_g[:, :, goal].sum() < sem[:, :, goal].sum()
+    for c in present[1:]:
+        assert np.array_equal(sem_g[:, :, c], sem[:, :, c])
+    again, _ = model.get_prediction(frame)
+    assert np.array_equal(again, sem), "CUDA-graph replay must be bit-stable"
+    with pytest.raises(ValueError):
+        model.get_prediction(frame[:100])
+
+
+def test_batch_equals_single(weights):
+    frames = np.stack([O.synth_rgb(s, H, W) for s in (1, 2)])
+    e2 = _engine(weights, "bf16", batch=2)
+    both = e2.forward_device(torch.from_numpy(frames).cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR).cpu()
+    e1 = _engine(weights, "bf16", batch=1)
+    for i in range(2):
+        one = e1.forward_device(torch.from_numpy(frames[i:i + 1]).cuda(), score_thresh=THR, sem_pred_prob_thr=THR,
+                                goal_thr=THR).cpu()
+        assert torch.equal(one[0], both[i])
+    assert both.sum() > 0

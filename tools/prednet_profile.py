@@ -14,10 +14,10 @@ def main():
     x = torch.rand((B, C, H, H), device="cuda")
     seg.forward_device(x); seg.forward_device(x); torch.cuda.synchronize()
     prof = seg.profile(5)
-    tot = sum(ms for _, ms in prof)
+    tot = sum(ms for _, ms, _ in prof)
     print(f"# prednet B={B} C={C} H={H} {prec}: {len(prof)} ops, eager sum {tot:.3f} ms")
-    for name, ms in prof:
-        print(f"{ms*1000:9.1f} us  {name}")
+    for name, ms, fl in prof:
+        print(f"{ms*1000:9.1f} us  {fl/ms/1e9 if ms > 0 else 0:8.1f} TF/s  {name}")
     # graph replay timing
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out = seg.forward_device(x)

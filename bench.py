@@ -191,18 +191,14 @@ def run_reference(a):
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from peanut_b200 import _lib
+    from peanut_b200 import parallel
     from peanut_b200.pipeline import PerceptionPipeline
 
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (ours) needs a GPU: peanut_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    rank, local, world = parallel.init_from_env("nccl")
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[a.workload]
     E = a.envs or wl["envs"]
     precision = a.precision or wl["precision"]
@@ -262,23 +258,20 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = parallel.max_over_ranks([dev_ms, e2e_ms], device=dev)
 
     # ---- result gather (the only collective on the path: per-env predicted maps to rank 0; outside the timed region)
     gather_ms = None
     if world > 1:
-        out = [torch.empty_like(pipe.pred_out) for _ in range(world)]
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.all_gather(out, pipe.pred_out)
+        parallel.gather_env_results(pipe.pred_out, E * world, dst=0)
         torch.cuda.synchronize()
         g0.record()
-        dist.all_gather(out, pipe.pred_out)
+        allp = parallel.gather_env_results(pipe.pred_out, E * world, dst=0)
         g1.record()
         torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
+        gather_ms = parallel.max_over_ranks([g0.elapsed_time(g1)], device=dev)[0]
+        assert rank != 0 or tuple(allp.shape) == (E * world,) + tuple(pipe.pred_out.shape[1:])
 
     if rank != 0:
         if world > 1:

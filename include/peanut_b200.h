@@ -170,6 +170,11 @@ int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, in
               const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
               int stride, int dil, int pad, int relu, int force_bn, float* y_dev);
 
+/* Tuning / roofline aid: builds one fused conv (+BN scale/bias, +ReLU, optional residual) on constant data and returns
+ * the mean device time of `iters` back-to-back launches (CUDA events) and the N tile the heuristic (or force_bn) chose. */
+int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int Cout, int R, int S, int stride, int dil,
+                  int pad, int with_residual, int force_bn, int iters, float* ms_out, int* bn_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
     "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "pn_semmap_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_conv_bench": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 14 + [ctypes.c_void_p, ctypes.c_void_p]),
     "pn_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                   [ctypes.c_void_p] * 4 + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
 }

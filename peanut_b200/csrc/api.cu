@@ -591,10 +591,55 @@ int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, in
   sp.relu = relu != 0;
   sp.force_bn = force_bn & 0xfff;
   sp.force_direct_epilogue = (force_bn & 0x1000) != 0;
+  sp.force_splits = (force_bn >> 16) & 0xff;
   add_conv(net, "pn_conv2d", x, y, w_host, scale_host, bias_host, sp, residual_dev ? &res : nullptr);
   net.run(nullptr);
+  if (sp.force_splits > 1) net.run(nullptr);  // a second pass over the same workspace: split-K must leave it clean
   nhwc_to_nchw(y, Cout, y_dev, nullptr);
   PN_CUDA_CHECK(cudaDeviceSynchronize());
+  PN_API_END
+}
+
+int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int Cout, int R, int S, int stride, int dil,
+                  int pad, int with_residual, int force_bn, int iters, float* ms_out, int* bn_out) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(ms_out && iters > 0, "pn_conv_bench: bad arguments");
+  const DType dt = precision == PN_BF16 ? kBF16 : kF32;
+  Net net;
+  net.num_sms = c->num_sms;
+  net.use_graph = false;
+  Tensor x = net.arena.tensor(B, H, W, pad_channels(Cin, dt), dt);
+  PN_CUDA_CHECK(cudaMemset(x.ptr, 0x3c, x.bytes()));
+  const int Ho = conv_out(H, R, stride, dil, pad), Wo = conv_out(W, S, stride, dil, pad);
+  PN_REQUIRE(Ho > 0 && Wo > 0, "pn_conv_bench: empty output");
+  Tensor y = net.arena.tensor(B, Ho, Wo, pad_channels(Cout, dt), dt);
+  Tensor res;
+  if (with_residual) {
+    res = net.arena.tensor(B, Ho, Wo, pad_channels(Cout, dt), dt);
+    PN_CUDA_CHECK(cudaMemset(res.ptr, 0x3c, res.bytes()));
+  }
+  std::vector<float> w(static_cast<size_t>(Cout) * Cin * R * S, 0.01f), sc(Cout, 1.f), bi(Cout, 0.f);
+  ConvSpec sp;
+  sp.Cin = Cin, sp.Cout = Cout, sp.R = R, sp.S = S, sp.stride = stride, sp.dil = dil, sp.pad = pad, sp.relu = true;
+  sp.force_bn = force_bn & 0xfff;
+  sp.force_splits = (force_bn >> 16) & 0xff;
+  add_conv(net, "bench", x, y, w.data(), sc.data(), bi.data(), sp, with_residual ? &res : nullptr);
+  if (bn_out) *bn_out = net.last_bn;
+  cudaEvent_t e0, e1;
+  PN_CUDA_CHECK(cudaEventCreate(&e0));
+  PN_CUDA_CHECK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) net.run_eager(c->stream);
+  PN_CUDA_CHECK(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i) net.run_eager(c->stream);
+  PN_CUDA_CHECK(cudaEventRecord(e1, c->stream));
+  PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  PN_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
   PN_API_END
 }
 

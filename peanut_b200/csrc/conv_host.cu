@@ -49,8 +49,8 @@ CUtensorMap encode_tiled_2d(DType dt, const void* base, uint64_t inner, uint64_t
 }
 
 // (C, W, H, N) activation tensor, one box = `pixels` output positions x `channels` channels.
-CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pad, int dil, int R, int S, int stride,
-                          uint32_t box_channels, uint32_t pixels, int sw) {
+CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pad_h, int pad_w, int dil, int R, int S,
+                          int stride_h, int stride_w, uint32_t box_channels, uint32_t pixels, int sw) {
   static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
   CUtensorMap m;
   const uint64_t es = dtype_size(dt);
@@ -59,9 +59,9 @@ CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pa
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.ld) * es, static_cast<cuuint64_t>(in.ld) * es * in.W,
                            static_cast<cuuint64_t>(in.ld) * es * in.W * in.H};
   // Bounding box of base pixels: [-pad, extent + pad - (taps-1)*dil) in each spatial dimension.
-  int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (S - 1) * dil, pad - (R - 1) * dil};
-  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  int lower[2] = {-pad_w, -pad_h};
+  int upper[2] = {pad_w - (S - 1) * dil, pad_h - (R - 1) * dil};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
   CUresult r = fn(&m, dtype_enum(dt), 4, in.ptr, dims, strides, lower, upper, box_channels, pixels, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -87,7 +87,13 @@ void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem,
                                        227 * 1024));
     configured = true;
   }
-  conv_umma_kernel<T, BN><<<grid, kNumThreads, smem, s>>>(tm.a, tm.b, tm.out, tm.res, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kNumThreads), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, BN>, tm.a, tm.b, tm.out, tm.res, p));
 }
 
 template <typename T>
@@ -138,8 +144,10 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
               const float* scale, const float* bias, const ConvSpec& sp, const Tensor* residual) {
   const DType dt = in.dt;
   const int es = static_cast<int>(dtype_size(dt));
+  const int stride_w = sp.stride_w >= 0 ? sp.stride_w : sp.stride;
+  const int pad_w = sp.pad_w >= 0 ? sp.pad_w : sp.pad;
   const int Ho = conv_out(in.H, sp.R, sp.stride, sp.dil, sp.pad);
-  const int Wo = conv_out(in.W, sp.S, sp.stride, sp.dil, sp.pad);
+  const int Wo = conv_out(in.W, sp.S, stride_w, sp.dil, pad_w);
   PN_REQUIRE(out.B == in.B && out.H == Ho && out.W == Wo, name + ": output shape mismatch");
   PN_REQUIRE(in.C >= sp.Cin, name + ": input view has fewer channels than the filter");
   PN_REQUIRE(out.dt == dt || (sp.out_fp32 && out.dt == kF32), name + ": output dtype mismatch");
@@ -162,18 +170,37 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   const long long M = static_cast<long long>(in.B) * Ho * Wo;
   PN_REQUIRE(M < (1ll << 31), name + ": M too large");
   const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
-  int bn = 32;
-  if (sp.force_bn) {
-    bn = sp.force_bn;
-  } else {
+  // N tile: the kernel streams (128 + bn) * K bytes of operands per tile through one SM's TMA path (~125 GB/s per SM,
+  // ~14 TB/s out of L2 in aggregate, measured with tools/conv_tune.py); the MMA itself needs max(bn/2, 32) cycles
+  // per 32-byte K step (below N = 64 the A-operand shared-memory read dominates).  Pick the tile that minimises
+  // waves * max(stream time, MMA time): wide tiles for big layers, narrower ones when the grid would not fill.
+  int bn = 32, splits = 1;
+  {
+    const int kblocks_total = taps * kb_per_tap;
+    double best = 1e30;
     for (int cand : {256, 128, 64, 32}) {
-      if (cand > cout32) continue;
-      if (cout32 % cand != 0) continue;
-      bn = cand;
-      const long long tiles = static_cast<long long>(m_tiles) * (cout32 / cand);
-      if (tiles >= net.num_sms || cand == 32) break;
+      if (sp.force_bn ? cand != (sp.force_bn & 0x3ff) : (cand > cout32 || cout32 % cand != 0)) continue;
+      for (int s : {1, 2, 3, 4, 6, 8, 12, 16}) {
+        if (sp.force_splits ? s != sp.force_splits : (s > 1 && (sp.no_split || kblocks_total / s < 4))) continue;
+        if (s > kblocks_total) continue;
+        const int kbs = (kblocks_total + s - 1) / s;
+        if (s > 1 && kbs * (s - 1) >= kblocks_total) continue;  // the last split would be empty
+        const double work = static_cast<double>(m_tiles) * ((cout32 + cand - 1) / cand) * s;
+        const double active = std::min<double>(work, net.num_sms);
+        const double waves = std::ceil(work / net.num_sms);
+        const double bytes = static_cast<double>(kbs) * block_k * es * (kBlockM + cand);
+        const double t_mem = bytes / std::min(125e9, 14e12 / active);
+        const double t_mma = static_cast<double>(kbs) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
+        const double t_epi = 0.25e-6 * cand / 32.0;  // un-overlapped epilogue of the last tile
+        // split-K: red.add of the partial tile, fence + ticket, read-back by the last CTA
+        const double t_red = s > 1 ? 1.5e-6 + 2.0 * kBlockM * cand * 4.0 / 100e9 : 0.0;
+        const double t = waves * std::max(t_mem, t_mma) + t_epi + t_red;
+        if (t < best * (s > 1 ? 0.9 : 1.0)) best = t, bn = cand, splits = s;
+      }
     }
+    PN_REQUIRE(best < 1e29, name + ": no valid tile configuration");
   }
+  net.last_bn = bn + 1000 * splits;
   const int cout_pad = round_up(sp.Cout, bn);
   const int n_tiles = cout_pad / bn;
 
@@ -208,12 +235,12 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   const float* sc_dev = net.arena.upload(sc);
   const float* bi_dev = net.arena.upload(bi);
 
-  const bool a_tiled = (taps == 1 && sp.stride == 1 && sp.pad == 0);
+  const bool a_tiled = (taps == 1 && sp.stride == 1 && stride_w == 1 && sp.pad == 0 && pad_w == 0);
   ConvMaps tm;
   if (a_tiled) {
     tm.a = encode_tiled_2d(dt, in.ptr, cin_pad, M, static_cast<uint64_t>(in.ld) * es, block_k, kBlockM, sw);
   } else {
-    tm.a = encode_im2col(dt, in, cin_pad, sp.pad, sp.dil, sp.R, sp.S, sp.stride, block_k, kBlockM, sw);
+    tm.a = encode_im2col(dt, in, cin_pad, sp.pad, pad_w, sp.dil, sp.R, sp.S, sp.stride, stride_w, block_k, kBlockM, sw);
   }
   tm.b = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, bn, sw);
   tm.out = tm.b;
@@ -224,6 +251,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.M = static_cast<int>(M);
   p.Ho = Ho, p.Wo = Wo, p.R = sp.R, p.S = sp.S;
   p.stride = sp.stride, p.dil = sp.dil, p.pad = sp.pad;
+  p.stride_w = stride_w, p.pad_w = pad_w;
   p.kb_per_tap = kb_per_tap, p.block_k = block_k, p.sw = sw;
   p.m_tiles = m_tiles, p.n_tiles = n_tiles;
   p.cout_store = std::min(round_up(sp.Cout, 8), out.C);
@@ -239,6 +267,13 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.round_tf32 = (dt == kF32 && !sp.out_fp32) ? 1 : 0;
   p.m_limit = sp.m_limit;
   p.m_limit_rows = sp.m_limit_rows;
+  p.splits = splits;
+  p.kb_per_split = (taps * kb_per_tap + splits - 1) / splits;
+  if (splits > 1) {
+    p.ldw = static_cast<long long>(n_tiles) * bn;
+    p.ws = static_cast<float*>(net.arena.alloc(static_cast<size_t>(m_tiles) * kBlockM * p.ldw * sizeof(float)));
+    p.counters = static_cast<int*>(net.arena.alloc(static_cast<size_t>(m_tiles) * n_tiles * sizeof(int)));
+  }
 
   // Epilogue mode: smem-staged TMA stores (+ TMA residual prefetch) whenever a stored row chunk is at
   // least 64 bytes and the output has the activation dtype; otherwise direct per-thread stores.
@@ -246,7 +281,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   {
     const int store_bytes = p.cout_store * es;
     int cb = 0;
-    if (out.dt == dt && !sp.force_direct_epilogue) {
+    if (out.dt == dt && !sp.force_direct_epilogue && splits == 1) {
       if (store_bytes >= 128 && bn * es >= 128) cb = 128;
       else if (store_bytes >= 64 && bn * es >= 64 && es == 2) cb = 64;
     }
@@ -280,12 +315,18 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
       stages = stages1;
     }
   }
+  // Single-wave layers (one tile per CTA) are latency-bound: cap the footprint at ~half an SM so that the next
+  // kernel's CTA can become resident beside this one (programmatic dependent launch) and overlap its prologue.
+  if (static_cast<long long>(m_tiles) * n_tiles * splits <= net.num_sms) {
+    const int cap = static_cast<int>((110 * 1024 - std::min<size_t>(fixed_bytes, 100 * 1024)) / stage_bytes);
+    if (cap >= 3) stages = std::min(stages, cap);
+  }
   if (stages > 8) stages = 8;
-  if (stages > kblocks + 1) stages = std::max(2, kblocks + 1);
+  if (stages > p.kb_per_split + 1) stages = std::max(2, p.kb_per_split + 1);
   p.stages = stages;
   PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
   const size_t smem = fixed_bytes + stages * stage_bytes;
-  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles * splits;
   const int grid = static_cast<int>(std::min<long long>(tiles, net.num_sms));
 
   const double flops = 2.0 * static_cast<double>(M) * sp.Cout * sp.Cin * taps;

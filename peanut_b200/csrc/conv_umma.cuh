@@ -29,7 +29,8 @@ struct ConvParams {
   int M;           // number of output pixels = B * Ho * Wo (GEMM rows)
   int Ho, Wo;      // output spatial size
   int R, S;        // filter taps
-  int stride, dil, pad;
+  int stride, dil, pad;  // vertical stride / padding (and horizontal unless overridden below)
+  int stride_w, pad_w;
   int kb_per_tap;  // Cin_pad / BLOCK_K
   int block_k;     // elements per K block (sw / sizeof(T))
   int sw;          // bytes per smem row == TMA swizzle span: 32, 64 or 128
@@ -52,6 +53,13 @@ struct ConvParams {
   int out_bufs;  // output staging depth: 2, or 1 for K-heavy layers where a deeper A/B pipeline matters more
   const int* m_limit;  // optional device-side count of valid row groups (ROIs); rows = *m_limit * m_limit_rows
   int m_limit_rows;
+  // split-K: every output tile is computed by `splits` CTAs over disjoint K-block ranges; partial sums meet in an
+  // fp32 workspace (vector red.global.add), the last CTA to arrive applies the epilogue and re-zeroes the workspace.
+  int splits;        // >= 1
+  int kb_per_split;  // K blocks per split (the last split may be shorter)
+  float* ws;         // [m_tiles * 128][ldw] fp32, all zero between launches
+  long long ldw;
+  int* counters;     // [m_tiles * n_tiles], all zero between launches
 };
 
 constexpr int kBlockM = 128;
@@ -84,10 +92,13 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t r, uint32_t j, uint32_t cb)
 }
 
 template <typename T, int BN>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const ConvParams p) {
+  // Programmatic dependent launch: let the next kernel in the stream start its prologue (and become resident next
+  // to this CTA when both fit) right away; it blocks in griddep_wait() until this grid has completed.
+  griddep_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = kBlockM * p.sw;
@@ -139,6 +150,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on we read what it wrote
+  griddep_wait();
 
   int m_tiles_live = p.m_tiles;
   if (p.m_limit != nullptr) {
@@ -146,9 +160,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int t = static_cast<int>((rows + kBlockM - 1) / kBlockM);
     m_tiles_live = t < p.m_tiles ? t : p.m_tiles;
   }
-  const int num_tiles = m_tiles_live * p.n_tiles;
+  const int num_tiles = m_tiles_live * p.n_tiles * p.splits;  // work items: (m_tile, n_tile, split), split fastest
   const int taps = p.R * p.S;
   const int kblocks = taps * p.kb_per_tap;
+  uint32_t* last_flag = tmem_ptr + 1;
   const int cols_per_chunk = p.epi_tma ? p.cb / static_cast<int>(sizeof(T)) : 32;
 
   if (warp == 0) {
@@ -156,7 +171,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int tile = work / p.splits;
+        const int split = work - tile * p.splits;
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
         const int m0 = m_tile * kBlockM;
@@ -164,26 +181,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int t = m0 / p.Wo;
         const int pp = t % p.Ho;
         const int img = t / p.Ho;
-        const int w0 = q * p.stride - p.pad;
+        const int w0 = q * p.stride_w - p.pad_w;
         const int h0 = pp * p.stride - p.pad;
-        int kb_global = 0;
-        for (int r = 0; r < p.R; ++r) {
-          for (int s = 0; s < p.S; ++s) {
-            for (int kb = 0; kb < p.kb_per_tap; ++kb, ++kb_global) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-              if (p.a_tiled) {
-                tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, m0);
-              } else {
-                tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0,
-                                   img, static_cast<uint16_t>(s * p.dil), static_cast<uint16_t>(r * p.dil));
-              }
-              tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
-            }
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(kblocks, kb_begin + p.kb_per_split);
+        int tap = kb_begin / p.kb_per_tap;
+        int kb = kb_begin - tap * p.kb_per_tap;
+        int r = tap / p.S, sx = tap - r * p.S;
+        for (int kb_global = kb_begin; kb_global < kb_end; ++kb_global) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          if (p.a_tiled) {
+            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, m0);
+          } else {
+            tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0, img,
+                               static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+          }
+          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++kb == p.kb_per_tap) {
+            kb = 0;
+            if (++sx == p.S) sx = 0, ++r;
           }
         }
       }
@@ -196,13 +217,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int split = work % p.splits;
+        const int my_kblocks = min(kblocks, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
+        for (int kb = 0; kb < my_kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = umma_smem_desc(smem_u32(smem_a + stage * a_bytes), p.sw);
@@ -216,7 +239,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == my_kblocks - 1) umma_commit(&tfull_bar[acc]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -359,20 +382,62 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ epilogue, direct path: TMEM -> regs -> global
     const int quarter = warp & 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int tile = work / p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const long long m = static_cast<long long>(m_tile) * kBlockM + quarter * 32 + lane;
       const bool row_ok = m < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      bool from_ws = false;
+      float* wrow = nullptr;
+      if (p.splits > 1) {
+        // ---- split-K: add this CTA's partial tile into the workspace; the last arrival finishes the tile
+        wrow = p.ws + m * p.ldw + n_tile * BN;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chunk * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            red_add_v4(wrow + chunk * 32 + g * 4, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(p.counters + tile, 1);
+          const bool last = (old == p.splits - 1);
+          if (last) p.counters[tile] = 0;  // every split has arrived: clean for the next launch
+          *last_flag = last ? 1u : 0u;
+        }
+        named_bar_sync(1, 128);
+        if (*last_flag == 0u) continue;
+        __threadfence();
+        from_ws = true;
+      }
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chunk * 32, v);
-        tmem_ld_wait();
+        if (from_ws) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t4 = ld_cg_v4(wrow + chunk * 32 + g * 4);
+            v[g * 4] = __float_as_uint(t4.x), v[g * 4 + 1] = __float_as_uint(t4.y);
+            v[g * 4 + 2] = __float_as_uint(t4.z), v[g * 4 + 3] = __float_as_uint(t4.w);
+            *reinterpret_cast<float4*>(wrow + chunk * 32 + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chunk * 32, v);
+          tmem_ld_wait();
+        }
         const int n0 = n_tile * BN + chunk * 32;
         if (row_ok && n0 < p.cout_store) {
           float y[32];
@@ -441,9 +506,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (!from_ws) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 

@@ -139,22 +139,145 @@ __global__ void k_subsample2(const T* __restrict__ in, long long ldi, int H, int
 // ---------------------------------------------------------------------------------------------------
 // RPN per (level, image): exact top-k by 4-pass radix select (ties -> lower index), sort, decode, clip,
 // drop empty / non-finite, greedy NMS via a shared-memory suppression bit matrix.  block = 1024 threads.
+constexpr int kCandCap = 4096;     // candidate capacity of the multi-CTA pre-selection (fallback beyond it)
+constexpr int kHistBins = 65536;   // histogram over the top 16 bits of the order-preserving key
+
 struct RpnSmem {
-  unsigned long long keys[kRpnCap];
-  float4 box[kRpnCap];
-  float score[kRpnCap];
+  unsigned long long keys[kCandCap];
   uint32_t hist[256];
   int warp_sums[33];
   uint32_t prefix, rank, cnt_eq;
-  int ncand, nvalid, nkept;
-  int kept[kRpnCap];
+  int ncand;
 };
 
-__global__ void __launch_bounds__(1024, 1) k_rpn_select_nms(RpnMeta meta, float* __restrict__ lvl_boxes,
-                                                            float* __restrict__ lvl_scores, int* __restrict__ lvl_count) {
+// ---- multi-CTA pre-selection: (1) 16-bit key histogram per (image, level), (2) threshold bin holding the k-th
+// largest key, (3) every logit at or above that bin is appended to a candidate list.  The list is a superset of
+// the exact top-k (typically k + a few dozen); k_rpn_select_nms sorts it.  Scanning the 163 200 logits of P2 is
+// spread over ~50 CTAs instead of one.
+constexpr int kPixPerBlock = 1024;
+
+__global__ void __launch_bounds__(256) k_rpn_hist(RpnMeta meta, uint32_t* __restrict__ hist) {
+  const int L = blockIdx.y % kRpnLevels, b = blockIdx.y / kRpnLevels;
+  const RpnLevel& lv = meta.lv[L];
+  const int npix = lv.H * lv.W;
+  const int p0 = blockIdx.x * kPixPerBlock;
+  if (p0 >= npix) return;
+  const float* head = lv.head + static_cast<size_t>(b) * npix * kRpnHeadC;
+  uint32_t* h = hist + static_cast<size_t>(b * kRpnLevels + L) * kHistBins;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < kPixPerBlock / 256; ++j) {
+    const int pix = p0 + j * 256 + threadIdx.x;
+    const bool in = pix < npix;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) v = *reinterpret_cast<const float4*>(head + static_cast<size_t>(pix) * kRpnHeadC);
+    const float lg[3] = {v.x, v.y, v.z};
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+#pragma unroll
+      for (int a = 0; a < kAnchors; ++a) {
+        const uint32_t bin = fkey(lg[a]) >> 16;
+        const unsigned peers = __match_any_sync(act, bin);
+        if (lane == __ffs(peers) - 1) atomicAdd(&h[bin], static_cast<uint32_t>(__popc(peers)));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_rpn_threshold(RpnMeta meta, const uint32_t* __restrict__ hist,
+                                                        uint32_t* __restrict__ thr_bin, int* __restrict__ ncand) {
+  __shared__ int warp_sums[33];
+  __shared__ uint32_t s_bin;
+  const int L = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const RpnLevel& lv = meta.lv[L];
+  const int n = lv.H * lv.W * kAnchors;
+  const uint32_t k = static_cast<uint32_t>(min(n, meta.pre_topk));
+  const uint32_t* h = hist + static_cast<size_t>(b * kRpnLevels + L) * kHistBins;
+  // thread t owns the 64 bins [65535 - 64t - 63, 65535 - 64t], i.e. descending key order across threads
+  constexpr int kPer = kHistBins / 1024;
+  const int hi = kHistBins - 1 - tid * kPer;
+  uint32_t c[kPer], sum = 0;
+#pragma unroll
+  for (int j = 0; j < kPer / 4; ++j) {
+    const uint4 v = *reinterpret_cast<const uint4*>(h + hi - 4 * j - 3);
+    c[4 * j] = v.w, c[4 * j + 1] = v.z, c[4 * j + 2] = v.y, c[4 * j + 3] = v.x;
+    sum += v.x + v.y + v.z + v.w;
+  }
+  // inclusive scan of `sum` over threads
+  const int lane = tid & 31, wid = tid >> 5;
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_sums[wid] = static_cast<int>(incl);
+  __syncthreads();
+  if (wid == 0) {
+    int v = warp_sums[lane], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    warp_sums[lane] = x - v;
+  }
+  __syncthreads();
+  incl += static_cast<uint32_t>(warp_sums[wid]);
+  const uint32_t before = incl - sum;
+  if (k - 1 >= before && k - 1 < incl) {  // the k-th largest key falls into one of this thread's bins
+    uint32_t rr = k - 1 - before;
+    int j = 0;
+    while (rr >= c[j]) rr -= c[j], ++j;
+    s_bin = static_cast<uint32_t>(hi - j);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    thr_bin[b * kRpnLevels + L] = s_bin;
+    ncand[b * kRpnLevels + L] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rpn_collect(RpnMeta meta, const uint32_t* __restrict__ thr_bin, int* __restrict__ ncand,
+                                                     unsigned long long* __restrict__ cand) {
+  const int L = blockIdx.y % kRpnLevels, b = blockIdx.y / kRpnLevels;
+  const RpnLevel& lv = meta.lv[L];
+  const int npix = lv.H * lv.W;
+  const int p0 = blockIdx.x * kPixPerBlock;
+  if (p0 >= npix) return;
+  const float* head = lv.head + static_cast<size_t>(b) * npix * kRpnHeadC;
+  const uint32_t T16 = thr_bin[b * kRpnLevels + L];
+  int* cnt = ncand + b * kRpnLevels + L;
+  unsigned long long* out = cand + static_cast<size_t>(b * kRpnLevels + L) * kCandCap;
+#pragma unroll
+  for (int j = 0; j < kPixPerBlock / 256; ++j) {
+    const int pix = p0 + j * 256 + threadIdx.x;
+    if (pix >= npix) continue;
+    const float4 v = *reinterpret_cast<const float4*>(head + static_cast<size_t>(pix) * kRpnHeadC);
+    const float lg[3] = {v.x, v.y, v.z};
+#pragma unroll
+    for (int a = 0; a < kAnchors; ++a) {
+      const uint32_t key = fkey(lg[a]);
+      if ((key >> 16) >= T16) {
+        const int slot = atomicAdd(cnt, 1);
+        if (slot < kCandCap)
+          out[slot] = (static_cast<unsigned long long>(key) << 32) | (0xffffffffu - static_cast<uint32_t>(pix * kAnchors + a));
+      }
+    }
+  }
+}
+
+// (a) k_rpn_sort_decode: per (level, image) - exact top-k (sorted pre-selection, or in-block radix select as the
+//     fallback), box decoding, clipping, removal of empty / non-finite boxes -> score-ordered list in global memory;
+// (b) k_rpn_mask: the m x m suppression bit matrix, 32 rows per CTA (the ~500 k IoU tests of one level would
+//     otherwise serialise on a single SM);
+// (c) k_rpn_sweep: greedy sweep over the bit matrix + compaction of the survivors.
+__global__ void __launch_bounds__(1024, 1) k_rpn_sort_decode(RpnMeta meta, const int* __restrict__ ncand,
+                                                             const unsigned long long* __restrict__ cand,
+                                                             float4* __restrict__ sbox, float* __restrict__ sscore,
+                                                             int* __restrict__ scount) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   RpnSmem& S = *reinterpret_cast<RpnSmem*>(smem_raw);
-  uint32_t* mask = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(RpnSmem) + 15) & ~size_t(15)));  // [kRpnCap][32]
   const int L = blockIdx.x, b = blockIdx.y;
   const RpnLevel& lv = meta.lv[L];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -164,7 +287,17 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_select_nms(RpnMeta meta, float*
   const float* head = lv.head + static_cast<size_t>(b) * npix * kRpnHeadC;
   auto logit_at = [&](int i) { return head[static_cast<size_t>(i / kAnchors) * kRpnHeadC + (i % kAnchors)]; };
 
-  // ---- radix select of the k-th largest key
+  const int nc = ncand[b * kRpnLevels + L];
+  if (nc <= kCandCap) {
+    // ---- fast path: sort the pre-selected superset; its first k entries are the exact top-k
+    int npow = 1;
+    while (npow < nc) npow <<= 1;
+    const unsigned long long* src = cand + static_cast<size_t>(b * kRpnLevels + L) * kCandCap;
+    for (int i = tid; i < npow; i += 1024) S.keys[i] = i < nc ? src[i] : 0ull;
+    __syncthreads();
+    if (npow > 1) bitonic_desc(S.keys, npow);
+  } else {
+  // ---- fallback (more than kCandCap logits share the threshold bin): in-block radix select of the k-th largest key
   if (tid == 0) S.prefix = 0, S.rank = static_cast<uint32_t>(k - 1), S.ncand = 0;
   __syncthreads();
   for (int pass = 0; pass < 4; ++pass) {
@@ -238,6 +371,7 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_select_nms(RpnMeta meta, float*
   for (int i = S.ncand + tid; i < kRpnCap; i += 1024) S.keys[i] = 0ull;
   __syncthreads();
   bitonic_desc(S.keys, kRpnCap);
+  }
 
   // ---- decode, clip, validity
   bool valid = false;
@@ -261,24 +395,54 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_select_nms(RpnMeta meta, float*
   }
   int m;
   const int pos = block_scan_flag(valid, S.warp_sums, m);
-  if (valid) S.box[pos] = bx, S.score[pos] = sc;
-  __syncthreads();
+  const size_t base = (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap;
+  if (valid) sbox[base + pos] = bx, sscore[base + pos] = sc;
+  if (tid == 0) scount[b * kRpnLevels + L] = m;
+}
 
-  // ---- suppression bit matrix: bit jj of mask[i][j] <=> box 32j+jj (later in score order) overlaps box i
+__global__ void __launch_bounds__(256) k_rpn_mask(float nms_thr, const float4* __restrict__ sbox, const int* __restrict__ scount,
+                                                  uint32_t* __restrict__ mask_g) {
+  __shared__ float4 box[kRpnCap];
+  const int L = blockIdx.y, b = blockIdx.z;
+  const int m = scount[b * kRpnLevels + L];
+  const int r0 = blockIdx.x * 32;
+  if (r0 >= m) return;
+  const size_t base = (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) box[i] = sbox[base + i];
+  __syncthreads();
   const int nw = (m + 31) >> 5;
-  for (int p = tid; p < m * nw; p += 1024) {
-    const int i = p / nw, j = p - i * nw;
-    uint32_t bits = 0;
-    if (j >= (i >> 5)) {
-      const float4 a = S.box[i];
-      const int c0 = j << 5;
-      const int cend = min(32, m - c0);
-      for (int jj = 0; jj < cend; ++jj) {
-        const int c = c0 + jj;
-        if (c > i && iou_gt(a, S.box[c], meta.nms_thr)) bits |= 1u << jj;
-      }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* mk = mask_g + base * 32;
+  // bit jj of mask[i][j] <=> box 32j+jj (later in score order) overlaps box i; lane jj tests one box, the word is
+  // the ballot.  Only the upper triangle (j >= i / 32) is ever consulted by the sweep.
+  for (int i = r0 + warp; i < min(r0 + 32, m); i += 8) {
+    const float4 a = box[i];
+    for (int j = i >> 5; j < nw; ++j) {
+      const int c = (j << 5) + lane;
+      const bool hit = c < m && c > i && iou_gt(a, box[c], nms_thr);
+      const unsigned bits = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) mk[i * 32 + j] = bits;
     }
-    mask[i * 32 + j] = bits;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_rpn_sweep(const float4* __restrict__ sbox, const float* __restrict__ sscore,
+                                                       const int* __restrict__ scount, const uint32_t* __restrict__ mask_g,
+                                                       float* __restrict__ lvl_boxes, float* __restrict__ lvl_scores,
+                                                       int* __restrict__ lvl_count) {
+  extern __shared__ __align__(16) uint32_t mask[];  // [kRpnCap][32]
+  __shared__ int kept[kRpnCap];
+  __shared__ int s_nkept;
+  const int L = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int m = scount[b * kRpnLevels + L];
+  const int nw = (m + 31) >> 5;
+  const size_t base = (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap;
+  {
+    // rows i need words j >= i / 32 only; copy whole rows (coalesced 128-byte lines)
+    const uint4* src = reinterpret_cast<const uint4*>(mask_g + base * 32);
+    uint4* dst = reinterpret_cast<uint4*>(mask);
+    for (int i = tid; i < m * 8; i += 1024) dst[i] = src[i];
   }
   __syncthreads();
   // ---- greedy sweep by one warp: lane l owns word l of the `removed` bit vector
@@ -298,27 +462,27 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_select_nms(RpnMeta meta, float*
           rem |= row;
         }
       }
-      // fold the rows of the kept boxes into every word
+      // fold the rows of the kept boxes into every word (words below the diagonal were never written: skip them)
       uint32_t kb = kept_bits;
       while (kb) {
         const int j = __ffs(kb) - 1;
         kb &= kb - 1;
-        if (lane < nw) removed |= mask[((c << 5) + j) * 32 + lane];
+        if (lane < nw && lane >= c) removed |= mask[((c << 5) + j) * 32 + lane];
       }
-      if ((kept_bits >> lane) & 1u) S.kept[nkept + __popc(kept_bits & ((1u << lane) - 1u))] = i_lane;
+      if ((kept_bits >> lane) & 1u) kept[nkept + __popc(kept_bits & ((1u << lane) - 1u))] = i_lane;
       nkept += __popc(kept_bits);
     }
-    if (lane == 0) S.nkept = nkept;
+    if (lane == 0) s_nkept = nkept;
   }
   __syncthreads();
-  const int nk = S.nkept;
+  const int nk = s_nkept;
   float* ob = lvl_boxes + (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap * 4;
   float* os = lvl_scores + (static_cast<size_t>(b) * kRpnLevels + L) * kRpnCap;
   for (int i = tid; i < nk; i += 1024) {
-    const int src = S.kept[i];
-    const float4 v = S.box[src];
+    const int src = kept[i];
+    const float4 v = sbox[base + src];
     ob[i * 4] = v.x, ob[i * 4 + 1] = v.y, ob[i * 4 + 2] = v.z, ob[i * 4 + 3] = v.w;
-    os[i] = S.score[src];
+    os[i] = sscore[base + src];
   }
   if (tid == 0) lvl_count[b * kRpnLevels + L] = nk;
 }
@@ -370,10 +534,44 @@ __global__ void __launch_bounds__(1024) k_rpn_merge(int post_topk, const float* 
 // ---------------------------------------------------------------------------------------------------
 // ROIAlignV2 (aligned=True, sampling_ratio=0) with detectron2's level assignment.  One CTA per ROI, one warp
 // per output bin (round robin), one lane per 8 channels (256 channels).
+// One sample of ROIAlign: the four bilinear taps (8 channels per lane) and their weights; ok = false when the
+// sample falls outside the feature map (contributes 0).
 template <typename T>
-__global__ void __launch_bounds__(256) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
+struct RoiSample {
+  float w1, w2, w3, w4;
+  float v1[8], v2[8], v3[8], v4[8];
+  bool ok;
+  __device__ __forceinline__ void fetch(const T* feat, int H, int W, long long ld, int lane, float y, float x) {
+    ok = !(y < -1.0f || y > static_cast<float>(H) || x < -1.0f || x > static_cast<float>(W));
+    if (!ok) return;
+    if (y <= 0.f) y = 0.f;
+    if (x <= 0.f) x = 0.f;
+    int yl = static_cast<int>(y), xl = static_cast<int>(x), yh, xh;
+    if (yl >= H - 1) yh = yl = H - 1, y = static_cast<float>(yl);
+    else yh = yl + 1;
+    if (xl >= W - 1) xh = xl = W - 1, x = static_cast<float>(xl);
+    else xh = xl + 1;
+    const float ly = y - static_cast<float>(yl), lx = x - static_cast<float>(xl);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+    load8(feat + (static_cast<size_t>(yl) * W + xl) * ld + lane * 8, v1);
+    load8(feat + (static_cast<size_t>(yl) * W + xh) * ld + lane * 8, v2);
+    load8(feat + (static_cast<size_t>(yh) * W + xl) * ld + lane * 8, v3);
+    load8(feat + (static_cast<size_t>(yh) * W + xh) * ld + lane * 8, v4);
+  }
+  __device__ __forceinline__ void accumulate(float (&acc)[8]) const {
+    if (!ok) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (((w1 * v1[j] + w2 * v2[j]) + w3 * v3[j]) + w4 * v4[j]);
+  }
+};
+
+// grid = (S bin rows, ROIs); block = S warps: warp pw owns output bin (ph = blockIdx.x, pw); lane = 8 channels.
+// Samples are visited in torchvision's order (iy outer, ix inner) with the loads of two samples in flight.
+template <typename T>
+__global__ void __launch_bounds__(448) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
                                                    int S, T* __restrict__ out, long long ldo) {
-  const int r = blockIdx.x;
+  const int r = blockIdx.y;
   const int b = img[r];
   if (b < 0) return;
   const float x1 = boxes[r * 4], y1 = boxes[r * 4 + 1], x2 = boxes[r * 4 + 2], y2 = boxes[r * 4 + 3];
@@ -389,49 +587,88 @@ __global__ void __launch_bounds__(256) k_roi_align(Pyramid pyr, const float* __r
   const int gh = static_cast<int>(ceilf(rh / static_cast<float>(S)));
   const int gw = static_cast<int>(ceilf(rw / static_cast<float>(S)));
   const float count = static_cast<float>(max(gh * gw, 1));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ph = blockIdx.x, pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int ns = gh * gw;
+  auto sample_y = [&](int iy) { return rsh + static_cast<float>(ph) * bin_h + (static_cast<float>(iy) + .5f) * bin_h / static_cast<float>(gh); };
+  auto sample_x = [&](int ix) { return rsw + static_cast<float>(pw) * bin_w + (static_cast<float>(ix) + .5f) * bin_w / static_cast<float>(gw); };
+  // Bilinear sampling is separable and the bin is a sum over a regular sample grid, so
+  //   bin = sum_rows sum_cols WY[row] * WX[col] * feat[row][col],  WY[row] = sum over the bin's sample rows of their
+  // weight on that feature row (same for WX): every feature cell under the bin is read ONCE instead of once per
+  // (sample, tap).  Lane l accumulates the weight of row rlo + l / column clo + l; bins spanning more than 32 rows or
+  // columns (never with detectron2's level assignment) take the per-sample path.
   const float fh = static_cast<float>(lv.H), fw = static_cast<float>(lv.W);
-  for (int bin = warp; bin < S * S; bin += 8) {
-    const int ph = bin / S, pw = bin - ph * S;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const float yf = fminf(fmaxf(sample_y(0), 0.f), fh), yl_ = fminf(fmaxf(sample_y(gh - 1), 0.f), fh);
+  const float xf = fminf(fmaxf(sample_x(0), 0.f), fw), xl_ = fminf(fmaxf(sample_x(gw - 1), 0.f), fw);
+  const int rlo = min(static_cast<int>(yf), lv.H - 1), rhi = min(static_cast<int>(yl_) + 1, lv.H - 1);
+  const int clo = min(static_cast<int>(xf), lv.W - 1), chi = min(static_cast<int>(xl_) + 1, lv.W - 1);
+  if (ns > 0 && rhi - rlo < 32 && chi - clo < 32) {
+    float WY = 0.f, WX = 0.f;
     for (int iy = 0; iy < gh; ++iy) {
-      float y = rsh + static_cast<float>(ph) * bin_h + (static_cast<float>(iy) + .5f) * bin_h / static_cast<float>(gh);
-      for (int ix = 0; ix < gw; ++ix) {
-        float x = rsw + static_cast<float>(pw) * bin_w + (static_cast<float>(ix) + .5f) * bin_w / static_cast<float>(gw);
-        float yy = y;
-        if (yy < -1.0f || yy > fh || x < -1.0f || x > fw) continue;
-        if (yy <= 0.f) yy = 0.f;
-        if (x <= 0.f) x = 0.f;
-        int yl = static_cast<int>(yy), xl = static_cast<int>(x), yh, xh;
-        if (yl >= lv.H - 1) yh = yl = lv.H - 1, yy = static_cast<float>(yl);
-        else yh = yl + 1;
-        if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
-        else xh = xl + 1;
-        const float ly = yy - static_cast<float>(yl), lx = x - static_cast<float>(xl);
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-        float v1[8], v2[8], v3[8], v4[8];
-        load8(feat + (static_cast<size_t>(yl) * lv.W + xl) * lv.ld + lane * 8, v1);
-        load8(feat + (static_cast<size_t>(yl) * lv.W + xh) * lv.ld + lane * 8, v2);
-        load8(feat + (static_cast<size_t>(yh) * lv.W + xl) * lv.ld + lane * 8, v3);
-        load8(feat + (static_cast<size_t>(yh) * lv.W + xh) * lv.ld + lane * 8, v4);
+      float y = sample_y(iy);
+      if (y < -1.0f || y > fh) continue;
+      if (y <= 0.f) y = 0.f;
+      int yl = static_cast<int>(y), yh;
+      if (yl >= lv.H - 1) yh = yl = lv.H - 1, y = static_cast<float>(yl);
+      else yh = yl + 1;
+      const float ly = y - static_cast<float>(yl), hy = 1.f - ly;
+      if (rlo + lane == yl) WY += hy;
+      if (rlo + lane == yh) WY += ly;
+    }
+    for (int ix = 0; ix < gw; ++ix) {
+      float x = sample_x(ix);
+      if (x < -1.0f || x > fw) continue;
+      if (x <= 0.f) x = 0.f;
+      int xl = static_cast<int>(x), xh;
+      if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
+      else xh = xl + 1;
+      const float lx = x - static_cast<float>(xl), hx = 1.f - lx;
+      if (clo + lane == xl) WX += hx;
+      if (clo + lane == xh) WX += lx;
+    }
+    const int ncols = chi - clo + 1;
+    for (int rr = 0; rr <= rhi - rlo; ++rr) {
+      const float wy = __shfl_sync(0xffffffffu, WY, rr);
+      if (wy == 0.f) continue;
+      const T* rowp = feat + (static_cast<size_t>(rlo + rr) * lv.W + clo) * lv.ld + lane * 8;
+      for (int cc = 0; cc < ncols; cc += 2) {
+        const float wa = wy * __shfl_sync(0xffffffffu, WX, cc);
+        const float wb = (cc + 1 < ncols) ? wy * __shfl_sync(0xffffffffu, WX, (cc + 1) & 31) : 0.f;
+        float va[8], vb[8];
+        if (wa != 0.f) load8(rowp + static_cast<size_t>(cc) * lv.ld, va);
+        if (wb != 0.f) load8(rowp + static_cast<size_t>(cc + 1) * lv.ld, vb);
+        if (wa != 0.f) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (((w1 * v1[j] + w2 * v2[j]) + w3 * v3[j]) + w4 * v4[j]);
+          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + wa * va[j];
+        }
+        if (wb != 0.f) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + wb * vb[j];
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] = acc[j] / count;
-      if (sizeof(T) == 4) {
-        uint32_t q;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(acc[j]));
-        acc[j] = __uint_as_float(q);
-      }
+  } else {
+    for (int s0 = 0; s0 < ns; s0 += 2) {
+      RoiSample<T> A, Bs;
+      A.fetch(feat, lv.H, lv.W, lv.ld, lane, sample_y(s0 / gw), sample_x(s0 % gw));
+      Bs.ok = false;
+      if (s0 + 1 < ns) Bs.fetch(feat, lv.H, lv.W, lv.ld, lane, sample_y((s0 + 1) / gw), sample_x((s0 + 1) % gw));
+      A.accumulate(acc);
+      Bs.accumulate(acc);
     }
-    store8(out + (static_cast<size_t>(r) * S * S + bin) * ldo + lane * 8, acc);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = acc[j] / count;
+    if (sizeof(T) == 4) {
+      uint32_t q;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(acc[j]));
+      acc[j] = __uint_as_float(q);
+    }
+  }
+  store8(out + (static_cast<size_t>(r) * S * S + ph * S + pw) * ldo + lane * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -442,7 +679,8 @@ __global__ void __launch_bounds__(1024, 1) k_detections(const MrcnnSlots* __rest
                                                         const float* __restrict__ box_out, int ldb,
                                                         const float* __restrict__ prop_boxes, const int* __restrict__ prop_count,
                                                         float* __restrict__ det_boxes, float* __restrict__ det_scores,
-                                                        int* __restrict__ det_classes, int* __restrict__ det_count, int cap) {
+                                                        int* __restrict__ det_classes, int* __restrict__ det_count, int cap,
+                                                        float4* __restrict__ cand_boxes, int* __restrict__ cand_cls) {
   extern __shared__ __align__(16) unsigned long long dkeys[];  // [cap]
   __shared__ int s_n;
   __shared__ float4 kbox[128];
@@ -475,39 +713,59 @@ __global__ void __launch_bounds__(1024, 1) k_detections(const MrcnnSlots* __rest
   for (int i = n + tid; i < npow; i += blockDim.x) dkeys[i] = 0ull;
   __syncthreads();
   if (npow > 1) bitonic_desc(dkeys, npow);
-  // greedy per-class NMS by warp 0, candidates in score order
+  // decode + clip every candidate in parallel (score order) into the scratch list
+  float4* cb = cand_boxes + static_cast<size_t>(b) * cap;
+  int* cc = cand_cls + static_cast<size_t>(b) * cap;
+  for (int c = tid; c < n; c += blockDim.x) {
+    const unsigned long long kk = dkeys[c];
+    const int flat = static_cast<int>(0xffffffffu - static_cast<uint32_t>(kk & 0xffffffffull));
+    const int r = flat / K, cls = flat - r * K;
+    const float* row = box_out + (static_cast<size_t>(b) * post_topk + r) * ldb;
+    const float* pb = prop_boxes + (static_cast<size_t>(b) * post_topk + r) * 4;
+    const float anchor[4] = {pb[0], pb[1], pb[2], pb[3]};
+    const float* d = row + (K + 1) + cls * 4;
+    float o[4];
+    decode_box(anchor, d[0], d[1], d[2], d[3], 10.f, 10.f, 5.f, 5.f, o);
+    // (valid_mask of the reference drops whole rows with a non-finite box of ANY class; a non-finite decoded box
+    // here can only come from non-finite deltas, which also poison that row's other classes)
+    const bool finite_box = isfinite(o[0]) && isfinite(o[1]) && isfinite(o[2]) && isfinite(o[3]);
+    cb[c] = make_float4(clampf(o[0], 0.f, img_w), clampf(o[1], 0.f, img_h), clampf(o[2], 0.f, img_w), clampf(o[3], 0.f, img_h));
+    cc[c] = finite_box ? cls : -1;
+  }
+  __syncthreads();
+  // greedy per-class NMS in score order by warp 0, 32 candidates at a time: each lane first tests its candidate
+  // against the boxes kept so far, then the chunk is resolved in order with shuffles.
   if (tid < 32) {
     const int lane = tid;
     int nk = 0;
-    for (int c = 0; c < n && nk < max_det; ++c) {
-      const unsigned long long kk = dkeys[c];
-      const int flat = static_cast<int>(0xffffffffu - static_cast<uint32_t>(kk & 0xffffffffull));
-      const int r = flat / K, cls = flat - r * K;
-      const float* row = box_out + (static_cast<size_t>(b) * post_topk + r) * ldb;
-      const float* pb = prop_boxes + (static_cast<size_t>(b) * post_topk + r) * 4;
-      const float anchor[4] = {pb[0], pb[1], pb[2], pb[3]};
-      const float* d = row + (K + 1) + cls * 4;
-      float o[4];
-      decode_box(anchor, d[0], d[1], d[2], d[3], 10.f, 10.f, 5.f, 5.f, o);
-      const bool finite_box = isfinite(o[0]) && isfinite(o[1]) && isfinite(o[2]) && isfinite(o[3]);
-      const float4 bx = make_float4(clampf(o[0], 0.f, img_w), clampf(o[1], 0.f, img_h), clampf(o[2], 0.f, img_w),
-                                    clampf(o[3], 0.f, img_h));
-      bool hit = false;
-      for (int j = lane; j < nk; j += 32)
-        if (kcls[j] == cls && iou_gt(kbox[j], bx, nms_thr)) hit = true;
-      // (valid_mask of the reference drops whole rows with a non-finite box of ANY class; a non-finite
-      // decoded box here can only come from non-finite deltas, which also poison that row's other classes)
-      if (!__any_sync(0xffffffffu, hit) && finite_box) {
-        if (lane == 0) {
-          kbox[nk] = bx, kcls[nk] = cls;
-          float* ob = det_boxes + (static_cast<size_t>(b) * max_det + nk) * 4;
-          ob[0] = bx.x, ob[1] = bx.y, ob[2] = bx.z, ob[3] = bx.w;
-          det_scores[static_cast<size_t>(b) * max_det + nk] = fkey_inv(static_cast<uint32_t>(kk >> 32));
-          det_classes[static_cast<size_t>(b) * max_det + nk] = cls;
-        }
-        ++nk;
-        __syncwarp();
+    for (int c0 = 0; c0 < n && nk < max_det; c0 += 32) {
+      const int c = c0 + lane;
+      float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cls = -1;
+      if (c < n) bx = cb[c], cls = cc[c];
+      bool alive = cls >= 0;
+      for (int j = 0; j < nk && alive; ++j)
+        if (kcls[j] == cls && iou_gt(kbox[j], bx, nms_thr)) alive = false;
+      for (int j = 0; j < 32; ++j) {
+        const bool j_alive = __shfl_sync(0xffffffffu, alive ? 1 : 0, j) != 0;
+        if (!j_alive) continue;  // warp-uniform
+        float4 o;
+        o.x = __shfl_sync(0xffffffffu, bx.x, j), o.y = __shfl_sync(0xffffffffu, bx.y, j);
+        o.z = __shfl_sync(0xffffffffu, bx.z, j), o.w = __shfl_sync(0xffffffffu, bx.w, j);
+        const int ocls = __shfl_sync(0xffffffffu, cls, j);
+        if (lane > j && alive && cls == ocls && iou_gt(o, bx, nms_thr)) alive = false;
       }
+      const unsigned keep = __ballot_sync(0xffffffffu, alive);
+      const int pos = nk + __popc(keep & ((1u << lane) - 1u));
+      if (alive && pos < max_det) {
+        kbox[pos] = bx, kcls[pos] = cls;
+        float* ob = det_boxes + (static_cast<size_t>(b) * max_det + pos) * 4;
+        ob[0] = bx.x, ob[1] = bx.y, ob[2] = bx.z, ob[3] = bx.w;
+        det_scores[static_cast<size_t>(b) * max_det + pos] = fkey_inv(static_cast<uint32_t>(dkeys[c] >> 32));
+        det_classes[static_cast<size_t>(b) * max_det + pos] = cls;
+      }
+      nk = min(nk + __popc(keep), max_det);
+      __syncwarp();
     }
     if (lane == 0) det_count[b] = nk;
   }
@@ -539,54 +797,87 @@ __global__ void k_compact_dets(int B, int max_det, const float* __restrict__ det
 }
 
 // ---------------------------------------------------------------------------------------------------
-// detector_postprocess + paste_masks_in_image + the accumulation loop of segmentation.py:47-62, one thread
-// per output pixel: for every detection of the frame that passes the score gates, the 28x28 mask
-// probabilities are bilinearly sampled (grid_sample, align_corners=False, zero padding) at the pixel centre
-// mapped into the detection's box; >= threshold adds 1 to the class channel.
-__global__ void __launch_bounds__(256) k_paste_accumulate(const MrcnnSlots* __restrict__ slots, int H, int W, int K, int max_det,
-                                                          float sx, float sy, float mask_thr, const float* __restrict__ det_scores,
-                                                          const int* __restrict__ det_count, const int* __restrict__ mroi_total,
-                                                          const float* __restrict__ mroi_boxes, const int* __restrict__ mroi_cls,
-                                                          const float* __restrict__ mask_logits) {
-  const int b = blockIdx.z;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
-  __shared__ float4 sbox[128];
-  __shared__ int scls[128];
-  __shared__ int sroi[128];
-  __shared__ int s_n;
+// detector_postprocess + paste_masks_in_image + the accumulation loop of segmentation.py:47-62.
+//   k_paste_prepare  per frame: zero the output stack, apply the score gates, rescale the boxes to the camera frame,
+//                    clip, drop empty -> active list;
+//   k_paste_dets     kPasteSplit CTAs per active detection walk the pixels of its box (+1 px halo): the 28x28 mask
+//                    probabilities (sigmoid once per CTA into smem) are bilinearly sampled (grid_sample,
+//                    align_corners=False, zero padding) at the pixel centre; >= threshold adds 1 to the class channel
+//                    (atomicAdd of small integers in fp32: exact and order-independent).
+constexpr int kPasteSplit = 4;
+
+__global__ void __launch_bounds__(256) k_paste_prepare(const MrcnnSlots* __restrict__ slots, int H, int W, int K, int max_det,
+                                                       float sx, float sy, const float* __restrict__ det_scores,
+                                                       const int* __restrict__ det_count, const int* __restrict__ mroi_total,
+                                                       const float* __restrict__ mroi_boxes, const int* __restrict__ mroi_cls,
+                                                       float4* __restrict__ act_box, int* __restrict__ act_cls,
+                                                       int* __restrict__ act_roi, int* __restrict__ act_n) {
+  const int b = blockIdx.y;
+  // zero this frame's output stack (grid.x CTAs share the work)
+  float4* out4 = reinterpret_cast<float4*>(slots->sem_out + static_cast<size_t>(b) * H * W * (K + 1));
+  const size_t n4 = static_cast<size_t>(H) * W * (K + 1) / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  // gates + rescale + clip + drop empty, order preserved (one warp, ballot compaction)
+  const int lane = threadIdx.x;
   const int n_det = det_count[b];
   const int start = mroi_total[1 + b];
-  if (threadIdx.x == 0) {
-    // gates + rescale to the camera frame + clip + drop empty (serial: n_det <= 100, negligible)
-    const float sem_thr = slots->sem_thr, goal_thr = slots->goal_thr;
-    const int goal = slots->goal_cat ? slots->goal_cat[b] : -1;
-    int n = 0;
-    for (int i = 0; i < n_det; ++i) {
-      const int cls = mroi_cls[start + i];
+  const float sem_thr = slots->sem_thr, goal_thr = slots->goal_thr;
+  const int goal = slots->goal_cat ? slots->goal_cat[b] : -1;
+  int n = 0;
+  for (int i0 = 0; i0 < n_det; i0 += 32) {
+    const int i = i0 + lane;
+    bool ok = false;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cls = -1;
+    if (i < n_det) {
+      cls = mroi_cls[start + i];
       const float score = det_scores[static_cast<size_t>(b) * max_det + i];
       const float* pb = mroi_boxes + static_cast<size_t>(start + i) * 4;
-      float4 bx = make_float4(pb[0] * sx, pb[1] * sy, pb[2] * sx, pb[3] * sy);
+      bx = make_float4(pb[0] * sx, pb[1] * sy, pb[2] * sx, pb[3] * sy);
       bx.x = clampf(bx.x, 0.f, static_cast<float>(W)), bx.z = clampf(bx.z, 0.f, static_cast<float>(W));
       bx.y = clampf(bx.y, 0.f, static_cast<float>(H)), bx.w = clampf(bx.w, 0.f, static_cast<float>(H));
-      if (!((bx.z - bx.x) > 0.f && (bx.w - bx.y) > 0.f)) continue;
-      if (cls < 0 || cls >= K) continue;
-      if (score < sem_thr) continue;
-      if (cls == goal && score < goal_thr) continue;
-      sbox[n] = bx, scls[n] = cls, sroi[n] = start + i;
-      ++n;
+      ok = (bx.z - bx.x) > 0.f && (bx.w - bx.y) > 0.f && cls >= 0 && cls < K && !(score < sem_thr) &&
+           !(cls == goal && score < goal_thr);
     }
-    s_n = n;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int pos = n + __popc(m & ((1u << lane) - 1u));
+      act_box[b * max_det + pos] = bx, act_cls[b * max_det + pos] = cls, act_roi[b * max_det + pos] = start + i;
+    }
+    n += __popc(m);
+  }
+  if (lane == 0) act_n[b] = n;
+}
+
+__global__ void __launch_bounds__(256) k_paste_dets(const MrcnnSlots* __restrict__ slots, int H, int W, int K, int max_det,
+                                                    float mask_thr, const float4* __restrict__ act_box,
+                                                    const int* __restrict__ act_cls, const int* __restrict__ act_roi,
+                                                    const int* __restrict__ act_n, const float* __restrict__ mask_logits) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  if (i >= act_n[b]) return;
+  __shared__ float prob[28 * 28];
+  const float4 bx = act_box[b * max_det + i];
+  const int cls = act_cls[b * max_det + i];
+  const float* ml = mask_logits + static_cast<size_t>(act_roi[b * max_det + i]) * (14 * 14 * 4) * 16 + cls;
+  for (int p = threadIdx.x; p < 28 * 28; p += blockDim.x) {
+    const int Y = p / 28, X = p - Y * 28;
+    const int row = (((Y >> 1) * 14) + (X >> 1)) * 4 + ((Y & 1) << 1) + (X & 1);
+    prob[p] = 1.f / (1.f + expf(-ml[static_cast<size_t>(row) * 16]));
   }
   __syncthreads();
-  if (x >= W) return;
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  const int n = s_n;
-  const float px = static_cast<float>(x) + 0.5f, py = static_cast<float>(y) + 0.5f;
-  for (int i = 0; i < n; ++i) {
-    const float4 bx = sbox[i];
+  // pixels whose centre can map into (-1, 28) mask coordinates: the box widened by one mask cell, +1 px of slack
+  const float cw = (bx.z - bx.x) / 28.f, ch = (bx.w - bx.y) / 28.f;
+  const int xa = max(0, static_cast<int>(floorf(bx.x - cw)) - 1), xb = min(W, static_cast<int>(ceilf(bx.z + cw)) + 1);
+  const int ya = max(0, static_cast<int>(floorf(bx.y - ch)) - 1), yb = min(H, static_cast<int>(ceilf(bx.w + ch)) + 1);
+  const int bw = xb - xa, bh = yb - ya;
+  if (bw <= 0 || bh <= 0) return;
+  float* out = slots->sem_out + static_cast<size_t>(b) * H * W * (K + 1) + cls;
+  const int total = bw * bh;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    const int y = ya + p / bw, x = xa + p % bw;
+    const float px = static_cast<float>(x) + 0.5f, py = static_cast<float>(y) + 0.5f;
     const float gx = (px - bx.x) / (bx.z - bx.x) * 2.f - 1.f;
     const float gy = (py - bx.y) / (bx.w - bx.y) * 2.f - 1.f;
     const float ix = (gx + 1.f) * 14.f - 0.5f, iy = (gy + 1.f) * 14.f - 0.5f;  // ((g + 1) * 28 - 1) / 2
@@ -595,18 +886,10 @@ __global__ void __launch_bounds__(256) k_paste_accumulate(const MrcnnSlots* __re
     const float w = ix - xw, e = 1.f - w, nn = iy - yn, s = 1.f - nn;
     const float wnw = s * e, wne = s * w, wsw = nn * e, wse = nn * w;
     const int X0 = static_cast<int>(xw), Y0 = static_cast<int>(yn);
-    const int cls = scls[i];
-    const float* ml = mask_logits + static_cast<size_t>(sroi[i]) * (14 * 14 * 4) * 16 + cls;
-    auto prob = [&](int Y, int X) -> float {
-      if (X < 0 || X >= 28 || Y < 0 || Y >= 28) return 0.f;
-      const int row = (((Y >> 1) * 14) + (X >> 1)) * 4 + ((Y & 1) << 1) + (X & 1);
-      return 1.f / (1.f + expf(-ml[static_cast<size_t>(row) * 16]));
-    };
-    const float v = ((prob(Y0, X0) * wnw + prob(Y0, X0 + 1) * wne) + prob(Y0 + 1, X0) * wsw) + prob(Y0 + 1, X0 + 1) * wse;
-    if (v >= mask_thr) acc[cls] += 1.f;
+    auto at = [&](int Y, int X) -> float { return (X < 0 || X >= 28 || Y < 0 || Y >= 28) ? 0.f : prob[Y * 28 + X]; };
+    const float v = ((at(Y0, X0) * wnw + at(Y0, X0 + 1) * wne) + at(Y0 + 1, X0) * wsw) + at(Y0 + 1, X0 + 1) * wse;
+    if (v >= mask_thr) atomicAdd(out + (static_cast<size_t>(y) * W + x) * (K + 1), 1.f);
   }
-  float* o = slots->sem_out + ((static_cast<size_t>(b) * H + y) * W + x) * (K + 1);
-  for (int c = 0; c <= K; ++c) o[c] = c < K ? acc[c] : 0.f;
 }
 
 }  // namespace
@@ -647,13 +930,40 @@ void add_subsample2(Net& net, const Tensor& in, const Tensor& out) {
 
 void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
   PN_REQUIRE(meta.pre_topk <= kRpnCap && meta.post_topk >= 1, "rpn: pre_nms_topk exceeds the per-level capacity");
-  const size_t smem = ((sizeof(RpnSmem) + 15) & ~size_t(15)) + static_cast<size_t>(kRpnCap) * 32 * sizeof(uint32_t);
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_rpn_select_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const size_t smem = (sizeof(RpnSmem) + 15) & ~size_t(15);
+  const size_t smem_mask = static_cast<size_t>(kRpnCap) * 32 * sizeof(uint32_t);
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_rpn_sort_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_rpn_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_mask)));
   const int B = m.cfg.B;
   float* lb = m.lvl_boxes;
   float* ls = m.lvl_scores;
   int* lc = m.lvl_count;
-  net.add("rpn_select_nms", [=](cudaStream_t s) { k_rpn_select_nms<<<dim3(kRpnLevels, B), 1024, smem, s>>>(meta, lb, ls, lc); });
+  uint32_t* hist = static_cast<uint32_t*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kHistBins * sizeof(uint32_t)));
+  uint32_t* thr = static_cast<uint32_t*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * sizeof(uint32_t)));
+  int* ncand = static_cast<int*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * sizeof(int)));
+  unsigned long long* cand = static_cast<unsigned long long*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kCandCap * sizeof(unsigned long long)));
+  int max_pix = 0;
+  for (int l = 0; l < kRpnLevels; ++l) max_pix = std::max(max_pix, meta.lv[l].H * meta.lv[l].W);
+  const dim3 scan_grid((max_pix + kPixPerBlock - 1) / kPixPerBlock, kRpnLevels * B);
+  const size_t hist_bytes = static_cast<size_t>(B) * kRpnLevels * kHistBins * sizeof(uint32_t);
+  net.add("rpn_preselect", [=](cudaStream_t s) {
+    PN_CUDA_CHECK(cudaMemsetAsync(hist, 0, hist_bytes, s));
+    k_rpn_hist<<<scan_grid, 256, 0, s>>>(meta, hist);
+    k_rpn_threshold<<<dim3(kRpnLevels, B), 1024, 0, s>>>(meta, hist, thr, ncand);
+    k_rpn_collect<<<scan_grid, 256, 0, s>>>(meta, thr, ncand, cand);
+  });
+  net.launches_per_forward += 4;
+  float4* sbox = static_cast<float4*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kRpnCap * sizeof(float4)));
+  float* sscore = static_cast<float*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kRpnCap * sizeof(float)));
+  int* scount = static_cast<int*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * sizeof(int)));
+  uint32_t* mask_g = static_cast<uint32_t*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kRpnCap * 32 * sizeof(uint32_t)));
+  const float nms_thr = meta.nms_thr;
+  net.add("rpn_sort_decode", [=](cudaStream_t s) { k_rpn_sort_decode<<<dim3(kRpnLevels, B), 1024, smem, s>>>(meta, ncand, cand, sbox, sscore, scount); });
+  net.add("rpn_nms", [=](cudaStream_t s) {
+    k_rpn_mask<<<dim3(kRpnCap / 32, kRpnLevels, B), 256, 0, s>>>(nms_thr, sbox, scount, mask_g);
+    k_rpn_sweep<<<dim3(kRpnLevels, B), 1024, smem_mask, s>>>(sbox, sscore, scount, mask_g, lb, ls, lc);
+  });
+  net.launches_per_forward += 2;
   float* pb = m.prop_boxes;
   float* ps = m.prop_scores;
   int* pi = m.prop_img;
@@ -665,13 +975,13 @@ void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
 
 void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr, DType dt, const float* boxes, const int* img,
                    int nrois, int S, const Tensor& out) {
-  PN_REQUIRE(out.C == 256 && out.dt == dt, "roi_align: 256-channel pyramid expected");
+  PN_REQUIRE(out.C == 256 && out.dt == dt && S <= 14, "roi_align: 256-channel pyramid, at most 14 x 14 bins expected");
   Tensor o = out;
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
-      k_roi_align<__nv_bfloat16><<<nrois, 256, 0, s>>>(pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
+      k_roi_align<__nv_bfloat16><<<dim3(S, nrois), S * 32, 0, s>>>(pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
     else
-      k_roi_align<float><<<nrois, 256, 0, s>>>(pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
+      k_roi_align<float><<<dim3(S, nrois), S * 32, 0, s>>>(pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
   });
   net.launches_per_forward += 1;
 }
@@ -693,9 +1003,11 @@ void add_detections(Net& net, MaskRcnn& m) {
   float* ds = m.det_scores;
   int* dc = m.det_classes;
   int* dn = m.det_count;
+  float4* cand_boxes = static_cast<float4*>(net.arena.alloc(static_cast<size_t>(c.B) * cap * sizeof(float4)));
+  int* cand_cls = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * cap * sizeof(int)));
   net.add("detections", [=](cudaStream_t s) {
     k_detections<<<c.B, 1024, smem, s>>>(slots, c.num_classes, c.post_nms_topk, c.detections, c.box_nms, img_h, img_w, box_out,
-                                         64, pb, pc, db, ds, dc, dn, cap);
+                                         64, pb, pc, db, ds, dc, dn, cap, cand_boxes, cand_cls);
   });
   float* mb = m.mroi_boxes;
   int* mi = m.mroi_img;
@@ -709,6 +1021,7 @@ void add_detections(Net& net, MaskRcnn& m) {
 void add_paste_accumulate(Net& net, MaskRcnn& m) {
   const MrcnnCfg c = m.cfg;
   const MrcnnSlots* slots = m.slots;
+  PN_REQUIRE((static_cast<long long>(c.H) * c.W * (c.num_classes + 1)) % 4 == 0, "paste: frame size must allow float4 stores");
   // boxes[:, 0::2] *= scale_x with the python float cast to fp32 (detector_postprocess)
   const float sx = static_cast<float>(static_cast<double>(c.W) / m.Wn), sy = static_cast<float>(static_cast<double>(c.H) / m.Hn);
   const float* ds = m.det_scores;
@@ -717,11 +1030,18 @@ void add_paste_accumulate(Net& net, MaskRcnn& m) {
   const float* mb = m.mroi_boxes;
   const int* mc = m.mroi_cls;
   const float* ml = m.mask_logits;
-  net.add("paste_accumulate", [=](cudaStream_t s) {
-    k_paste_accumulate<<<dim3((c.W + 255) / 256, c.H, c.B), 256, 0, s>>>(slots, c.H, c.W, c.num_classes, c.detections, sx, sy,
-                                                                       c.mask_thresh, ds, dn, mt, mb, mc, ml);
+  float4* ab = static_cast<float4*>(net.arena.alloc(static_cast<size_t>(c.B) * c.detections * sizeof(float4)));
+  int* ac = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * c.detections * sizeof(int)));
+  int* ar = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * c.detections * sizeof(int)));
+  int* an = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * sizeof(int)));
+  net.add("paste_prepare", [=](cudaStream_t s) {
+    k_paste_prepare<<<dim3(64, c.B), 256, 0, s>>>(slots, c.H, c.W, c.num_classes, c.detections, sx, sy, ds, dn, mt, mb, mc, ab, ac, ar, an);
   });
-  net.launches_per_forward += 1;
+  net.add("paste_dets", [=](cudaStream_t s) {
+    k_paste_dets<<<dim3(kPasteSplit, c.detections, c.B), 256, 0, s>>>(slots, c.H, c.W, c.num_classes, c.detections, c.mask_thresh,
+                                                                     ab, ac, ar, an, ml);
+  });
+  net.launches_per_forward += 2;
 }
 
 }  // namespace pn

@@ -110,6 +110,7 @@ struct Net {
   DType dt = kBF16;
   int num_sms = 148;
   long long launches_per_forward = 0;
+  int last_bn = 0;  // N tile chosen by the most recent add_conv (tuning aid)
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t cap_stream = nullptr;
   int warm_runs = 0;
@@ -153,9 +154,12 @@ inline const HostArray& get_weight(const WeightStore& w, const std::string& name
 // Convolution (conv_host.cu)
 struct ConvSpec {
   int Cin = 0, Cout = 0, R = 1, S = 1, stride = 1, dil = 1, pad = 0;
+  int stride_w = -1, pad_w = -1;  // horizontal stride / padding when they differ from the vertical ones (-1 = same)
   bool relu = false;
   bool out_fp32 = false;
   int force_bn = 0;  // test hook: force the N tile
+  int force_splits = 0;  // test hook: force the split-K factor
+  bool no_split = false;  // never split K (layers whose row count is dynamic keep one CTA per tile)
   bool force_direct_epilogue = false;  // test hook: bypass the TMA-staged epilogue
   // Dynamic row limit: when set, only the first (*m_limit) * m_limit_rows GEMM rows are computed (device-side
   // count of valid ROIs x rows per ROI); tiles beyond are skipped by every warp role.

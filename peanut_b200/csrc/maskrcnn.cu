@@ -84,15 +84,32 @@ void build_maskrcnn(MaskRcnn& m, const WeightStore& w, const MrcnnCfg& cfg, DTyp
   // ---- input: PIL-exact resize, BGR, mean subtraction, zero padding (yaml:26-30, 82-89)
   net.stage("preprocess");
   m.resized_u8 = static_cast<uint8_t*>(A.alloc(static_cast<size_t>(B) * m.Hn * m.Wn * 3));
-  m.input = A.tensor(B, m.Hp, m.Wp, pad_channels(3, dt), dt);
+  m.input = A.tensor(B, m.Hp, m.Wp / 2, 32, dt);
   const float mean_bgr[3] = {103.53f, 116.28f, 123.675f}, std_bgr[3] = {1.f, 1.f, 1.f};
-  add_resize_normalize(net, &m.slots->rgb, B, cfg.H, cfg.W, m.Hn, m.Wn, m.input, m.resized_u8, mean_bgr, std_bgr);
-  net.taps["input"] = m.input;
+  add_resize_pack_stem(net, &m.slots->rgb, B, cfg.H, cfg.W, m.Hn, m.Wn, m.input, m.resized_u8, mean_bgr, std_bgr);
+  net.taps["stem_in"] = m.input;
 
   // ---- ResNet-101 bottom-up, STRIDE_IN_1X1 (yaml:101-112)
   net.stage("backbone");
   const std::string bu = "backbone.bottom_up.";
-  Tensor x = conv_frozen_bn(net, w, bu + "stem.conv1", m.input, spec(3, 64, 7, 2, 3, true));
+  Tensor x;
+  {
+    // 7x7 stride-2 stem as a 7x1 convolution over the tap-packed input (see k_pack_stem): W'[co][r][s*3+c] = W[co][c][r][s]
+    const HostArray& wt = conv_weight(w, bu + "stem.conv1.weight", 64, 3, 7);
+    std::vector<float> wp(static_cast<size_t>(64) * 32 * 7, 0.f);
+    for (int co = 0; co < 64; ++co)
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s) wp[(static_cast<size_t>(co) * 32 + (s * 3 + c)) * 7 + r] = wt.data[((static_cast<size_t>(co) * 3 + c) * 7 + r) * 7 + s];
+    std::vector<float> scale, bias;
+    fold_bn(w, bu + "stem.conv1.norm", 64, scale, bias, 1e-5f);
+    ConvSpec s7;
+    s7.Cin = 32, s7.Cout = 64, s7.R = 7, s7.S = 1, s7.stride = 2, s7.stride_w = 1, s7.dil = 1, s7.pad = 3, s7.pad_w = 0, s7.relu = true;
+    x = A.tensor(B, conv_out(m.Hp, 7, 2, 1, 3), m.Wp / 2, 64, dt);
+    add_conv(net, bu + "stem.conv1", m.input, x, wp.data(), scale.data(), bias.data(), s7);
+    // the packed channels 21..31 are zero padding: report the 7x7x3 FLOPs, not the packed K
+    net.op_flops.back() = 2.0 * static_cast<double>(x.pixels()) * 64 * 147;
+  }
   {
     Tensor p = A.tensor(B, conv_out(x.H, 3, 2, 1, 1), conv_out(x.W, 3, 2, 1, 1), x.C, dt);
     add_maxpool3x3s2(net, x, p);

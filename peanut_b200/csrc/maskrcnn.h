@@ -82,7 +82,7 @@ struct MaskRcnn {
   int* mroi_cls = nullptr;              // [B*detections]
   int* mroi_total = nullptr;            // [1] + det_start [B] behind it
   float* mask_logits = nullptr;         // fp32 [B*detections*14*14*4][16]
-  Tensor input;                         // NHWC network input
+  Tensor input;                         // stem input [B, Hp, Wp/2, 32]: 7 horizontal taps x BGR packed into channels
   Pyramid pyramid{};
   float* stage_sem = nullptr;           // staging for the host entry point
   uint8_t* stage_rgb = nullptr;
@@ -93,7 +93,7 @@ void resized_shape(int h, int w, int min_size, int max_size, int& newh, int& new
 
 // preproc.cu
 void pil_bilinear_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk, int& ksize);
-void add_resize_normalize(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
+void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
                           uint8_t* resized_u8, const float mean_bgr[3], const float std_bgr[3]);
 void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, int E, int H, int W, int ds, int h, int w,
                      int nsem, float min_d, float max_d, float* obs, cudaStream_t s);

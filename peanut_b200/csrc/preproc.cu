@@ -63,58 +63,79 @@ __device__ __forceinline__ int clip8(int v) {
 }
 
 // One thread per output pixel (all 3 channels).  hb/hk, vb/vk: bounds + coefficients of the two passes.
-template <typename T>
-__global__ void k_resize_normalize(const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, int Hp, int Wp,
-                                   int Cpad, const int* __restrict__ hb, const int* __restrict__ hk, int hks,
-                                   const int* __restrict__ vb, const int* __restrict__ vk, int vks, float3 mean_bgr,
-                                   float3 std_bgr, T* __restrict__ out, uint8_t* __restrict__ resized_u8) {
+// Output: resized uint8 BGR [B, Hn, Wn, 3].
+__global__ void k_resize_u8(const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const int* __restrict__ hb,
+                            const int* __restrict__ hk, int hks, const int* __restrict__ vb, const int* __restrict__ vk, int vks,
+                            uint8_t* __restrict__ resized_u8) {
   const uint8_t* rgb = *rgb_slot;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Hp * Wp;
+  const long long total = static_cast<long long>(B) * Hn * Wn;
   if (idx >= total) return;
-  const int x = static_cast<int>(idx % Wp);
-  const long long t = idx / Wp;
+  const int x = static_cast<int>(idx % Wn);
+  const long long t = idx / Wn;
+  const int y = static_cast<int>(t % Hn);
+  const int b = static_cast<int>(t / Hn);
+  const int x0 = hb[2 * x], xn = hb[2 * x + 1];
+  const int y0 = vb[2 * y], yn = vb[2 * y + 1];
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int j = 0; j < yn; ++j) {
+    const uint8_t* row = rgb + (static_cast<size_t>(b) * H + (y0 + j)) * W * 3;
+    int h[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int i = 0; i < xn; ++i) {
+      const int k = hk[x * hks + i];
+      const uint8_t* px = row + (x0 + i) * 3;
+      h[0] += px[0] * k, h[1] += px[1] * k, h[2] += px[2] * k;
+    }
+    const int kv = vk[y * vks + j];
+    acc[0] += clip8(h[0]) * kv, acc[1] += clip8(h[1]) * kv, acc[2] += clip8(h[2]) * kv;
+  }
+  uint8_t* o = resized_u8 + idx * 3;
+  o[0] = static_cast<uint8_t>(clip8(acc[2])), o[1] = static_cast<uint8_t>(clip8(acc[1])), o[2] = static_cast<uint8_t>(clip8(acc[0]));
+}
+
+// Normalise + zero-pad + pack the 7 horizontal taps of the stride-2 7x7 stem convolution into channels:
+//   out[b, y, xo, s*3 + c] = (bgr[b, y, 2*xo - 3 + s, c] - mean[c]) / std[c]   (0 outside the resized image),
+// channels 21..31 zero.  The stem then runs as a 7x1 convolution with 32 input channels (K = 224 instead of the
+// 784 a 16-channel-padded 7x7 im2col would need) at stride (2, 1), padding (3, 0).
+template <typename T>
+__global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int Hn, int Wn, int Hp, int Wo, float3 mean_bgr,
+                            float3 std_bgr, T* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Hp * Wo;
+  if (idx >= total) return;
+  const int xo = static_cast<int>(idx % Wo);
+  const long long t = idx / Wo;
   const int y = static_cast<int>(t % Hp);
   const int b = static_cast<int>(t / Hp);
-  float v[8];
+  float v[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (y < Hn && x < Wn) {
-    const int x0 = hb[2 * x], xn = hb[2 * x + 1];
-    const int y0 = vb[2 * y], yn = vb[2 * y + 1];
-    int acc[3] = {1 << 21, 1 << 21, 1 << 21};
-    for (int j = 0; j < yn; ++j) {
-      const uint8_t* row = rgb + (static_cast<size_t>(b) * H + (y0 + j)) * W * 3;
-      int h[3] = {1 << 21, 1 << 21, 1 << 21};
-      for (int i = 0; i < xn; ++i) {
-        const int k = hk[x * hks + i];
-        const uint8_t* px = row + (x0 + i) * 3;
-        h[0] += px[0] * k, h[1] += px[1] * k, h[2] += px[2] * k;
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  if (y < Hn) {
+    const uint8_t* row = resized_u8 + (static_cast<size_t>(b) * Hn + y) * Wn * 3;
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      const int x = 2 * xo - 3 + s;
+      if (x >= 0 && x < Wn) {
+        v[s * 3] = (static_cast<float>(row[x * 3]) - mean_bgr.x) / std_bgr.x;
+        v[s * 3 + 1] = (static_cast<float>(row[x * 3 + 1]) - mean_bgr.y) / std_bgr.y;
+        v[s * 3 + 2] = (static_cast<float>(row[x * 3 + 2]) - mean_bgr.z) / std_bgr.z;
       }
-      const int kv = vk[y * vks + j];
-      acc[0] += clip8(h[0]) * kv, acc[1] += clip8(h[1]) * kv, acc[2] += clip8(h[2]) * kv;
     }
-    const int r = clip8(acc[0]), g = clip8(acc[1]), bl = clip8(acc[2]);
-    if (resized_u8 != nullptr) {
-      uint8_t* o = resized_u8 + ((static_cast<size_t>(b) * Hn + y) * Wn + x) * 3;
-      o[0] = static_cast<uint8_t>(bl), o[1] = static_cast<uint8_t>(g), o[2] = static_cast<uint8_t>(r);
-    }
-    v[0] = (static_cast<float>(bl) - mean_bgr.x) / std_bgr.x;
-    v[1] = (static_cast<float>(g) - mean_bgr.y) / std_bgr.y;
-    v[2] = (static_cast<float>(r) - mean_bgr.z) / std_bgr.z;
     if (sizeof(T) == 4) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < 21; ++j) {
         uint32_t q;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v[j]));
         v[j] = __uint_as_float(q);
       }
     }
   }
-  T* o = out + idx * Cpad;
-  store8(o, v);
-  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int c0 = 8; c0 < Cpad; c0 += 8) store8(o + c0, z);
+  T* o = out + idx * 32;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    const float w[8] = {v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3], v[c0 + 4], v[c0 + 5], v[c0 + 6], v[c0 + 7]};
+    store8(o + c0, w);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -166,9 +187,10 @@ __global__ void k_make_obs(const float* __restrict__ depth_all, const uint8_t* _
 
 }  // namespace
 
-void add_resize_normalize(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
+void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
                           uint8_t* resized_u8, const float mean_bgr[3], const float std_bgr[3]) {
-  PN_REQUIRE(out.ld == out.C && out.C % 8 == 0 && out.C >= 8, "resize_normalize: output must be dense, >= 8 channels");
+  PN_REQUIRE(out.ld == 32 && out.C == 32, "pack_stem: output must be a dense 32-channel tensor");
+  PN_REQUIRE(out.W * 2 >= Wn && out.H >= Hn, "pack_stem: output too small");
   std::vector<int> hb, hk, vb, vk;
   int hks = 0, vks = 0;
   pil_bilinear_coeffs(W, Wn, hb, hk, hks);
@@ -178,18 +200,23 @@ void add_resize_normalize(Net& net, const uint8_t* const* rgb_slot, int B, int H
   const int* d_vb = net.arena.upload(vb);
   const int* d_vk = net.arena.upload(vk);
   const float3 mean = make_float3(mean_bgr[0], mean_bgr[1], mean_bgr[2]);
-  const float3 inv = make_float3(std_bgr[0], std_bgr[1], std_bgr[2]);
-  const long long total = out.pixels();
+  const float3 sd = make_float3(std_bgr[0], std_bgr[1], std_bgr[2]);
   const int threads = 256;
-  const int blocks = static_cast<int>((total + threads - 1) / threads);
-  Tensor o = out;
-  net.add("resize_normalize", [=](cudaStream_t s) {
-    if (o.dt == kBF16)
-      k_resize_normalize<__nv_bfloat16><<<blocks, threads, 0, s>>>(rgb_slot, B, H, W, Hn, Wn, o.H, o.W, o.C, d_hb, d_hk, hks, d_vb, d_vk, vks, mean, inv, static_cast<__nv_bfloat16*>(o.ptr), resized_u8);
-    else
-      k_resize_normalize<float><<<blocks, threads, 0, s>>>(rgb_slot, B, H, W, Hn, Wn, o.H, o.W, o.C, d_hb, d_hk, hks, d_vb, d_vk, vks, mean, inv, static_cast<float*>(o.ptr), resized_u8);
+  const long long total1 = static_cast<long long>(B) * Hn * Wn;
+  const int blocks1 = static_cast<int>((total1 + threads - 1) / threads);
+  net.add("resize_u8", [=](cudaStream_t s) {
+    k_resize_u8<<<blocks1, threads, 0, s>>>(rgb_slot, B, H, W, Hn, Wn, d_hb, d_hk, hks, d_vb, d_vk, vks, resized_u8);
   });
-  net.launches_per_forward += 1;
+  const long long total2 = out.pixels();
+  const int blocks2 = static_cast<int>((total2 + threads - 1) / threads);
+  Tensor o = out;
+  net.add("pack_stem", [=](cudaStream_t s) {
+    if (o.dt == kBF16)
+      k_pack_stem<__nv_bfloat16><<<blocks2, threads, 0, s>>>(resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr));
+    else
+      k_pack_stem<float><<<blocks2, threads, 0, s>>>(resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<float*>(o.ptr));
+  });
+  net.launches_per_forward += 2;
 }
 
 void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, int E, int H, int W, int ds, int h, int w,

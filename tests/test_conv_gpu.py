@@ -36,7 +36,13 @@ CASES = [
     (1, 256, 24, 24, 512, 1, 2, 1, 0, 0x1000 | 128),
     (1, 64, 36, 36, 48, 1, 1, 1, 0, 0),      # Cout 48: partial 128-byte chunk clipped by the TMA store
     (6, 512, 30, 30, 2048, 1, 1, 1, 0, 0),   # conv3-like: many chunks per tile, residual ring wraps
+    # split-K (force_bn bits 16..23 = splits): partial tiles meet in the fp32 workspace, last CTA runs the epilogue
+    (1, 1024, 9, 9, 512, 3, 1, 1, 1, (4 << 16) | 128),   # 144 K blocks in 4 splits, 3x3 taps cross split boundaries
+    (3, 2048, 6, 6, 512, 1, 1, 1, 0, (3 << 16) | 64),    # 1x1, 32 K blocks in 3 uneven splits (11, 11, 10)
+    (2, 512, 25, 34, 512, 3, 1, 1, 1, (8 << 16) | 256),  # res5.conv2 at B=2: 14 m-tiles x 2 n-tiles x 8 splits
+    (1, 256, 10, 10, 24, 3, 1, 1, 1, (2 << 16) | 32),    # narrow output (24 -> 32-wide tile) through the workspace
 ]
+SPLIT_CASES = [c for c in CASES if c[9] >> 16]
 
 
 def _run(ctx, case, precision, with_res=True):
@@ -75,12 +81,20 @@ def test_conv_bf16(ctx, case):
     assert (y - ref).abs().mean().item() <= 2e-3 * scale
 
 
-@pytest.mark.parametrize("case", CASES[:12], ids=[str(c) for c in CASES[:12]])
+@pytest.mark.parametrize("case", CASES[:12] + SPLIT_CASES, ids=[str(c) for c in CASES[:12] + SPLIT_CASES])
 def test_conv_tf32(ctx, case):
     y, ref = _run(ctx, case, _lib.PN_TF32)
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-6
     assert err <= 3e-3 * scale, f"max abs err {err} vs scale {scale}"
+
+
+def test_split_k_workspace_is_left_clean(ctx):
+    """Two different inputs through the same split-K configuration, twice each: results must not depend on history."""
+    case = SPLIT_CASES[0]
+    a1, ref1 = _run(ctx, case, _lib.PN_BF16)
+    a2, ref2 = _run(ctx, case, _lib.PN_BF16)
+    assert torch.equal(a1, a2)
 
 
 def test_conv_no_epilogue_extras(ctx):

@@ -71,10 +71,15 @@ def test_resize_is_pil_exact_and_input_normalised(eng_tf32, frame, ocfg, otaps):
     ref = np.asarray(Image.fromarray(np.ascontiguousarray(frame[:, :, ::-1])).resize((wn, hn), Image.BILINEAR))
     got = e.read_tap("resized_u8", (1, hn, wn, 3), torch.uint8).cpu().numpy()[0]
     assert np.array_equal(got, ref), f"{(got != ref).sum()} resized pixels differ from PIL"
-    x = e.read_tap("input", (1, 3, hp, wp)).cpu()
-    # stored as tf32 (10-bit mantissa, round to nearest): |err| <= 2^-11 * 128
-    assert (x - otaps["input"]).abs().max().item() <= 0.0626
-    assert (x[:, :, hn:, :] == 0).all() and (x[:, :, :, wn:] == 0).all()
+    # the stem input packs the 7 horizontal taps of the stride-2 7x7 stem into channels:
+    #   t[b, s*3 + c, y, xo] = input[b, c, y, 2*xo - 3 + s]  (0 outside), channels 21..31 zero
+    t = e.read_tap("stem_in", (1, 32, hp, wp // 2)).cpu()
+    ref = torch.nn.functional.pad(otaps["input"], (3, 3))            # [1, 3, hp, wp + 6]
+    for s in range(7):
+        want = ref[:, :, :, s:s + wp:2]                               # x = 2*xo - 3 + s  <=>  padded index 2*xo + s
+        # stored as tf32 (10-bit mantissa, round to nearest): |err| <= 2^-11 * 128
+        assert (t[:, 3 * s:3 * s + 3] - want).abs().max().item() <= 0.0626, f"tap {s}"
+    assert (t[:, 21:] == 0).all() and (t[:, :, hn:, :] == 0).all()
 
 
 def test_backbone_fpn_rpn_head_tf32(eng_tf32, otaps):

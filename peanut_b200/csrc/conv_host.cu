@@ -75,38 +75,52 @@ CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pa
   return m;
 }
 
-// Automatic split-K stays off until the reduction no longer goes through L2 atomics (measured 10x slower than the
-// un-split layer on B200: ~30 G fp32 red/s device-wide); the forced path is kept for the parity tests.
-constexpr bool kAutoSplitK = false;
+// Automatic split-K (cluster reduce-scatter over distributed shared memory) for layers with too few tiles to fill the GPU.
+constexpr bool kAutoSplitK = true;
 
 struct ConvMaps {
   CUtensorMap a, b, out, res;
 };
 
-template <typename T, int BN>
+template <typename T, int BN, bool kSplit>
 void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    PN_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PN_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<T, BN, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kNumThreads), cfg.dynamicSmemBytes = smem, cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, BN>, tm.a, tm.b, tm.out, tm.res, p));
+  if (kSplit) {  // one thread-block cluster per output tile
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = p.splits, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, BN, kSplit>, tm.a, tm.b, tm.out, tm.res, p));
 }
 
 template <typename T>
 void launch_conv_bn(int bn, const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
+  if (p.splits > 1) {
+    switch (bn) {
+      case 32: launch_conv<T, 32, true>(tm, p, grid, smem, s); break;
+      case 64: launch_conv<T, 64, true>(tm, p, grid, smem, s); break;
+      case 128: launch_conv<T, 128, true>(tm, p, grid, smem, s); break;
+      case 256: launch_conv<T, 256, true>(tm, p, grid, smem, s); break;
+      default: PN_REQUIRE(false, "unsupported N tile");
+    }
+    return;
+  }
   switch (bn) {
-    case 32: launch_conv<T, 32>(tm, p, grid, smem, s); break;
-    case 64: launch_conv<T, 64>(tm, p, grid, smem, s); break;
-    case 128: launch_conv<T, 128>(tm, p, grid, smem, s); break;
-    case 256: launch_conv<T, 256>(tm, p, grid, smem, s); break;
+    case 32: launch_conv<T, 32, false>(tm, p, grid, smem, s); break;
+    case 64: launch_conv<T, 64, false>(tm, p, grid, smem, s); break;
+    case 128: launch_conv<T, 128, false>(tm, p, grid, smem, s); break;
+    case 256: launch_conv<T, 256, false>(tm, p, grid, smem, s); break;
     default: PN_REQUIRE(false, "unsupported N tile");
   }
 }
@@ -184,21 +198,24 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     double best = 1e30;
     for (int cand : {256, 128, 64, 32}) {
       if (sp.force_bn ? cand != (sp.force_bn & 0x3ff) : (cand > cout32 || cout32 % cand != 0)) continue;
-      for (int s : {1, 2, 3, 4, 6, 8, 12, 16}) {
+      for (int s : {1, 2, 4, 8}) {
         if (sp.force_splits ? s != sp.force_splits : (s > 1 && (sp.no_split || !kAutoSplitK || kblocks_total / s < 4))) continue;
         if (s > kblocks_total) continue;
         const int kbs = (kblocks_total + s - 1) / s;
         if (s > 1 && kbs * (s - 1) >= kblocks_total) continue;  // the last split would be empty
+        // cluster split-K: each rank finishes cand / s columns in 8-column units, and the fp32 partial tile is parked
+        // in the operand ring (at most 8 stages deep)
+        if (s > 1 && ((cand / s) % 8 != 0 || sw != 128 || 8 * (kBlockM + cand) * sw < kBlockM * cand * 4)) continue;
         const double work = static_cast<double>(m_tiles) * ((cout32 + cand - 1) / cand) * s;
         const double active = std::min<double>(work, net.num_sms);
-        const double waves = std::ceil(work / net.num_sms);
+        const double waves = std::ceil(work / (s > 1 ? 128.0 : net.num_sms));  // clusters cannot use every SM of a GPC
         const double bytes = static_cast<double>(kbs) * block_k * es * (kBlockM + cand);
         const double t_mem = bytes / std::min(125e9, 14e12 / active);
         const double t_mma = static_cast<double>(kbs) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
-        const double t_epi = 0.25e-6 * cand / 32.0;  // un-overlapped epilogue of the last tile
-        // split-K: red.add of the partial tile, fence + ticket, read-back by the last CTA
-        const double t_red = s > 1 ? 1.5e-6 + 2.0 * kBlockM * cand * 4.0 / 100e9 : 0.0;
-        const double t = waves * std::max(t_mem, t_mma) + t_epi + t_red;
+        const double t_epi = 0.25e-6 * cand / 32.0 / s;  // un-overlapped epilogue of the last tile
+        // split-K: park the partial tile in shared memory, cluster barrier, read one slice of every peer's tile
+        const double t_red = s > 1 ? 1.5e-6 + 2.0 * kBlockM * cand * 4.0 / 200e9 : 0.0;
+        const double t = waves * (std::max(t_mem, t_mma) + t_red) + t_epi;
         if (t < best * (s > 1 ? 0.9 : 1.0)) best = t, bn = cand, splits = s;
       }
     }
@@ -273,12 +290,6 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.m_limit_rows = sp.m_limit_rows;
   p.splits = splits;
   p.kb_per_split = (taps * kb_per_tap + splits - 1) / splits;
-  if (splits > 1) {
-    p.ldw = static_cast<long long>(n_tiles) * bn;
-    p.ws = static_cast<float*>(net.arena.alloc(static_cast<size_t>(m_tiles) * kBlockM * p.ldw * sizeof(float)));
-    p.counters = static_cast<int*>(net.arena.alloc(static_cast<size_t>(m_tiles) * n_tiles * sizeof(int)));
-  }
-
   // Epilogue mode: smem-staged TMA stores (+ TMA residual prefetch) whenever a stored row chunk is at
   // least 64 bytes and the output has the activation dtype; otherwise direct per-thread stores.
   size_t epi_bytes = 0;
@@ -327,11 +338,16 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   }
   if (stages > 8) stages = 8;
   if (stages > p.kb_per_split + 1) stages = std::max(2, p.kb_per_split + 1);
+  if (splits > 1) {  // the operand ring doubles as the parking area of the fp32 partial tile
+    const int need = static_cast<int>((static_cast<size_t>(kBlockM) * bn * 4 + stage_bytes - 1) / stage_bytes);
+    stages = std::max(stages, need);
+    PN_REQUIRE(fixed_bytes + stages * stage_bytes <= 227 * 1024, name + ": split-K partial tile does not fit");
+  }
   p.stages = stages;
   PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
   const size_t smem = fixed_bytes + stages * stage_bytes;
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles * splits;
-  const int grid = static_cast<int>(std::min<long long>(tiles, net.num_sms));
+  const int grid = static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, net.num_sms));
 
   const double flops = 2.0 * static_cast<double>(M) * sp.Cout * sp.Cin * taps;
   net.add(name, [=](cudaStream_t s) {

@@ -53,13 +53,12 @@ struct ConvParams {
   int out_bufs;  // output staging depth: 2, or 1 for K-heavy layers where a deeper A/B pipeline matters more
   const int* m_limit;  // optional device-side count of valid row groups (ROIs); rows = *m_limit * m_limit_rows
   int m_limit_rows;
-  // split-K: every output tile is computed by `splits` CTAs over disjoint K-block ranges; partial sums meet in an
-  // fp32 workspace (vector red.global.add), the last CTA to arrive applies the epilogue and re-zeroes the workspace.
-  int splits;        // >= 1
+  // split-K: every output tile is computed by a thread-block cluster of `splits` CTAs over disjoint K-block ranges
+  // (one tile per cluster, grid = tiles * splits).  Each CTA parks its fp32 partial tile in its own shared memory
+  // (the operand ring, idle by then), and after a cluster barrier CTA r sums column slice r of all partial tiles
+  // over distributed shared memory in a fixed order (bit-reproducible) and applies the epilogue to that slice.
+  int splits;        // >= 1; BN / splits is a multiple of 8
   int kb_per_split;  // K blocks per split (the last split may be shorter)
-  float* ws;         // [m_tiles * 128][ldw] fp32, all zero between launches
-  long long ldw;
-  int* counters;     // [m_tiles * n_tiles], all zero between launches
 };
 
 constexpr int kBlockM = 128;
@@ -91,7 +90,50 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t r, uint32_t j, uint32_t cb)
   return off ^ (((off >> 7) & ((cb >> 4) - 1)) << 4);
 }
 
-template <typename T, int BN>
+// Direct epilogue tail for 8 consecutive output channels of row m: y already holds scale*acc + bias.
+template <typename T>
+__device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long m, int n0, float* y) {
+  if (p.residual != nullptr) {
+    const T* rp = reinterpret_cast<const T*>(p.residual) + m * p.ldr + n0;
+    if constexpr (sizeof(T) == 2) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(rp);
+      const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+        y[2 * e] += f2.x;
+        y[2 * e + 1] += f2.y;
+      }
+    } else {
+      const float4 r0 = *reinterpret_cast<const float4*>(rp);
+      const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+      y[0] += r0.x, y[1] += r0.y, y[2] += r0.z, y[3] += r0.w;
+      y[4] += r1.x, y[5] += r1.y, y[6] += r1.z, y[7] += r1.w;
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+  }
+  if (sizeof(T) == 2 && !p.out_fp32) {
+    uint4 o;
+    o.x = pack_bf16(y[0], y[1]);
+    o.y = pack_bf16(y[2], y[3]);
+    o.z = pack_bf16(y[4], y[5]);
+    o.w = pack_bf16(y[6], y[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0) = o;
+  } else {
+    if (p.round_tf32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = round_tf32(y[j]);
+    }
+    float* op = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
+    *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
+template <typename T, int BN, bool kSplit>
 __global__ void __launch_bounds__(kNumThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -163,7 +205,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_tiles = m_tiles_live * p.n_tiles * p.splits;  // work items: (m_tile, n_tile, split), split fastest
   const int taps = p.R * p.S;
   const int kblocks = taps * p.kb_per_tap;
-  uint32_t* last_flag = tmem_ptr + 1;
   const int cols_per_chunk = p.epi_tma ? p.cb / static_cast<int>(sizeof(T)) : 32;
 
   if (warp == 0) {
@@ -392,11 +433,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool row_ok = m < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      bool from_ws = false;
-      float* wrow = nullptr;
-      if (p.splits > 1) {
-        // ---- split-K: add this CTA's partial tile into the workspace; the last arrival finishes the tile
-        wrow = p.ws + m * p.ldw + n_tile * BN;
+      if constexpr (kSplit) {
+        // park the partial tile in the (now idle) operand ring: 16-byte unit (column group g, row) at (g*128 + row)*16
+        float4* part = reinterpret_cast<float4*>(smem_a);
 #pragma unroll 1
         for (int chunk = 0; chunk < BN / 32; ++chunk) {
           uint32_t v[32];
@@ -404,114 +443,79 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            red_add_v4(wrow + chunk * 32 + g * 4, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
-                       __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+            part[(chunk * 8 + g) * kBlockM + quarter * 32 + lane] =
+                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                            __uint_as_float(v[g * 4 + 3]));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        __threadfence();
-        named_bar_sync(1, 128);
-        if (threadIdx.x == 64) {
-          const int old = atomicAdd(p.counters + tile, 1);
-          const bool last = (old == p.splits - 1);
-          if (last) p.counters[tile] = 0;  // every split has arrived: clean for the next launch
-          *last_flag = last ? 1u : 0u;
-        }
-        named_bar_sync(1, 128);
-        if (*last_flag == 0u) continue;
-        __threadfence();
-        from_ws = true;
-      }
+        // the tile is finished after the cluster barrier below
+      } else {
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t v[32];
-        if (from_ws) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 t4 = ld_cg_v4(wrow + chunk * 32 + g * 4);
-            v[g * 4] = __float_as_uint(t4.x), v[g * 4 + 1] = __float_as_uint(t4.y);
-            v[g * 4 + 2] = __float_as_uint(t4.z), v[g * 4 + 3] = __float_as_uint(t4.w);
-            *reinterpret_cast<float4*>(wrow + chunk * 32 + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        } else {
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chunk * 32, v);
           tmem_ld_wait();
-        }
-        const int n0 = n_tile * BN + chunk * 32;
-        if (row_ok && n0 < p.cout_store) {
-          float y[32];
+          const int n0 = n_tile * BN + chunk * 32;
+          if (row_ok && n0 < p.cout_store) {
+            float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            y[j] = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
-          }
-          if (p.residual != nullptr) {
-            const T* rp = reinterpret_cast<const T*>(p.residual) + m * p.ldr + n0;
-            if constexpr (sizeof(T) == 2) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (n0 + g * 8 + 8 <= p.cout_store) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + g * 8);
-                  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                    y[g * 8 + 2 * e] += f2.x;
-                    y[g * 8 + 2 * e + 1] += f2.y;
-                  }
-                }
-              }
-            } else {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (n0 + g * 4 + 4 <= p.cout_store) {
-                  const float4 rv = *reinterpret_cast<const float4*>(rp + g * 4);
-                  y[g * 4] += rv.x;
-                  y[g * 4 + 1] += rv.y;
-                  y[g * 4 + 2] += rv.z;
-                  y[g * 4 + 3] += rv.w;
-                }
-              }
+            for (int j = 0; j < 32; ++j) {
+              y[j] = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
             }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
-          }
-          if (sizeof(T) == 2 && !p.out_fp32) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (n0 + g * 8 + 8 <= p.cout_store) {
-                uint4 o;
-                o.x = pack_bf16(y[g * 8], y[g * 8 + 1]);
-                o.y = pack_bf16(y[g * 8 + 2], y[g * 8 + 3]);
-                o.z = pack_bf16(y[g * 8 + 4], y[g * 8 + 5]);
-                o.w = pack_bf16(y[g * 8 + 6], y[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(op + g * 8) = o;
-              }
-            }
-          } else {
-            if (p.round_tf32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) y[j] = round_tf32(y[j]);
-            }
-            float* op = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (n0 + g * 4 + 4 <= p.cout_store) {
-                *reinterpret_cast<float4*>(op + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
-              }
+              if (n0 + g * 8 + 8 <= p.cout_store) epilogue_store8<T>(p, m, n0 + g * 8, &y[g * 8]);
             }
           }
         }
       }
-      if (!from_ws) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  if constexpr (kSplit) {
+    // ------------------------------------------------------------ split-K: reduce-scatter over the cluster
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (warp >= 2 && warp < 6 && static_cast<int>(blockIdx.x) < num_tiles) {
+      const int tile = blockIdx.x / p.splits;
+      const int rank = blockIdx.x - tile * p.splits;  // == %cluster_ctarank for 1-D clusters of `splits` CTAs
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int row = (warp & 3) * 32 + lane;
+      const long long m = static_cast<long long>(m_tile) * kBlockM + row;
+      const int cols_per_rank = BN / p.splits;
+      const uint32_t part0 = smem_u32(smem_a);
+      if (m < p.M) {
+#pragma unroll 1
+        for (int c = rank * cols_per_rank; c < (rank + 1) * cols_per_rank; c += 8) {
+          const int n0 = n_tile * BN + c;
+          if (n0 >= p.cout_store) break;
+          float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          const uint32_t off = static_cast<uint32_t>(((c >> 2) * kBlockM + row) * 16);
+#pragma unroll 1
+          for (int s0 = 0; s0 < p.splits; s0 += 2) {  // fixed summation order: split 0, 1, 2, ...
+            const uint32_t ra = map_shared_rank(part0, s0) + off;
+            const uint32_t rb = map_shared_rank(part0, s0 + 1) + off;
+            const float4 a0 = ld_dsmem_v4(ra), a1 = ld_dsmem_v4(ra + kBlockM * 16);
+            const float4 b0 = ld_dsmem_v4(rb), b1 = ld_dsmem_v4(rb + kBlockM * 16);
+            y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w;
+            y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
+            y[0] += b0.x, y[1] += b0.y, y[2] += b0.z, y[3] += b0.w;
+            y[4] += b1.x, y[5] += b1.y, y[6] += b1.z, y[7] += b1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
+          epilogue_store8<T>(p, m, n0, y);
+        }
       }
     }
+    // nobody may exit (and release its shared memory) while a peer can still be reading it
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
   }
 
   tc_fence_before();

@@ -8,9 +8,10 @@ file:line it follows.  Pinning status:
 
 * ``oracle.mapper``   - pinned against the reference's own ``nav/agent/mapping.py`` executed in the build
   container (fixtures in tests/golden/semmap_*.npz, generator tests/golden/make_semmap_golden.py).
-* ``oracle.prednet``  - PARITY UNPINNED: mmcv 1.6.0 is not installable here and the reference tests hold
-  shape assertions only; pinned to those structural facts (46.61 M parameters,
-  61 convolutions, stage shapes) and to nothing numeric.
+* ``oracle.prednet``  - pinned against the reference's own model files (resnet.py, res_layer.py, psp_head.py,
+  decode_head.py, encoder_decoder.py, wrappers.py built from nav/pred_model_cfg.py) executed in the build
+  container over a restated mmcv-1.6.0 shim: bit-identical logits and stage outputs are required before
+  tests/golden/prednet_*.npz are written (generator tests/golden/make_prednet_golden.py, shim mmcv_shim.py).
 * ``oracle.maskrcnn`` - PARITY UNPINNED: detectron2 0.6 is absent; restated from the config
   nav/agent/utils/COCO-InstSeg/mask_rcnn_R_101_cat9.yaml and detectron2's published semantics.
 """

@@ -1,6 +1,9 @@
 """Oracle for stage C: the map-completion encoder-decoder (ResNetV1c-50-D8 + PSPHead).
 
-PARITY UNPINNED (see oracle/__init__.py): a plain-PyTorch restatement, test infrastructure only.
+PINNED (test infrastructure only): tests/golden/make_prednet_golden.py executes the reference's UNMODIFIED model files
+(resnet.py, res_layer.py, psp_head.py, decode_head.py, encoder_decoder.py, wrappers.py, built from nav/pred_model_cfg.py) over a
+restated mmcv-1.6.0 shim and requires this restatement to be BIT-IDENTICAL to them (logits and the four backbone stage outputs,
+three shapes, 14 and 24 input channels) before it writes tests/golden/prednet_*.npz.
 
 Follows, line by line:
   * config                      nav/pred_model_cfg.py:2-42
@@ -196,9 +199,9 @@ def run_inference(model, full_map):
 
 
 def get_prediction(model, full_map):
-    """nav/agent/prediction.py:155-158 (scipy.special.expit == logistic sigmoid, computed in fp32)."""
-    logits = run_inference(model, full_map)[0]
-    return (1.0 / (1.0 + np.exp(-logits.astype(np.float32)))).astype(np.float32)
+    """nav/agent/prediction.py:22-23, 155-158: scipy.special.expit on the fp32 logits."""
+    from scipy.special import expit
+    return expit(run_inference(model, full_map)[0])
 
 
 # ---------------------------------------------------------------------------------------------------

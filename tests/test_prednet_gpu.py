@@ -103,3 +103,29 @@ def test_wrong_channels_raises(weights):
     seg = _segmentor(weights, "bf16")
     with pytest.raises(RuntimeError):
         seg.forward_device(torch.zeros((1, 13, 64, 64), device="cuda"))
+
+
+def _golden_cases():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "prednet_*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden_cases(), ids=lambda p: p.rsplit("/", 1)[-1])
+def test_tf32_vs_reference_golden(path):
+    """CUDA path against logits produced by the reference's own model code (tests/golden/make_prednet_golden.py):
+    tf32 operands / fp32 accumulate -> 5e-3 of the logit range; argmax equal wherever the top-2 margin exceeds that."""
+    g = np.load(path)
+    C, H, W, wseed, xseed, _ = (int(v) for v in g["meta"])
+    sd = oracle.synth_state_dict(C, 6, seed=wseed)
+    seg = prediction.init_segmentor(prediction._default_cfg(C, 6), device="cuda:0", precision="tf32", state_dict=sd)
+    x = oracle.synth_partial_map(C, H, W, seed=xseed)
+    got = prediction.run_inference(seg, x)[0]
+    ref = g["logits"]
+    rng = float(np.abs(ref).max())
+    tol = 5e-3 * rng
+    assert got.shape == ref.shape and float(np.abs(got - ref).max()) <= tol
+    top2 = np.sort(ref, axis=0)[-2:]
+    decided = (top2[1] - top2[0]) > 2 * tol
+    assert decided.mean() > 0.5
+    assert np.array_equal(got.argmax(0)[decided], ref.argmax(0)[decided])

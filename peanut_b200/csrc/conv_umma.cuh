@@ -192,8 +192,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
-  // from here on we read what it wrote
+  // Weights do not depend on the previous kernel: arm the first pipeline stages of this CTA's first work item and
+  // fetch their weight tiles while the previous kernel drains (its tail would otherwise hide nothing but the prologue).
+  int pre_armed = 0;
+  if (warp == 0 && p.m_limit == nullptr && static_cast<int>(blockIdx.x) < p.m_tiles * p.n_tiles * p.splits) {
+    const int work0 = blockIdx.x;
+    const int tile0 = work0 / p.splits;
+    const int split0 = work0 - tile0 * p.splits;
+    const int n_tile0 = tile0 % p.n_tiles;
+    const int kb_total = p.R * p.S * p.kb_per_tap;
+    const int kb_begin0 = split0 * p.kb_per_split;
+    const int my_kb = min(kb_total, kb_begin0 + p.kb_per_split) - kb_begin0;
+    pre_armed = min(p.stages, my_kb);
+    if (elect_one()) {
+      for (int i = 0; i < pre_armed; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], a_bytes + b_bytes);
+        tma_load_2d(&tmap_b, &full_bar[i], smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k, n_tile0 * BN);
+      }
+    }
+  }
+  // everything above (barrier init, TMEM allocation, descriptor prefetch, weight prefetch) overlapped the previous
+  // kernel's tail; from here on we read what it wrote
   griddep_wait();
 
   int m_tiles_live = p.m_tiles;
@@ -230,15 +249,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int kb = kb_begin - tap * p.kb_per_tap;
         int r = tap / p.S, sx = tap - r * p.S;
         for (int kb_global = kb_begin; kb_global < kb_end; ++kb_global) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          const bool armed = pre_armed > 0;  // stage already armed and its weight tile already in flight
+          if (armed) {
+            --pre_armed;
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          }
           if (p.a_tiled) {
             tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, m0);
           } else {
             tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0, img,
                                static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
           }
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
+          if (!armed) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;

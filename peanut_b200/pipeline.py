@@ -52,6 +52,8 @@ class PerceptionPipeline:
         self.sem = torch.zeros((E, H, W, nsem), dtype=torch.float32, device=d)
         self.obs = torch.zeros((E, 4 + nsem, a.frame_height, a.frame_width), dtype=torch.float32, device=d)
         self.pred_out = torch.zeros((E, num_pred_classes) + self.map_shape[1:], dtype=torch.float32, device=d)
+        self._side = torch.cuda.Stream(device=d)
+        self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
         # staging for the host entry point
         self._dev_in = None
         self._host_out = None
@@ -69,15 +71,24 @@ class PerceptionPipeline:
         Returns (sem [E,H,W,S], fp_map [E,vr,vr], new_local_map [E,4+S,n,n], poses, pred_map [E,K,Hm,Wm]);
         no host synchronisation."""
         a = self.args
+        # The map-completion net only reads the caller's partial map: it runs on a side stream next to Mask-RCNN and the
+        # mapper (at small E every layer is a single wave of CTAs that leaves room for a second resident CTA per SM).
+        main = torch.cuda.current_stream(self.device)
+        self._fork.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._fork)
+            pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
+            self._join.record(self._side)
+        partial_map.record_stream(self._side)
         self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = main.cuda_stream
         lib = self.seg.ctx.lib
         _lib.check(lib.pn_make_obs(self.seg.ctx.handle, depth.data_ptr(), rgb.data_ptr(), self.sem.data_ptr(), self.E,
                                    a.env_frame_height, a.env_frame_width, a.frame_height, a.frame_width,
                                    a.num_sem_categories, a.min_depth, a.max_depth, self.obs.data_ptr(),
                                    ctypes.c_void_p(stream)))
         fp, new_map, poses = self.mapper.forward_batch(self.obs, pose_delta, local_map, poses)
-        pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
+        main.wait_event(self._join)
         return self.sem, fp, new_map, poses, pred
 
     def step_host(self, rgb_h, depth_h, pose_delta_h, partial_map_h, local_map, poses):

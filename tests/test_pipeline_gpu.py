@@ -1,0 +1,74 @@
+"""PerceptionPipeline (peanut_b200/pipeline.py): the batched composition of the three reference call sites must equal the
+stages run one by one through their reference-facing shims, for device and host entry points alike (bit-exact: same
+kernels, same launch lists; the prediction net merely runs on a side stream)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mapper as OB
+from oracle import maskrcnn as OA
+from oracle import prednet as OC
+from oracle import preproc as OP
+from peanut_b200.pipeline import PerceptionPipeline
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    E, shape = 2, (14, 96, 96)
+    wa, wc = OA.synth_weights(0), OC.synth_state_dict(shape[0], 6, seed=0)
+    pipe = PerceptionPipeline(wa, wc, num_envs=E, device="cuda:0", precision="bf16", map_shape=shape)
+    pipe.args.sem_pred_prob_thr = 0.3   # random weights: keep some detections alive
+    pipe.args.goal_thr = 0.3
+    args = OB.default_args()
+    rgb = torch.from_numpy(np.stack([OA.synth_rgb(10 + e) for e in range(E)]))
+    depth = torch.from_numpy(np.stack([OP.synth_depth(10 + e)[:, :, 0] for e in range(E)]))
+    st = [OB.synth_state(10 + e, args) for e in range(E)]
+    delta = torch.from_numpy(np.stack([s[0] for s in st]))
+    maps = torch.from_numpy(np.stack([s[1] for s in st]))
+    poses = torch.from_numpy(np.stack([s[2] for s in st]))
+    pmap = torch.from_numpy(np.stack([OC.synth_partial_map(*shape, seed=40 + e) for e in range(E)]))
+    return pipe, dict(rgb=rgb, depth=depth, delta=delta, maps=maps, poses=poses, pmap=pmap)
+
+
+def test_step_equals_stages(setup):
+    pipe, h = setup
+    d = {k: v.cuda() for k, v in h.items()}
+    poses = d["poses"].clone()
+    sem, fp, new_map, poses_out, pred = pipe.step_device(d["rgb"], d["depth"], d["delta"], d["maps"], poses, d["pmap"])
+    torch.cuda.synchronize()
+    sem, fp, new_map, pred, poses_out = sem.clone(), fp.clone(), new_map.clone(), pred.clone(), poses_out.clone()
+    a = pipe.args
+    # stage by stage on the current stream
+    sem1 = pipe.seg.forward_device(d["rgb"], None, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr).clone()
+    assert torch.equal(sem1, sem) and float(sem.sum()) > 0
+    pred1 = pipe.pred.forward_device(d["pmap"], apply_sigmoid=True).clone()
+    assert torch.equal(pred1, pred)
+    assert float(pred.min()) >= 0.0 and float(pred.max()) <= 1.0
+    # mapper on the observation the glue kernel built: against the oracle composition (bit-exact integer part)
+    for e in range(pipe.E):
+        obs = OP.preprocess_obs(h["rgb"][e].numpy(), h["depth"][e].numpy()[:, :, None], sem[e].cpu().numpy())
+        p = h["poses"][e:e + 1].clone()
+        fp_r, mp_r, _, cur = OB.forward(torch.from_numpy(obs)[None], h["delta"][e:e + 1], h["maps"][e:e + 1], p,
+                                        OB.default_args())
+        assert torch.equal(fp[e].cpu(), fp_r[0])
+        assert float((new_map[e].cpu() - mp_r[0]).abs().max()) <= 1e-4
+        assert float((poses_out[e].cpu() - cur[0]).abs().max()) <= 1e-4
+
+
+def test_step_host_equals_step_device(setup):
+    pipe, h = setup
+    d = {k: v.cuda() for k, v in h.items()}
+    _, fp, new_map, poses_d, pred = pipe.step_device(d["rgb"], d["depth"], d["delta"], d["maps"], d["poses"].clone(), d["pmap"])
+    torch.cuda.synchronize()
+    fp, new_map, pred, poses_d = fp.clone(), new_map.clone(), pred.clone(), poses_d.clone()
+    pin = {k: v.pin_memory() for k, v in h.items()}
+    pred_h, poses_h, fp_h, map_h = pipe.step_host(pin["rgb"], pin["depth"], pin["delta"], pin["pmap"], d["maps"],
+                                                  d["poses"].clone())
+    assert torch.equal(pred_h, pred.cpu()) and torch.equal(fp_h, fp.cpu()) and torch.equal(poses_h, poses_d.cpu())
+    assert torch.equal(map_h, new_map)
+    assert pipe.h2d_bytes(pin["rgb"], pin["depth"], pin["delta"], pin["pmap"]) == sum(
+        pin[k].numel() * pin[k].element_size() for k in ("rgb", "depth", "delta", "pmap"))
+    assert pipe.d2h_bytes() == pred_h.numel() * 4 + poses_h.numel() * 4 + fp_h.numel() * 4
+    assert pipe.launches_per_step() > 100

@@ -1,5 +1,7 @@
 // C-ABI of libpeanut_b200.so (declared in include/peanut_b200.h).  Every entry point translates
 // C++ exceptions into a status code + thread-local message; no torch types cross this boundary.
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -625,6 +627,11 @@ int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int 
   sp.Cin = Cin, sp.Cout = Cout, sp.R = R, sp.S = S, sp.stride = stride, sp.dil = dil, sp.pad = pad, sp.relu = true;
   sp.force_bn = force_bn & 0xfff;
   sp.force_splits = (force_bn >> 16) & 0xff;
+  long long* dbg = nullptr;
+  if (std::getenv("PN_CONV_DBG")) {
+    dbg = static_cast<long long*>(net.arena.alloc(64 * 16 * sizeof(long long)));
+    sp.dbg = dbg;
+  }
   add_conv(net, "bench", x, y, w.data(), sc.data(), bi.data(), sp, with_residual ? &res : nullptr);
   if (bn_out) *bn_out = net.last_bn;
   cudaEvent_t e0, e1;
@@ -640,6 +647,19 @@ int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int 
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms_out = ms / iters;
+  if (dbg) {  // timeline of CTA 0 in the last launch, cycles relative to its first event
+    std::vector<long long> h(64 * 16);
+    PN_CUDA_CHECK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    std::printf("# CTA0 timeline (cycles): tile: load0 | mma: enter, acc free, first mma, commit | epi: enter, acc full, done | group pairs\n");
+    for (int t = 0; t < 64; ++t) {
+      if (!h[t * 16 + 6]) break;
+      std::printf("tile %2d:", t);
+      for (int k = 0; k < 16; ++k) std::printf(" %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      std::printf("\n");
+    }
+  }
   PN_API_END
 }
 

@@ -286,6 +286,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.relu = sp.relu ? 1 : 0;
   p.out_fp32 = (out.dt == kF32) ? 1 : 0;
   p.round_tf32 = (dt == kF32 && !sp.out_fp32) ? 1 : 0;
+  p.dbg = sp.dbg;
   p.m_limit = sp.m_limit;
   p.m_limit_rows = sp.m_limit_rows;
   p.splits = splits;
@@ -304,7 +305,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
       p.epi_tma = 1;
       p.cb = cb;
       p.res_bufs = residual ? 3 : 0;
-      tm.out = encode_tiled_2d(dt, out.ptr, p.cout_store, M, static_cast<uint64_t>(out.ld) * es, cb / es, kBlockM, cb);
+      tm.out = encode_tiled_2d(dt, out.ptr, p.cout_store, M, static_cast<uint64_t>(out.ld) * es, cb / es, 32, cb);  // one box per epilogue warp
       if (residual)
         tm.res = encode_tiled_2d(dt, residual->ptr, p.cout_store, M, static_cast<uint64_t>(residual->ld) * es, cb / es,
                                  kBlockM, cb);
@@ -315,7 +316,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
 
   const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * sw;
   const int kblocks = taps * kb_per_tap;
-  size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 2 * bn * sizeof(float) + 256 /*barriers*/;
+  size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 8 * bn * sizeof(float) /*scale+bias per epilogue warp*/ + 256 /*barriers*/;
   size_t budget = 227 * 1024 - fixed_bytes;
   int stages = static_cast<int>(budget / stage_bytes);
   if (p.epi_tma && kblocks >= 32) {

@@ -14,8 +14,8 @@
 //   memory and written back with TMA bulk stores (full 128-byte lines, M/N tails clipped by hardware).
 //   Fallback path (narrow or mixed-precision outputs): direct 16-byte global stores per thread.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (one per TMEM lane quarter),
-// 6 = residual prefetcher.
+// Warp roles: 0..3 = epilogue (one per TMEM lane quarter; warpgroup 0, which takes the registers warpgroup 1 gives up
+// through setmaxnreg), 4 = TMA producer, 5 = MMA issuer + TMEM owner, 6 = residual prefetcher, 7 = idle.
 //
 // Replaces the cuDNN conv + separate BN + ReLU kernels the reference reaches through
 // mmcv ConvModule / mmseg Bottleneck (prediction/mmseg/models/backbones/resnet.py:267-307) and
@@ -57,12 +57,14 @@ struct ConvParams {
   // (one tile per cluster, grid = tiles * splits).  Each CTA parks its fp32 partial tile in its own shared memory
   // (the operand ring, idle by then), and after a cluster barrier CTA r sums column slice r of all partial tiles
   // over distributed shared memory in a fixed order (bit-reproducible) and applies the epilogue to that slice.
+  long long* dbg;    // optional per-tile timeline of CTA 0 (tuning aid; nullptr in production): 16 clock64 slots per tile
   int splits;        // >= 1; BN / splits is a multiple of 8
   int kb_per_split;  // K blocks per split (the last split may be shorter)
 };
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 224;
+constexpr int kNumThreads = 256;  // warpgroup 0 = epilogue warps, warpgroup 1 = producer / MMA / residual (+1 idle)
+constexpr int kProducerWarp = 4, kMmaWarp = 5, kResidualWarp = 6;
 
 template <typename T>
 struct ElemTraits;
@@ -78,6 +80,12 @@ struct ElemTraits<float> {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// {lo, hi} -> bf16x2 with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
@@ -133,6 +141,13 @@ __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long m
   }
 }
 
+// Tuning aid (build with -DPN_CONV_TIMELINE, run tools/conv_one.py with PN_CONV_DBG=1): clock64 timeline of CTA 0.
+#ifdef PN_CONV_TIMELINE
+#define PN_DBG(iter, slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < 64) p.dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define PN_DBG(iter, slot) do { } while (0)
+#endif
+
 template <typename T, int BN, bool kSplit>
 __global__ void __launch_bounds__(kNumThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -151,8 +166,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem_out = smem_b + p.stages * b_bytes;
   uint8_t* smem_res = smem_out + p.out_bufs * chunk_bytes;
   float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * chunk_bytes);
-  float* smem_bias = smem_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_scale + 8 * BN);  // one [scale BN][bias BN] copy per epilogue warp
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -184,7 +198,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_ptr, kTmemCols);
     tmem_relinquish();
   }
@@ -195,7 +209,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // Weights do not depend on the previous kernel: arm the first pipeline stages of this CTA's first work item and
   // fetch their weight tiles while the previous kernel drains (its tail would otherwise hide nothing but the prologue).
   int pre_armed = 0;
-  if (warp == 0 && p.m_limit == nullptr && static_cast<int>(blockIdx.x) < p.m_tiles * p.n_tiles * p.splits) {
+  if (warp == kProducerWarp && p.m_limit == nullptr && static_cast<int>(blockIdx.x) < p.m_tiles * p.n_tiles * p.splits) {
     const int work0 = blockIdx.x;
     const int tile0 = work0 / p.splits;
     const int split0 = work0 - tile0 * p.splits;
@@ -226,7 +240,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int kblocks = taps * p.kb_per_tap;
   const int cols_per_chunk = p.epi_tma ? p.cb / static_cast<int>(sizeof(T)) : 32;
 
-  if (warp == 0) {
+  if (warp >= 4) {
+  setmaxnreg_dec<64>();  // data-movement / issue warps need few registers: the epilogue warpgroup takes the rest
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
@@ -248,6 +264,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int tap = kb_begin / p.kb_per_tap;
         int kb = kb_begin - tap * p.kb_per_tap;
         int r = tap / p.S, sx = tap - r * p.S;
+        PN_DBG((work - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x), 0);
         for (int kb_global = kb_begin; kb_global < kb_end; ++kb_global) {
           const bool armed = pre_armed > 0;  // stage already armed and its weight tile already in flight
           if (armed) {
@@ -274,7 +291,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer (one elected lane)
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(ElemTraits<T>::kFormat, BN);
@@ -285,8 +302,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        PN_DBG(it, 1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        PN_DBG(it, 2);
         const uint32_t d_tmem = tmem_base + acc * BN;
         const int split = work % p.splits;
         const int my_kblocks = min(kblocks, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
@@ -304,7 +323,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == my_kblocks - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == 0) PN_DBG(it, 3);
+          if (kb == my_kblocks - 1) {
+            umma_commit(&tfull_bar[acc]);
+            PN_DBG(it, 4);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -312,7 +335,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == kResidualWarp) {
     // ------------------------------------------------------------ residual prefetcher (TMA epilogue only)
     if (p.epi_tma && p.residual != nullptr && elect_one()) {
       uint32_t g = 0;  // running chunk counter, same sequence as the epilogue warps
@@ -328,121 +351,170 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (p.epi_tma) {
+  }
+    if constexpr (kSplit) {  // keep pace with the epilogue warps' two cluster barriers (see below)
+      __syncwarp();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      __syncwarp();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
+  } else {
+  setmaxnreg_inc<192>();
+  if (p.epi_tma) {
     // ------------------------------------------------------------ epilogue, fast path
+    // Every warp is self-contained: it owns 32 accumulator rows (its TMEM lane quarter), a private copy of the tile's
+    // scale/bias, its 32-row slice of the output staging buffers and its own TMA stores (32-row boxes), so the four
+    // warps never meet at a barrier.  TMEM loads are double-buffered in registers (32 columns in flight while the
+    // previous 32 are processed).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const uint32_t row = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
-    const bool issuer = (et == 0);
     constexpr int kUnits = 32 * sizeof(T) / 16;  // 16-byte units per 32 columns
-    uint32_t g = 0;
+    const int subs_per_chunk = cols_per_chunk / 32;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t sb_addr = smem_u32(smem_scale) + quarter * (2 * BN * 4);  // [scale BN][bias BN] of this warp
+    const uint32_t out_addr = smem_u32(smem_out);
+    const uint32_t res_addr = smem_u32(smem_res);
+    const bool has_res = p.residual != nullptr;
+    uint32_t g = 0;  // running chunk counter (same sequence as the residual prefetcher)
+    uint32_t rb = 0, rphase = 0;  // residual ring slot / phase of chunk g
     int it = 0;
+    int cached_n_tile = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
-      // per-tile scale/bias -> smem (previous tile's readers are all past their last chunk barrier)
-      for (int i = et; i < BN; i += 128) {
-        smem_scale[i] = __ldg(p.scale + n_tile * BN + i);
-        smem_bias[i] = __ldg(p.bias + n_tile * BN + i);
+      if (n_tile != cached_n_tile) {
+        __syncwarp();
+        for (int i = lane * 4; i < BN; i += 128) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n_tile * BN + i));
+          const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n_tile * BN + i));
+          sts_v4(sb_addr + i * 4, __float_as_uint(sc.x), __float_as_uint(sc.y), __float_as_uint(sc.z), __float_as_uint(sc.w));
+          sts_v4(sb_addr + (BN + i) * 4, __float_as_uint(bi.x), __float_as_uint(bi.y), __float_as_uint(bi.z), __float_as_uint(bi.w));
+        }
+        cached_n_tile = n_tile;
+        __syncwarp();
       }
+      const int cols_live = min(BN, p.cout_store - n_tile * BN);
+      const int nchunks = (cols_live + cols_per_chunk - 1) / cols_per_chunk;
+      const int ngroups = nchunks * subs_per_chunk;
+      const uint32_t acc_taddr = lane_taddr + acc * BN;
+      if (warp == 0 && lane == 0) PN_DBG(it, 5);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      for (int n0 = n_tile * BN; n0 < n_tile * BN + BN && n0 < p.cout_store; n0 += cols_per_chunk, ++g) {
-        uint8_t* obuf = smem_out + (p.out_bufs == 2 ? (g & 1) : 0) * chunk_bytes;
-        if (issuer) {  // the store that last read this buffer has drained
-          if (p.out_bufs == 2) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
+      if (warp == 0 && lane == 0) PN_DBG(it, 6);
+
+      // one 32-column group: v holds the accumulators of columns [grp*32, grp*32+32) of this thread's row
+      auto process = [&](uint32_t (&v)[32], int grp) {
+        const int sub = (subs_per_chunk == 2) ? (grp & 1) : 0;
+        const uint32_t buf = (p.out_bufs == 2) ? (g & 1u) : 0u;
+        const uint32_t obuf = out_addr + buf * chunk_bytes;
+        if (sub == 0) {
+          if (lane == 0) {  // this warp's earlier store out of this buffer has been read
+            if (p.out_bufs == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          __syncwarp();
+          if (has_res) mbar_wait(&rfull_bar[rb], rphase);
         }
-        named_bar_sync(1, 128);
-        const uint8_t* rbuf = nullptr;
-        uint32_t rb = 0;
-        if (p.residual != nullptr) {
-          rb = g % p.res_bufs;
-          mbar_wait(&rfull_bar[rb], (g / p.res_bufs) & 1);
-          rbuf = smem_res + rb * chunk_bytes;
+        if (warp == 0 && lane == 0 && grp < 2) PN_DBG(it, 8 + grp * 4);
+        const uint32_t sb = sb_addr + grp * 32 * 4;
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = lds_f4(sb + j * 4);
+          const float4 bi = lds_f4(sb + (BN + j) * 4);
+          y[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+          y[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+          y[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+          y[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
         }
-        const int nl0 = n0 - n_tile * BN;  // column offset inside the tile
-#pragma unroll 1
-        for (int sub = 0; sub < cols_per_chunk / 32; ++sub) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + nl0 + sub * 32, v);
-          tmem_ld_wait();
-          float y[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(smem_scale + nl0 + sub * 32 + j);
-            const float4 bi = *reinterpret_cast<const float4*>(smem_bias + nl0 + sub * 32 + j);
-            y[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
-            y[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-            y[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-            y[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
-          }
-          if (rbuf != nullptr) {
-#pragma unroll
-            for (int u = 0; u < kUnits; ++u) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + swz_off(row, sub * kUnits + u, p.cb));
-              if constexpr (sizeof(T) == 2) {
-                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                  y[u * 8 + 2 * e] += f2.x;
-                  y[u * 8 + 2 * e + 1] += f2.y;
-                }
-              } else {
-                y[u * 4] += __uint_as_float(rv.x);
-                y[u * 4 + 1] += __uint_as_float(rv.y);
-                y[u * 4 + 2] += __uint_as_float(rv.z);
-                y[u * 4 + 3] += __uint_as_float(rv.w);
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
-          }
+        if (has_res) {
+          const uint32_t rbuf = res_addr + rb * chunk_bytes;
 #pragma unroll
           for (int u = 0; u < kUnits; ++u) {
-            uint4 o;
+            const uint4 rv = lds_v4(rbuf + swz_off(row, sub * kUnits + u, p.cb));
             if constexpr (sizeof(T) == 2) {
-              o.x = pack_bf16(y[u * 8], y[u * 8 + 1]);
-              o.y = pack_bf16(y[u * 8 + 2], y[u * 8 + 3]);
-              o.z = pack_bf16(y[u * 8 + 4], y[u * 8 + 5]);
-              o.w = pack_bf16(y[u * 8 + 6], y[u * 8 + 7]);
-            } else {
-              if (p.round_tf32) {
-                o.x = __float_as_uint(round_tf32(y[u * 4]));
-                o.y = __float_as_uint(round_tf32(y[u * 4 + 1]));
-                o.z = __float_as_uint(round_tf32(y[u * 4 + 2]));
-                o.w = __float_as_uint(round_tf32(y[u * 4 + 3]));
-              } else {
-                o.x = __float_as_uint(y[u * 4]);
-                o.y = __float_as_uint(y[u * 4 + 1]);
-                o.z = __float_as_uint(y[u * 4 + 2]);
-                o.w = __float_as_uint(y[u * 4 + 3]);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                y[u * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                y[u * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
               }
+            } else {
+              y[u * 4] += __uint_as_float(rv.x);
+              y[u * 4 + 1] += __uint_as_float(rv.y);
+              y[u * 4 + 2] += __uint_as_float(rv.z);
+              y[u * 4 + 3] += __uint_as_float(rv.w);
             }
-            *reinterpret_cast<uint4*>(obuf + swz_off(row, sub * kUnits + u, p.cb)) = o;
           }
         }
-        fence_proxy_async();  // make the st.shared above visible to the TMA (async proxy)
-        if (rbuf != nullptr) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&rempty_bar[rb]);
+#pragma unroll
+        for (int u = 0; u < kUnits; ++u) {
+          uint32_t o0, o1, o2, o3;
+          if constexpr (sizeof(T) == 2) {
+            if (p.relu) {
+              o0 = pack_bf16_relu(y[u * 8], y[u * 8 + 1]), o1 = pack_bf16_relu(y[u * 8 + 2], y[u * 8 + 3]);
+              o2 = pack_bf16_relu(y[u * 8 + 4], y[u * 8 + 5]), o3 = pack_bf16_relu(y[u * 8 + 6], y[u * 8 + 7]);
+            } else {
+              o0 = pack_bf16(y[u * 8], y[u * 8 + 1]), o1 = pack_bf16(y[u * 8 + 2], y[u * 8 + 3]);
+              o2 = pack_bf16(y[u * 8 + 4], y[u * 8 + 5]), o3 = pack_bf16(y[u * 8 + 6], y[u * 8 + 7]);
+            }
+          } else {
+            float a = y[u * 4], b = y[u * 4 + 1], c = y[u * 4 + 2], d = y[u * 4 + 3];
+            if (p.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f), c = fmaxf(c, 0.f), d = fmaxf(d, 0.f);
+            if (p.round_tf32) a = round_tf32(a), b = round_tf32(b), c = round_tf32(c), d = round_tf32(d);
+            o0 = __float_as_uint(a), o1 = __float_as_uint(b), o2 = __float_as_uint(c), o3 = __float_as_uint(d);
+          }
+          sts_v4(obuf + swz_off(row, sub * kUnits + u, p.cb), o0, o1, o2, o3);
         }
-        named_bar_sync(1, 128);
-        if (issuer) {
-          tma_store_2d(&tmap_out, obuf, n0, m_tile * kBlockM);
-          tma_store_commit();
+        if (warp == 0 && lane == 0 && grp < 2) PN_DBG(it, 10 + grp * 4);
+        if (sub == subs_per_chunk - 1) {
+          fence_proxy_async();  // make the st.shared above visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (has_res) mbar_arrive(&rempty_bar[rb]);
+            const int n0 = n_tile * BN + (grp - sub) * 32;
+            tma_store_2d_addr(&tmap_out, obuf + quarter * 32 * p.cb, n0, m_tile * kBlockM + quarter * 32);
+            tma_store_commit();
+          }
+          ++g;
+          if (has_res && ++rb == static_cast<uint32_t>(p.res_bufs)) rb = 0, rphase ^= 1;
+        }
+        if (warp == 0 && lane == 0 && grp < 2) PN_DBG(it, 11 + grp * 4);
+      };
+
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(acc_taddr, va);
+#pragma unroll 1
+      for (int grp = 0; grp < ngroups; grp += 2) {
+        tmem_ld_wait();
+        const bool more_b = grp + 1 < ngroups;
+        if (more_b) {
+          tmem_ld_32x32(acc_taddr + (grp + 1) * 32, vb);
+        } else {  // every accumulator column this warp needs is in registers: hand the TMEM stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        process(va, grp);
+        if (more_b) {
+          tmem_ld_wait();
+          if (grp + 2 < ngroups) {
+            tmem_ld_32x32(acc_taddr + (grp + 2) * 32, va);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          process(vb, grp + 1);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (warp == 0 && lane == 0) PN_DBG(it, 7);
     }
-    if (issuer) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------ epilogue, direct path: TMEM -> regs -> global
     const int quarter = warp & 3;
@@ -497,54 +569,55 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
-
-  if constexpr (kSplit) {
-    // ------------------------------------------------------------ split-K: reduce-scatter over the cluster
-    __syncwarp();
-    cluster_arrive_release();
-    cluster_wait_acquire();
-    if (warp >= 2 && warp < 6 && static_cast<int>(blockIdx.x) < num_tiles) {
-      const int tile = blockIdx.x / p.splits;
-      const int rank = blockIdx.x - tile * p.splits;  // == %cluster_ctarank for 1-D clusters of `splits` CTAs
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
-      const int row = (warp & 3) * 32 + lane;
-      const long long m = static_cast<long long>(m_tile) * kBlockM + row;
-      const int cols_per_rank = BN / p.splits;
-      const uint32_t part0 = smem_u32(smem_a);
-      if (m < p.M) {
-#pragma unroll 1
-        for (int c = rank * cols_per_rank; c < (rank + 1) * cols_per_rank; c += 8) {
-          const int n0 = n_tile * BN + c;
-          if (n0 >= p.cout_store) break;
-          float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          const uint32_t off = static_cast<uint32_t>(((c >> 2) * kBlockM + row) * 16);
-#pragma unroll 1
-          for (int s0 = 0; s0 < p.splits; s0 += 2) {  // fixed summation order: split 0, 1, 2, ...
-            const uint32_t ra = map_shared_rank(part0, s0) + off;
-            const uint32_t rb = map_shared_rank(part0, s0 + 1) + off;
-            const float4 a0 = ld_dsmem_v4(ra), a1 = ld_dsmem_v4(ra + kBlockM * 16);
-            const float4 b0 = ld_dsmem_v4(rb), b1 = ld_dsmem_v4(rb + kBlockM * 16);
-            y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w;
-            y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
-            y[0] += b0.x, y[1] += b0.y, y[2] += b0.z, y[3] += b0.w;
-            y[4] += b1.x, y[5] += b1.y, y[6] += b1.z, y[7] += b1.w;
+    if constexpr (kSplit) {
+      // ------------------------------------------------------------ split-K: reduce-scatter over the cluster
+      __syncwarp();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      if (static_cast<int>(blockIdx.x) < num_tiles) {
+        const int tile = blockIdx.x / p.splits;
+        const int rank = blockIdx.x - tile * p.splits;  // == %cluster_ctarank for 1-D clusters of `splits` CTAs
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int row = warp * 32 + lane;
+        const long long m = static_cast<long long>(m_tile) * kBlockM + row;
+        const int cols_per_rank = BN / p.splits;
+        const uint32_t part0 = smem_u32(smem_a);
+        if (m < p.M) {
+  #pragma unroll 1
+          for (int c = rank * cols_per_rank; c < (rank + 1) * cols_per_rank; c += 8) {
+            const int n0 = n_tile * BN + c;
+            if (n0 >= p.cout_store) break;
+            float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const uint32_t off = static_cast<uint32_t>(((c >> 2) * kBlockM + row) * 16);
+  #pragma unroll 1
+            for (int s0 = 0; s0 < p.splits; s0 += 2) {  // fixed summation order: split 0, 1, 2, ...
+              const uint32_t ra = map_shared_rank(part0, s0) + off;
+              const uint32_t rb = map_shared_rank(part0, s0 + 1) + off;
+              const float4 a0 = ld_dsmem_v4(ra), a1 = ld_dsmem_v4(ra + kBlockM * 16);
+              const float4 b0 = ld_dsmem_v4(rb), b1 = ld_dsmem_v4(rb + kBlockM * 16);
+              y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w;
+              y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
+              y[0] += b0.x, y[1] += b0.y, y[2] += b0.z, y[3] += b0.w;
+              y[4] += b1.x, y[5] += b1.y, y[6] += b1.z, y[7] += b1.w;
+            }
+  #pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
+            epilogue_store8<T>(p, m, n0, y);
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
-          epilogue_store8<T>(p, m, n0, y);
         }
       }
+      // nobody may exit (and release its shared memory) while a peer can still be reading it
+      __syncwarp();
+      cluster_arrive_release();
+      cluster_wait_acquire();
     }
-    // nobody may exit (and release its shared memory) while a peer can still be reading it
-    __syncwarp();
-    cluster_arrive_release();
-    cluster_wait_acquire();
+
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

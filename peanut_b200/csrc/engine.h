@@ -160,6 +160,7 @@ struct ConvSpec {
   int force_bn = 0;  // test hook: force the N tile
   int force_splits = 0;  // test hook: force the split-K factor
   bool no_split = false;  // never split K (layers whose row count is dynamic keep one CTA per tile)
+  long long* dbg = nullptr;  // tuning aid: per-tile clock64 timeline of CTA 0
   bool force_direct_epilogue = false;  // test hook: bypass the TMA-staged epilogue
   // Dynamic row limit: when set, only the first (*m_limit) * m_limit_rows GEMM rows are computed (device-side
   // count of valid ROIs x rows per ROI); tiles beyond are skipped by every warp role.

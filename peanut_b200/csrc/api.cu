@@ -29,6 +29,7 @@ struct Ctx {
 thread_local std::string g_last_error;
 
 __global__ void set_pred_slots_kernel(PredSlots* slots, const float* in, float* out, int apply_sigmoid) {
+  pdl_grid_sync();
   slots->input = in;
   slots->output = out;
   slots->apply_sigmoid = apply_sigmoid;
@@ -37,6 +38,7 @@ __global__ void set_pred_slots_kernel(PredSlots* slots, const float* in, float* 
 // NHWC (dt) -> NCHW fp32, first C channels.
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* in, long long ldi, float* out, int B, int C, int HW) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * C * HW;
   if (idx >= total) return;
@@ -53,14 +55,15 @@ void nhwc_to_nchw(const Tensor& t, int C, float* out, cudaStream_t s) {
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   if (t.dt == kBF16)
-    nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(t.ptr), t.ld, out, t.B, C, HW);
+    launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, blocks, threads, 0, s, static_cast<const __nv_bfloat16*>(t.ptr), t.ld, out, t.B, C, HW);
   else
-    nhwc_to_nchw_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(t.ptr), t.ld, out, t.B, C, HW);
+    launch_pdl(nhwc_to_nchw_kernel<float>, blocks, threads, 0, s, static_cast<const float*>(t.ptr), t.ld, out, t.B, C, HW);
 }
 
 // NCHW fp32 -> NHWC (dt) first C channels of an existing tensor (tap injection).
 template <typename T>
 __global__ void nchw_to_nhwc_direct_kernel(const float* in, T* out, long long ldo, int B, int C, int HW, int round_tf32) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * C * HW;
   if (idx >= total) return;
@@ -83,9 +86,9 @@ void nchw_to_nhwc_direct(const float* in, const Tensor& t, int C, cudaStream_t s
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   if (t.dt == kBF16)
-    nchw_to_nhwc_direct_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(in, static_cast<__nv_bfloat16*>(t.ptr), t.ld, t.B, C, HW, 0);
+    launch_pdl(nchw_to_nhwc_direct_kernel<__nv_bfloat16>, blocks, threads, 0, s, in, static_cast<__nv_bfloat16*>(t.ptr), t.ld, t.B, C, HW, 0);
   else
-    nchw_to_nhwc_direct_kernel<float><<<blocks, threads, 0, s>>>(in, static_cast<float*>(t.ptr), t.ld, t.B, C, HW, 1);
+    launch_pdl(nchw_to_nhwc_direct_kernel<float>, blocks, threads, 0, s, in, static_cast<float*>(t.ptr), t.ld, t.B, C, HW, 1);
 }
 
 void check_device(Ctx* c) {
@@ -195,7 +198,7 @@ int pn_prednet_forward(pn_ctx* ctx, const float* map_dev, int apply_sigmoid, flo
   PN_REQUIRE(c->prednet, "pn_prednet_forward: call pn_prednet_build first");
   PN_REQUIRE(map_dev && out_dev, "pn_prednet_forward: null buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  set_pred_slots_kernel<<<1, 1, 0, s>>>(c->prednet->slots, map_dev, out_dev, apply_sigmoid);
+  launch_pdl(set_pred_slots_kernel, 1, 1, 0, s, c->prednet->slots, map_dev, out_dev, apply_sigmoid);
   c->prednet->net.run(s);
   PN_CUDA_CHECK(cudaGetLastError());
   PN_API_END
@@ -214,7 +217,7 @@ int pn_prednet_forward_host(pn_ctx* ctx, const float* map_host, int apply_sigmoi
     n.stage_out = static_cast<float*>(n.net.arena.alloc(out_bytes, false));
   }
   PN_CUDA_CHECK(cudaMemcpyAsync(n.stage_in, map_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
-  set_pred_slots_kernel<<<1, 1, 0, c->stream>>>(n.slots, n.stage_in, n.stage_out, apply_sigmoid);
+  launch_pdl(set_pred_slots_kernel, 1, 1, 0, c->stream, n.slots, n.stage_in, n.stage_out, apply_sigmoid);
   n.net.run(c->stream);
   PN_CUDA_CHECK(cudaMemcpyAsync(out_host, n.stage_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -629,7 +632,7 @@ int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int 
   sp.force_splits = (force_bn >> 16) & 0xff;
   long long* dbg = nullptr;
   if (std::getenv("PN_CONV_DBG")) {
-    dbg = static_cast<long long*>(net.arena.alloc(64 * 16 * sizeof(long long)));
+    dbg = static_cast<long long*>(net.arena.alloc((1024 + 1 + 64 * 4) * sizeof(long long)));
     sp.dbg = dbg;
   }
   add_conv(net, "bench", x, y, w.data(), sc.data(), bi.data(), sp, with_residual ? &res : nullptr);
@@ -648,16 +651,21 @@ int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int 
   cudaEventDestroy(e1);
   *ms_out = ms / iters;
   if (dbg) {  // timeline of CTA 0 in the last launch, cycles relative to its first event
-    std::vector<long long> h(64 * 16);
+    std::vector<long long> h(1024 + 1 + 64 * 4);
     PN_CUDA_CHECK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     long long t0 = 0;
-    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    for (int i = 0; i < 1024; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
     std::printf("# CTA0 timeline (cycles): tile: load0 | mma: enter, acc free, first mma, commit | epi: enter, acc full, done | group pairs\n");
     for (int t = 0; t < 64; ++t) {
       if (!h[t * 16 + 6]) break;
       std::printf("tile %2d:", t);
       for (int k = 0; k < 16; ++k) std::printf(" %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
       std::printf("\n");
+    }
+    std::printf("# CTA0 launch log (ns): entry->wait_done, wait_done->exit, exit->next wait_done\n");
+    for (long long i = 0; i < h[1024] && i < 64; ++i) {
+      const long long* e = &h[1025 + 4 * i];
+      std::printf("launch %2lld: %7lld %7lld %7lld\n", i, e[1] - e[0], e[2] - e[1], i + 1 < h[1024] ? h[1025 + 4 * (i + 1) + 1] - e[2] : -1);
     }
   }
   PN_API_END

@@ -87,10 +87,10 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// Round to the 10-bit tf32 mantissa, nearest with ties away from zero (what cvt.rna.tf32.f32 does for finite values),
+// in two full-rate integer instructions instead of a quarter-rate conversion.
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 // Byte offset of 16-byte unit j of row r inside a TMA-swizzled tile whose rows are cb bytes.
 __device__ __forceinline__ uint32_t swz_off(uint32_t r, uint32_t j, uint32_t cb) {
@@ -144,8 +144,19 @@ __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long m
 // Tuning aid (build with -DPN_CONV_TIMELINE, run tools/conv_one.py with PN_CONV_DBG=1): clock64 timeline of CTA 0.
 #ifdef PN_CONV_TIMELINE
 #define PN_DBG(iter, slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < 64) p.dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ long long pn_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// launch log of CTA 0 (thread 0): dbg[1024] counts launches, dbg[1025 + 4*i + {0,1,2}] = globaltimer at entry / after
+// griddepcontrol.wait / at exit of launch i
+#define PN_LOG(which) do { if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { \
+    const long long n_ = p.dbg[1024]; if (n_ < 64) p.dbg[1025 + 4 * n_ + (which)] = pn_globaltimer(); \
+    if ((which) == 2) p.dbg[1024] = n_ + 1; } } while (0)
 #else
 #define PN_DBG(iter, slot) do { } while (0)
+#define PN_LOG(which) do { } while (0)
 #endif
 
 template <typename T, int BN, bool kSplit>
@@ -156,6 +167,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // Programmatic dependent launch: let the next kernel in the stream start its prologue (and become resident next
   // to this CTA when both fit) right away; it blocks in griddep_wait() until this grid has completed.
   griddep_launch_dependents();
+  PN_LOG(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = kBlockM * p.sw;
@@ -228,6 +240,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // everything above (barrier init, TMEM allocation, descriptor prefetch, weight prefetch) overlapped the previous
   // kernel's tail; from here on we read what it wrote
   griddep_wait();
+  PN_LOG(1);
 
   int m_tiles_live = p.m_tiles;
   if (p.m_limit != nullptr) {
@@ -377,6 +390,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t out_addr = smem_u32(smem_out);
     const uint32_t res_addr = smem_u32(smem_res);
     const bool has_res = p.residual != nullptr;
+    // 16-byte unit j of this thread's row inside a TMA-swizzled chunk buffer: row_off + ((j ^ row_xor) << 4)
+    const uint32_t row_off = row * p.cb;
+    const uint32_t row_xor = (p.cb == 128) ? (row & 7u) : (p.cb == 64 ? ((row >> 1) & 3u) : 0u);
     uint32_t g = 0;  // running chunk counter (same sequence as the residual prefetcher)
     uint32_t rb = 0, rphase = 0;  // residual ring slot / phase of chunk g
     int it = 0;
@@ -419,58 +435,71 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (has_res) mbar_wait(&rfull_bar[rb], rphase);
         }
-        if (warp == 0 && lane == 0 && grp < 2) PN_DBG(it, 8 + grp * 4);
+        // All shared-memory loads of the group are issued back to back (the asm statements keep program order, so
+        // interleaving them with the stores would serialise one load-compute-store chain per 16-byte unit).
         const uint32_t sb = sb_addr + grp * 32 * 4;
+        float4 sc[8], bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sc[j] = lds_f4(sb + j * 16);
+          bi[j] = lds_f4(sb + BN * 4 + j * 16);
+        }
+        uint4 rv[kUnits];
+        if (has_res) {
+          const uint32_t rbuf = res_addr + rb * chunk_bytes + row_off;
+#pragma unroll
+          for (int u = 0; u < kUnits; ++u) rv[u] = lds_v4(rbuf + ((static_cast<uint32_t>(sub * kUnits + u) ^ row_xor) << 4));
+        }
         float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 sc = lds_f4(sb + j * 4);
-          const float4 bi = lds_f4(sb + (BN + j) * 4);
-          y[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
-          y[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-          y[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-          y[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+        for (int j = 0; j < 8; ++j) {
+          y[4 * j] = fmaf(__uint_as_float(v[4 * j]), sc[j].x, bi[j].x);
+          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc[j].y, bi[j].y);
+          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc[j].z, bi[j].z);
+          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc[j].w, bi[j].w);
         }
         if (has_res) {
-          const uint32_t rbuf = res_addr + rb * chunk_bytes;
 #pragma unroll
           for (int u = 0; u < kUnits; ++u) {
-            const uint4 rv = lds_v4(rbuf + swz_off(row, sub * kUnits + u, p.cb));
             if constexpr (sizeof(T) == 2) {
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+              const uint32_t w[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 y[u * 8 + 2 * e] += __uint_as_float(w[e] << 16);
                 y[u * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
               }
             } else {
-              y[u * 4] += __uint_as_float(rv.x);
-              y[u * 4 + 1] += __uint_as_float(rv.y);
-              y[u * 4 + 2] += __uint_as_float(rv.z);
-              y[u * 4 + 3] += __uint_as_float(rv.w);
+              y[u * 4] += __uint_as_float(rv[u].x);
+              y[u * 4 + 1] += __uint_as_float(rv[u].y);
+              y[u * 4 + 2] += __uint_as_float(rv[u].z);
+              y[u * 4 + 3] += __uint_as_float(rv[u].w);
             }
           }
         }
+        uint4 ov[kUnits];
 #pragma unroll
         for (int u = 0; u < kUnits; ++u) {
-          uint32_t o0, o1, o2, o3;
           if constexpr (sizeof(T) == 2) {
             if (p.relu) {
-              o0 = pack_bf16_relu(y[u * 8], y[u * 8 + 1]), o1 = pack_bf16_relu(y[u * 8 + 2], y[u * 8 + 3]);
-              o2 = pack_bf16_relu(y[u * 8 + 4], y[u * 8 + 5]), o3 = pack_bf16_relu(y[u * 8 + 6], y[u * 8 + 7]);
+              ov[u].x = pack_bf16_relu(y[u * 8], y[u * 8 + 1]), ov[u].y = pack_bf16_relu(y[u * 8 + 2], y[u * 8 + 3]);
+              ov[u].z = pack_bf16_relu(y[u * 8 + 4], y[u * 8 + 5]), ov[u].w = pack_bf16_relu(y[u * 8 + 6], y[u * 8 + 7]);
             } else {
-              o0 = pack_bf16(y[u * 8], y[u * 8 + 1]), o1 = pack_bf16(y[u * 8 + 2], y[u * 8 + 3]);
-              o2 = pack_bf16(y[u * 8 + 4], y[u * 8 + 5]), o3 = pack_bf16(y[u * 8 + 6], y[u * 8 + 7]);
+              ov[u].x = pack_bf16(y[u * 8], y[u * 8 + 1]), ov[u].y = pack_bf16(y[u * 8 + 2], y[u * 8 + 3]);
+              ov[u].z = pack_bf16(y[u * 8 + 4], y[u * 8 + 5]), ov[u].w = pack_bf16(y[u * 8 + 6], y[u * 8 + 7]);
             }
           } else {
             float a = y[u * 4], b = y[u * 4 + 1], c = y[u * 4 + 2], d = y[u * 4 + 3];
             if (p.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f), c = fmaxf(c, 0.f), d = fmaxf(d, 0.f);
             if (p.round_tf32) a = round_tf32(a), b = round_tf32(b), c = round_tf32(c), d = round_tf32(d);
-            o0 = __float_as_uint(a), o1 = __float_as_uint(b), o2 = __float_as_uint(c), o3 = __float_as_uint(d);
+            ov[u].x = __float_as_uint(a), ov[u].y = __float_as_uint(b), ov[u].z = __float_as_uint(c), ov[u].w = __float_as_uint(d);
           }
-          sts_v4(obuf + swz_off(row, sub * kUnits + u, p.cb), o0, o1, o2, o3);
         }
-        if (warp == 0 && lane == 0 && grp < 2) PN_DBG(it, 10 + grp * 4);
+        {
+          const uint32_t ob = obuf + row_off;
+#pragma unroll
+          for (int u = 0; u < kUnits; ++u)
+            sts_v4(ob + ((static_cast<uint32_t>(sub * kUnits + u) ^ row_xor) << 4), ov[u].x, ov[u].y, ov[u].z, ov[u].w);
+        }
         if (sub == subs_per_chunk - 1) {
           fence_proxy_async();  // make the st.shared above visible to the TMA (async proxy)
           __syncwarp();
@@ -483,7 +512,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ++g;
           if (has_res && ++rb == static_cast<uint32_t>(p.res_bufs)) rb = 0, rphase ^= 1;
         }
-        if (warp == 0 && lane == 0 && grp < 2) PN_DBG(it, 11 + grp * 4);
+        if (warp == 0 && lane == 0 && grp < 8) PN_DBG(it, 8 + grp);
       };
 
       uint32_t va[32], vb[32];
@@ -621,6 +650,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  PN_LOG(2);
 }
 
 }  // namespace pn

@@ -93,6 +93,7 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n) {
 template <typename T>
 __global__ void k_upsample2x_add(const T* __restrict__ prev, long long ldp, int h, int w, T* __restrict__ lat, long long ldl,
                                  int B, int H, int W, int C8, int round_tf32) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * H * W * C8;
   if (idx >= total) return;
@@ -122,6 +123,7 @@ __global__ void k_upsample2x_add(const T* __restrict__ prev, long long ldp, int 
 template <typename T>
 __global__ void k_subsample2(const T* __restrict__ in, long long ldi, int H, int W, T* __restrict__ out, long long ldo, int B,
                              int Ho, int Wo, int C8) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * Ho * Wo * C8;
   if (idx >= total) return;
@@ -157,6 +159,7 @@ struct RpnSmem {
 constexpr int kPixPerBlock = 1024;
 
 __global__ void __launch_bounds__(256) k_rpn_hist(RpnMeta meta, uint32_t* __restrict__ hist) {
+  pdl_grid_sync();
   const int L = blockIdx.y % kRpnLevels, b = blockIdx.y / kRpnLevels;
   const RpnLevel& lv = meta.lv[L];
   const int npix = lv.H * lv.W;
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(256) k_rpn_hist(RpnMeta meta, uint32_t* __rest
 
 __global__ void __launch_bounds__(1024) k_rpn_threshold(RpnMeta meta, const uint32_t* __restrict__ hist,
                                                         uint32_t* __restrict__ thr_bin, int* __restrict__ ncand) {
+  pdl_grid_sync();
   __shared__ int warp_sums[33];
   __shared__ uint32_t s_bin;
   const int L = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(1024) k_rpn_threshold(RpnMeta meta, const uint
 
 __global__ void __launch_bounds__(256) k_rpn_collect(RpnMeta meta, const uint32_t* __restrict__ thr_bin, int* __restrict__ ncand,
                                                      unsigned long long* __restrict__ cand) {
+  pdl_grid_sync();
   const int L = blockIdx.y % kRpnLevels, b = blockIdx.y / kRpnLevels;
   const RpnLevel& lv = meta.lv[L];
   const int npix = lv.H * lv.W;
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_sort_decode(RpnMeta meta, const
                                                              const unsigned long long* __restrict__ cand,
                                                              float4* __restrict__ sbox, float* __restrict__ sscore,
                                                              int* __restrict__ scount) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   RpnSmem& S = *reinterpret_cast<RpnSmem*>(smem_raw);
   const int L = blockIdx.x, b = blockIdx.y;
@@ -402,6 +408,7 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_sort_decode(RpnMeta meta, const
 
 __global__ void __launch_bounds__(256) k_rpn_mask(float nms_thr, const float4* __restrict__ sbox, const int* __restrict__ scount,
                                                   uint32_t* __restrict__ mask_g) {
+  pdl_grid_sync();
   __shared__ float4 box[kRpnCap];
   const int L = blockIdx.y, b = blockIdx.z;
   const int m = scount[b * kRpnLevels + L];
@@ -430,6 +437,7 @@ __global__ void __launch_bounds__(1024, 1) k_rpn_sweep(const float4* __restrict_
                                                        const int* __restrict__ scount, const uint32_t* __restrict__ mask_g,
                                                        float* __restrict__ lvl_boxes, float* __restrict__ lvl_scores,
                                                        int* __restrict__ lvl_count) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint32_t mask[];  // [kRpnCap][32]
   __shared__ int kept[kRpnCap];
   __shared__ int s_nkept;
@@ -493,6 +501,7 @@ __global__ void __launch_bounds__(1024) k_rpn_merge(int post_topk, const float* 
                                                     const float* __restrict__ lvl_scores, const int* __restrict__ lvl_count,
                                                     float* __restrict__ prop_boxes, float* __restrict__ prop_scores,
                                                     int* __restrict__ prop_img, int* __restrict__ prop_count) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   __shared__ int cnt[kRpnLevels];
   if (threadIdx.x < kRpnLevels) cnt[threadIdx.x] = lvl_count[b * kRpnLevels + threadIdx.x];
@@ -571,6 +580,7 @@ struct RoiSample {
 template <typename T>
 __global__ void __launch_bounds__(448) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
                                                    int S, T* __restrict__ out, long long ldo) {
+  pdl_grid_sync();
   const int r = blockIdx.y;
   const int b = img[r];
   if (b < 0) return;
@@ -681,6 +691,7 @@ __global__ void __launch_bounds__(1024, 1) k_detections(const MrcnnSlots* __rest
                                                         float* __restrict__ det_boxes, float* __restrict__ det_scores,
                                                         int* __restrict__ det_classes, int* __restrict__ det_count, int cap,
                                                         float4* __restrict__ cand_boxes, int* __restrict__ cand_cls) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) unsigned long long dkeys[];  // [cap]
   __shared__ int s_n;
   __shared__ float4 kbox[128];
@@ -775,6 +786,7 @@ __global__ void __launch_bounds__(1024, 1) k_detections(const MrcnnSlots* __rest
 __global__ void k_compact_dets(int B, int max_det, const float* __restrict__ det_boxes, const int* __restrict__ det_classes,
                                const int* __restrict__ det_count, float* __restrict__ mroi_boxes, int* __restrict__ mroi_img,
                                int* __restrict__ mroi_cls, int* __restrict__ mroi_total) {
+  pdl_grid_sync();
   __shared__ int start[1025];
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -812,6 +824,7 @@ __global__ void __launch_bounds__(256) k_paste_prepare(const MrcnnSlots* __restr
                                                        const float* __restrict__ mroi_boxes, const int* __restrict__ mroi_cls,
                                                        float4* __restrict__ act_box, int* __restrict__ act_cls,
                                                        int* __restrict__ act_roi, int* __restrict__ act_n) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   // zero this frame's output stack (grid.x CTAs share the work)
   float4* out4 = reinterpret_cast<float4*>(slots->sem_out + static_cast<size_t>(b) * H * W * (K + 1));
@@ -855,6 +868,7 @@ __global__ void __launch_bounds__(256) k_paste_dets(const MrcnnSlots* __restrict
                                                     float mask_thr, const float4* __restrict__ act_box,
                                                     const int* __restrict__ act_cls, const int* __restrict__ act_roi,
                                                     const int* __restrict__ act_n, const float* __restrict__ mask_logits) {
+  pdl_grid_sync();
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= act_n[b]) return;
   __shared__ float prob[28 * 28];
@@ -905,9 +919,9 @@ void add_upsample2x_add(Net& net, const Tensor& prev, const Tensor& lat) {
   Tensor p = prev, l = lat;
   net.add("fpn_upsample_add", [=](cudaStream_t s) {
     if (l.dt == kBF16)
-      k_upsample2x_add<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(p.ptr), p.ld, p.H, p.W, static_cast<__nv_bfloat16*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 0);
+      launch_pdl(k_upsample2x_add<__nv_bfloat16>, blocks, threads, 0, s, static_cast<const __nv_bfloat16*>(p.ptr), p.ld, p.H, p.W, static_cast<__nv_bfloat16*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 0);
     else
-      k_upsample2x_add<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(p.ptr), p.ld, p.H, p.W, static_cast<float*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 1);
+      launch_pdl(k_upsample2x_add<float>, blocks, threads, 0, s, static_cast<const float*>(p.ptr), p.ld, p.H, p.W, static_cast<float*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 1);
   });
   net.launches_per_forward += 1;
 }
@@ -921,9 +935,9 @@ void add_subsample2(Net& net, const Tensor& in, const Tensor& out) {
   Tensor i = in, o = out;
   net.add("fpn_p6_subsample", [=](cudaStream_t s) {
     if (i.dt == kBF16)
-      k_subsample2<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(i.ptr), i.ld, i.H, i.W, static_cast<__nv_bfloat16*>(o.ptr), o.ld, o.B, o.H, o.W, C8);
+      launch_pdl(k_subsample2<__nv_bfloat16>, blocks, threads, 0, s, static_cast<const __nv_bfloat16*>(i.ptr), i.ld, i.H, i.W, static_cast<__nv_bfloat16*>(o.ptr), o.ld, o.B, o.H, o.W, C8);
     else
-      k_subsample2<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(i.ptr), i.ld, i.H, i.W, static_cast<float*>(o.ptr), o.ld, o.B, o.H, o.W, C8);
+      launch_pdl(k_subsample2<float>, blocks, threads, 0, s, static_cast<const float*>(i.ptr), i.ld, i.H, i.W, static_cast<float*>(o.ptr), o.ld, o.B, o.H, o.W, C8);
   });
   net.launches_per_forward += 1;
 }
@@ -948,9 +962,9 @@ void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
   const size_t hist_bytes = static_cast<size_t>(B) * kRpnLevels * kHistBins * sizeof(uint32_t);
   net.add("rpn_preselect", [=](cudaStream_t s) {
     PN_CUDA_CHECK(cudaMemsetAsync(hist, 0, hist_bytes, s));
-    k_rpn_hist<<<scan_grid, 256, 0, s>>>(meta, hist);
-    k_rpn_threshold<<<dim3(kRpnLevels, B), 1024, 0, s>>>(meta, hist, thr, ncand);
-    k_rpn_collect<<<scan_grid, 256, 0, s>>>(meta, thr, ncand, cand);
+    launch_pdl(k_rpn_hist, scan_grid, 256, 0, s, meta, hist);
+    launch_pdl(k_rpn_threshold, dim3(kRpnLevels, B), 1024, 0, s, meta, hist, thr, ncand);
+    launch_pdl(k_rpn_collect, scan_grid, 256, 0, s, meta, thr, ncand, cand);
   });
   net.launches_per_forward += 4;
   float4* sbox = static_cast<float4*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kRpnCap * sizeof(float4)));
@@ -958,10 +972,10 @@ void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
   int* scount = static_cast<int*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * sizeof(int)));
   uint32_t* mask_g = static_cast<uint32_t*>(net.arena.alloc(static_cast<size_t>(B) * kRpnLevels * kRpnCap * 32 * sizeof(uint32_t)));
   const float nms_thr = meta.nms_thr;
-  net.add("rpn_sort_decode", [=](cudaStream_t s) { k_rpn_sort_decode<<<dim3(kRpnLevels, B), 1024, smem, s>>>(meta, ncand, cand, sbox, sscore, scount); });
+  net.add("rpn_sort_decode", [=](cudaStream_t s) { launch_pdl(k_rpn_sort_decode, dim3(kRpnLevels, B), 1024, smem, s, meta, ncand, cand, sbox, sscore, scount); });
   net.add("rpn_nms", [=](cudaStream_t s) {
-    k_rpn_mask<<<dim3(kRpnCap / 32, kRpnLevels, B), 256, 0, s>>>(nms_thr, sbox, scount, mask_g);
-    k_rpn_sweep<<<dim3(kRpnLevels, B), 1024, smem_mask, s>>>(sbox, sscore, scount, mask_g, lb, ls, lc);
+    launch_pdl(k_rpn_mask, dim3(kRpnCap / 32, kRpnLevels, B), 256, 0, s, nms_thr, sbox, scount, mask_g);
+    launch_pdl(k_rpn_sweep, dim3(kRpnLevels, B), 1024, smem_mask, s, sbox, sscore, scount, mask_g, lb, ls, lc);
   });
   net.launches_per_forward += 2;
   float* pb = m.prop_boxes;
@@ -969,7 +983,7 @@ void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
   int* pi = m.prop_img;
   int* pc = m.prop_count;
   const int post = meta.post_topk;
-  net.add("rpn_merge", [=](cudaStream_t s) { k_rpn_merge<<<B, 1024, 0, s>>>(post, lb, ls, lc, pb, ps, pi, pc); });
+  net.add("rpn_merge", [=](cudaStream_t s) { launch_pdl(k_rpn_merge, B, 1024, 0, s, post, lb, ls, lc, pb, ps, pi, pc); });
   net.launches_per_forward += 2;
 }
 
@@ -979,9 +993,9 @@ void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr, DType 
   Tensor o = out;
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
-      k_roi_align<__nv_bfloat16><<<dim3(S, nrois), S * 32, 0, s>>>(pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
+      launch_pdl(k_roi_align<__nv_bfloat16>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
     else
-      k_roi_align<float><<<dim3(S, nrois), S * 32, 0, s>>>(pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
+      launch_pdl(k_roi_align<float>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
   });
   net.launches_per_forward += 1;
 }
@@ -1006,7 +1020,7 @@ void add_detections(Net& net, MaskRcnn& m) {
   float4* cand_boxes = static_cast<float4*>(net.arena.alloc(static_cast<size_t>(c.B) * cap * sizeof(float4)));
   int* cand_cls = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * cap * sizeof(int)));
   net.add("detections", [=](cudaStream_t s) {
-    k_detections<<<c.B, 1024, smem, s>>>(slots, c.num_classes, c.post_nms_topk, c.detections, c.box_nms, img_h, img_w, box_out,
+    launch_pdl(k_detections, c.B, 1024, smem, s, slots, c.num_classes, c.post_nms_topk, c.detections, c.box_nms, img_h, img_w, box_out,
                                          64, pb, pc, db, ds, dc, dn, cap, cand_boxes, cand_cls);
   });
   float* mb = m.mroi_boxes;
@@ -1014,7 +1028,7 @@ void add_detections(Net& net, MaskRcnn& m) {
   int* mc = m.mroi_cls;
   int* mt = m.mroi_total;
   PN_REQUIRE(c.B <= 1024, "detections: batch too large");
-  net.add("compact_dets", [=](cudaStream_t s) { k_compact_dets<<<1, 256, 0, s>>>(c.B, c.detections, db, dc, dn, mb, mi, mc, mt); });
+  net.add("compact_dets", [=](cudaStream_t s) { launch_pdl(k_compact_dets, 1, 256, 0, s, c.B, c.detections, db, dc, dn, mb, mi, mc, mt); });
   net.launches_per_forward += 2;
 }
 
@@ -1035,10 +1049,10 @@ void add_paste_accumulate(Net& net, MaskRcnn& m) {
   int* ar = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * c.detections * sizeof(int)));
   int* an = static_cast<int*>(net.arena.alloc(static_cast<size_t>(c.B) * sizeof(int)));
   net.add("paste_prepare", [=](cudaStream_t s) {
-    k_paste_prepare<<<dim3(64, c.B), 256, 0, s>>>(slots, c.H, c.W, c.num_classes, c.detections, sx, sy, ds, dn, mt, mb, mc, ab, ac, ar, an);
+    launch_pdl(k_paste_prepare, dim3(64, c.B), 256, 0, s, slots, c.H, c.W, c.num_classes, c.detections, sx, sy, ds, dn, mt, mb, mc, ab, ac, ar, an);
   });
   net.add("paste_dets", [=](cudaStream_t s) {
-    k_paste_dets<<<dim3(kPasteSplit, c.detections, c.B), 256, 0, s>>>(slots, c.H, c.W, c.num_classes, c.detections, c.mask_thresh,
+    launch_pdl(k_paste_dets, dim3(kPasteSplit, c.detections, c.B), 256, 0, s, slots, c.H, c.W, c.num_classes, c.detections, c.mask_thresh,
                                                                      ab, ac, ar, an, ml);
   });
   net.launches_per_forward += 2;

@@ -30,6 +30,29 @@ inline size_t dtype_size(DType d) { return d == kBF16 ? 2 : 4; }
     if (!(cond)) throw std::runtime_error(std::string("peanut_b200: ") + (msg));     \
   } while (0)
 
+
+// ---- programmatic dependent launch for every non-GEMM kernel of the launch lists.
+// Each kernel starts with pdl_grid_sync(): it lets the NEXT kernel of the stream become resident right away and then
+// blocks until the PREVIOUS kernel has completed and flushed, so launch latency and block scheduling overlap the
+// predecessor's tail while every memory access stays ordered exactly as with plain stream serialization.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
+template <typename... P, typename... A>
+inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...));
+}
+
 // NHWC view: element (b, y, x, c) lives at ptr + ((b*H + y)*W + x)*ld + c.
 struct Tensor {
   void* ptr = nullptr;
@@ -116,7 +139,26 @@ struct Net {
   int warm_runs = 0;
   bool use_graph = true;
 
+  // Parallel lanes: ops added while cur_lane != 0 are launched on side stream `cur_lane`.  A side-lane op is ordered
+  // after every lane-0 op that precedes it in the list and after the earlier ops of its own lane; lane 0 (the caller's
+  // stream) does not wait for side lanes until join_lanes() - placed before the first op that consumes their results -
+  // or the end of the list.  run_range / profiling replay the list on one stream in list order, which satisfies the
+  // same dependencies.
+  std::vector<int> op_lane;
+  std::vector<char> op_join;  // join every side lane into lane 0 before this op
+  int cur_lane = 0;
+  bool pending_join = false;
+  static constexpr int kMaxLanes = 4;
+  cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_fork[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_done[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  void set_lane(int lane) { cur_lane = lane; }
+  void join_lanes() { pending_join = true, cur_lane = 0; }
+
   void add(const std::string& name, std::function<void(cudaStream_t)> f, double flops = 0.0) {
+    op_lane.push_back(cur_lane);
+    op_join.push_back(pending_join ? 1 : 0);
+    pending_join = false;
     ops.push_back(std::move(f));
     op_names.push_back(name);
     op_flops.push_back(flops);
@@ -134,9 +176,7 @@ struct Net {
     for (double f : op_flops) t += f;
     return t;
   }
-  void run_eager(cudaStream_t s) {
-    for (auto& f : ops) f(s);
-  }
+  void run_eager(cudaStream_t s);
   void run_range(int first, int last, cudaStream_t s) {
     for (int i = first; i < last; ++i) ops[i](s);
   }

@@ -124,9 +124,14 @@ void build_maskrcnn(MaskRcnn& m, const WeightStore& w, const MrcnnCfg& cfg, DTyp
       const std::string pre = bu + "res" + std::to_string(si + 2) + "." + std::to_string(bi);
       const int stride = (bi == 0 && si > 0) ? 2 : 1;
       Tensor identity = x;
-      if (bi == 0) identity = conv_frozen_bn(net, w, pre + ".shortcut", x, spec(cin, cout, 1, stride, 0, false));
+      if (bi == 0) {  // the projection shortcut runs beside conv1 -> conv2 on a side lane
+        net.set_lane(1);
+        identity = conv_frozen_bn(net, w, pre + ".shortcut", x, spec(cin, cout, 1, stride, 0, false));
+        net.set_lane(0);
+      }
       Tensor t = conv_frozen_bn(net, w, pre + ".conv1", x, spec(cin, mid, 1, stride, 0, true));
       t = conv_frozen_bn(net, w, pre + ".conv2", t, spec(mid, mid, 3, 1, 1, true));
+      if (bi == 0) net.join_lanes();
       x = conv_frozen_bn(net, w, pre + ".conv3", t, spec(mid, cout, 1, 1, 0, true), &identity);
       cin = cout;
     }
@@ -135,57 +140,65 @@ void build_maskrcnn(MaskRcnn& m, const WeightStore& w, const MrcnnCfg& cfg, DTyp
   }
 
   // ---- FPN (yaml:62-70): lateral 1x1 (+ nearest x2 of the coarser level), output 3x3, p6 = stride-2 subsample of p5
+  // ---- RPN head (shared over levels): 3x3 + ReLU, then objectness (3) and anchor deltas (12) as ONE 1x1 -> fp32.
+  // The top-down chain (laterals + upsample-adds) and the finest level stay on lane 0; the output conv and the RPN head
+  // of each coarser level form a chain of their own on a side lane (P5 and P6 share one) and run beside it.
   net.stage("fpn");
   Tensor P[5];
+  const int strides[5] = {4, 8, 16, 32, 64};
+  RpnMeta meta{};
+  const std::string rp = "proposal_generator.rpn_head.";
+  std::vector<float> wm(15 * 256), bm(15);
+  {
+    const HostArray& wo = conv_weight(w, rp + "objectness_logits.weight", kAnchors, 256, 1);
+    const HostArray& bo = get_weight(w, rp + "objectness_logits.bias");
+    const HostArray& wd = conv_weight(w, rp + "anchor_deltas.weight", 4 * kAnchors, 256, 1);
+    const HostArray& bd = get_weight(w, rp + "anchor_deltas.bias");
+    std::copy(wo.data.begin(), wo.data.end(), wm.begin());
+    std::copy(wd.data.begin(), wd.data.end(), wm.begin() + 3 * 256);
+    std::copy(bo.data.begin(), bo.data.end(), bm.begin());
+    std::copy(bd.data.begin(), bd.data.end(), bm.begin() + 3);
+  }
+  auto add_rpn_level = [&](int l) {
+    const double sizes[5] = {32, 64, 128, 256, 512}, ratios[3] = {0.5, 1.0, 2.0};  // yaml:45-58
+    Tensor t = conv_bias(net, w, rp + "conv", P[l], spec(256, 256, 3, 1, 1, true));
+    Tensor head = A.tensor(B, t.H, t.W, kRpnHeadC, kF32);
+    ConvSpec s = spec(256, 15, 1, 1, 0, false);
+    s.out_fp32 = true;
+    add_conv(net, rp + "predictors.p" + std::to_string(l + 2), t, head, wm.data(), nullptr, bm.data(), s);
+    m.rpn_head[l] = static_cast<float*>(head.ptr);
+    m.rpn_hw[l][0] = t.H, m.rpn_hw[l][1] = t.W;
+    RpnLevel& lv = meta.lv[l];
+    lv.head = m.rpn_head[l], lv.H = t.H, lv.W = t.W, lv.stride = strides[l];
+    for (int a = 0; a < kAnchors; ++a) {  // DefaultAnchorGenerator.generate_cell_anchors
+      const double area = sizes[l] * sizes[l];
+      const double ww = std::sqrt(area / ratios[a]), hh = ratios[a] * ww;
+      lv.base[a][0] = static_cast<float>(-ww / 2.0), lv.base[a][1] = static_cast<float>(-hh / 2.0);
+      lv.base[a][2] = static_cast<float>(ww / 2.0), lv.base[a][3] = static_cast<float>(hh / 2.0);
+    }
+    net.raw_taps["rpn_head.p" + std::to_string(l + 2)] = {head.ptr, head.bytes()};
+  };
   Tensor prev;
   for (int lvl = 5; lvl >= 2; --lvl) {
     const Tensor& c = res[lvl - 2];
     Tensor lat = conv_bias(net, w, "backbone.fpn_lateral" + std::to_string(lvl), c, spec(c.C, 256, 1, 1, 0, false));
     if (lvl < 5) add_upsample2x_add(net, prev, lat);
     prev = lat;
+    net.set_lane(lvl == 2 ? 0 : 6 - lvl);  // P5 (+P6) -> lane 1, P4 -> lane 2, P3 -> lane 3, P2 -> lane 0
     P[lvl - 2] = conv_bias(net, w, "backbone.fpn_output" + std::to_string(lvl), lat, spec(256, 256, 3, 1, 1, false));
     net.taps["p" + std::to_string(lvl)] = P[lvl - 2];
-  }
-  P[4] = A.tensor(B, (P[3].H - 1) / 2 + 1, (P[3].W - 1) / 2 + 1, 256, dt);
-  add_subsample2(net, P[3], P[4]);
-  net.taps["p6"] = P[4];
-  const int strides[5] = {4, 8, 16, 32, 64};
-  for (int l = 0; l < 4; ++l) m.pyramid.lv[l] = PyramidLevel{P[l].ptr, P[l].H, P[l].W, P[l].ld, 1.0f / strides[l]};
-
-  // ---- RPN head (shared over levels): 3x3 + ReLU, then objectness (3) and anchor deltas (12) as ONE 1x1 -> fp32
-  net.stage("rpn_head");
-  RpnMeta meta{};
-  {
-    const std::string rp = "proposal_generator.rpn_head.";
-    const HostArray& wo = conv_weight(w, rp + "objectness_logits.weight", kAnchors, 256, 1);
-    const HostArray& bo = get_weight(w, rp + "objectness_logits.bias");
-    const HostArray& wd = conv_weight(w, rp + "anchor_deltas.weight", 4 * kAnchors, 256, 1);
-    const HostArray& bd = get_weight(w, rp + "anchor_deltas.bias");
-    std::vector<float> wm(15 * 256), bm(15);
-    std::copy(wo.data.begin(), wo.data.end(), wm.begin());
-    std::copy(wd.data.begin(), wd.data.end(), wm.begin() + 3 * 256);
-    std::copy(bo.data.begin(), bo.data.end(), bm.begin());
-    std::copy(bd.data.begin(), bd.data.end(), bm.begin() + 3);
-    const double sizes[5] = {32, 64, 128, 256, 512}, ratios[3] = {0.5, 1.0, 2.0};  // yaml:45-58
-    for (int l = 0; l < kRpnLevels; ++l) {
-      Tensor t = conv_bias(net, w, rp + "conv", P[l], spec(256, 256, 3, 1, 1, true));
-      Tensor head = A.tensor(B, t.H, t.W, kRpnHeadC, kF32);
-      ConvSpec s = spec(256, 15, 1, 1, 0, false);
-      s.out_fp32 = true;
-      add_conv(net, rp + "predictors.p" + std::to_string(l + 2), t, head, wm.data(), nullptr, bm.data(), s);
-      m.rpn_head[l] = static_cast<float*>(head.ptr);
-      m.rpn_hw[l][0] = t.H, m.rpn_hw[l][1] = t.W;
-      RpnLevel& lv = meta.lv[l];
-      lv.head = m.rpn_head[l], lv.H = t.H, lv.W = t.W, lv.stride = strides[l];
-      for (int a = 0; a < kAnchors; ++a) {  // DefaultAnchorGenerator.generate_cell_anchors
-        const double area = sizes[l] * sizes[l];
-        const double ww = std::sqrt(area / ratios[a]), hh = ratios[a] * ww;
-        lv.base[a][0] = static_cast<float>(-ww / 2.0), lv.base[a][1] = static_cast<float>(-hh / 2.0);
-        lv.base[a][2] = static_cast<float>(ww / 2.0), lv.base[a][3] = static_cast<float>(hh / 2.0);
-      }
-      net.raw_taps["rpn_head.p" + std::to_string(l + 2)] = {head.ptr, head.bytes()};
+    add_rpn_level(lvl - 2);
+    if (lvl == 5) {
+      P[4] = A.tensor(B, (P[3].H - 1) / 2 + 1, (P[3].W - 1) / 2 + 1, 256, dt);
+      add_subsample2(net, P[3], P[4]);
+      net.taps["p6"] = P[4];
+      add_rpn_level(4);
     }
+    net.set_lane(0);
   }
+  for (int l = 0; l < 4; ++l) m.pyramid.lv[l] = PyramidLevel{P[l].ptr, P[l].H, P[l].W, P[l].ld, 1.0f / strides[l]};
+  net.stage("rpn_head");  // (kept as a stage name; its launches are interleaved with the FPN above)
+  net.join_lanes();
   meta.pre_topk = cfg.pre_nms_topk, meta.post_topk = R, meta.nms_thr = cfg.rpn_nms;
   meta.img_h = static_cast<float>(m.Hn), meta.img_w = static_cast<float>(m.Wn);
 

@@ -10,6 +10,7 @@ namespace pn {
 // fp32 NCHW (caller memory, pointer read from a device slot) -> NHWC dt with zero channel padding.
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* const* src_slot, T* dst, int B, int C, int HW, int Cpad) {
+  pdl_grid_sync();
   const float* src = *src_slot;
   const long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (pix >= static_cast<long long>(B) * HW) return;
@@ -41,9 +42,9 @@ void add_nchw_to_nhwc(Net& net, const float* const* src_slot, const Tensor& out,
   Tensor o = out;
   net.add("nchw_to_nhwc", [=](cudaStream_t s) {
     if (o.dt == kBF16)
-      nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(src_slot, static_cast<__nv_bfloat16*>(o.ptr), o.B, C, HW, o.C);
+      launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, blocks, threads, 0, s, src_slot, static_cast<__nv_bfloat16*>(o.ptr), o.B, C, HW, o.C);
     else
-      nchw_to_nhwc_kernel<float><<<blocks, threads, 0, s>>>(src_slot, static_cast<float*>(o.ptr), o.B, C, HW, o.C);
+      launch_pdl(nchw_to_nhwc_kernel<float>, blocks, threads, 0, s, src_slot, static_cast<float*>(o.ptr), o.B, C, HW, o.C);
   });
   net.launches_per_forward += 1;
 }
@@ -53,6 +54,7 @@ void add_nchw_to_nhwc(Net& net, const float* const* src_slot, const Tensor& out,
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* in, long long ldi, T* out, long long ldo, int B, int H, int W, int Ho,
                                     int Wo, int C8) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * Ho * Wo * C8;
   if (idx >= total) return;
@@ -90,9 +92,9 @@ void add_maxpool3x3s2(Net& net, const Tensor& in, const Tensor& out) {
   Tensor i = in, o = out;
   net.add("maxpool3x3s2", [=](cudaStream_t s) {
     if (i.dt == kBF16)
-      maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(i.ptr), i.ld, static_cast<__nv_bfloat16*>(o.ptr), o.ld, i.B, i.H, i.W, o.H, o.W, C8);
+      launch_pdl(maxpool3x3s2_kernel<__nv_bfloat16>, blocks, threads, 0, s, static_cast<const __nv_bfloat16*>(i.ptr), i.ld, static_cast<__nv_bfloat16*>(o.ptr), o.ld, i.B, i.H, i.W, o.H, o.W, C8);
     else
-      maxpool3x3s2_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(i.ptr), i.ld, static_cast<float*>(o.ptr), o.ld, i.B, i.H, i.W, o.H, o.W, C8);
+      launch_pdl(maxpool3x3s2_kernel<float>, blocks, threads, 0, s, static_cast<const float*>(i.ptr), i.ld, static_cast<float*>(o.ptr), o.ld, i.B, i.H, i.W, o.H, o.W, C8);
   });
   net.launches_per_forward += 1;
 }
@@ -113,6 +115,7 @@ __device__ __forceinline__ int bin_end(int i, int L, int s) { return ((i + 1) * 
 
 template <typename T>
 __global__ void ppm_rows_kernel(const T* in, long long ldi, float* rowpart, int B, int H, int W, int C, PpmMeta meta) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;  // b*H + y
   if (c >= C) return;
@@ -132,6 +135,7 @@ __global__ void ppm_rows_kernel(const T* in, long long ldi, float* rowpart, int 
 
 template <typename T>
 __global__ void ppm_bins_kernel(const float* rowpart, T* out, int H, int W, int C, int s, int bin_off, int nb) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int bx = blockIdx.y % s;
@@ -164,15 +168,15 @@ void add_ppm_pool(Net& net, const Tensor& in, const std::vector<int>& scales, co
     const int threads = 128;
     dim3 g1((i.C + threads - 1) / threads, i.B * i.H);
     if (i.dt == kBF16)
-      ppm_rows_kernel<__nv_bfloat16><<<g1, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(i.ptr), i.ld, rowpart, i.B, i.H, i.W, i.C, meta);
+      launch_pdl(ppm_rows_kernel<__nv_bfloat16>, g1, threads, 0, s, static_cast<const __nv_bfloat16*>(i.ptr), i.ld, rowpart, i.B, i.H, i.W, i.C, meta);
     else
-      ppm_rows_kernel<float><<<g1, threads, 0, s>>>(static_cast<const float*>(i.ptr), i.ld, rowpart, i.B, i.H, i.W, i.C, meta);
+      launch_pdl(ppm_rows_kernel<float>, g1, threads, 0, s, static_cast<const float*>(i.ptr), i.ld, rowpart, i.B, i.H, i.W, i.C, meta);
     for (int k = 0; k < meta.nscales; ++k) {
       dim3 g2((i.C + threads - 1) / threads, meta.scale[k] * meta.scale[k], i.B);
       if (i.dt == kBF16)
-        ppm_bins_kernel<__nv_bfloat16><<<g2, threads, 0, s>>>(rowpart, static_cast<__nv_bfloat16*>(o[k].ptr), i.H, i.W, i.C, meta.scale[k], meta.bin_off[k], nb);
+        launch_pdl(ppm_bins_kernel<__nv_bfloat16>, g2, threads, 0, s, rowpart, static_cast<__nv_bfloat16*>(o[k].ptr), i.H, i.W, i.C, meta.scale[k], meta.bin_off[k], nb);
       else
-        ppm_bins_kernel<float><<<g2, threads, 0, s>>>(rowpart, static_cast<float*>(o[k].ptr), i.H, i.W, i.C, meta.scale[k], meta.bin_off[k], nb);
+        launch_pdl(ppm_bins_kernel<float>, g2, threads, 0, s, rowpart, static_cast<float*>(o[k].ptr), i.H, i.W, i.C, meta.scale[k], meta.bin_off[k], nb);
     }
   });
   net.launches_per_forward += 1 + static_cast<long long>(scales.size());
@@ -195,6 +199,7 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
 template <typename T>
 __global__ void bilinear_into_kernel(const T* in, long long ldi, int h, int w, T* out, long long ldo, int B, int H, int W,
                                      int C8, float sy, float sx) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * H * W * C8;
   if (idx >= total) return;
@@ -230,9 +235,9 @@ void add_bilinear_into(Net& net, const Tensor& in, const Tensor& out) {
   Tensor i = in, o = out;
   net.add("bilinear_into", [=](cudaStream_t s) {
     if (i.dt == kBF16)
-      bilinear_into_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(i.ptr), i.ld, i.H, i.W, static_cast<__nv_bfloat16*>(o.ptr), o.ld, o.B, o.H, o.W, C8, sy, sx);
+      launch_pdl(bilinear_into_kernel<__nv_bfloat16>, blocks, threads, 0, s, static_cast<const __nv_bfloat16*>(i.ptr), i.ld, i.H, i.W, static_cast<__nv_bfloat16*>(o.ptr), o.ld, o.B, o.H, o.W, C8, sy, sx);
     else
-      bilinear_into_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(i.ptr), i.ld, i.H, i.W, static_cast<float*>(o.ptr), o.ld, o.B, o.H, o.W, C8, sy, sx);
+      launch_pdl(bilinear_into_kernel<float>, blocks, threads, 0, s, static_cast<const float*>(i.ptr), i.ld, i.H, i.W, static_cast<float*>(o.ptr), o.ld, o.B, o.H, o.W, C8, sy, sx);
   });
   net.launches_per_forward += 1;
 }
@@ -243,6 +248,7 @@ void add_bilinear_into(Net& net, const Tensor& in, const Tensor& out) {
 // NHWC fp32 [B,h,w,ld] -> NCHW fp32 [B,C,H,W] in caller memory (pointer read from a device slot).
 __global__ void upsample_logits_kernel(const float* in, long long ldi, int h, int w, int C, float* const* dst_slot,
                                        const int* sigmoid_slot, int B, int H, int W, float sy, float sx) {
+  pdl_grid_sync();
   float* dst = *dst_slot;
   const int apply_sigmoid = *sigmoid_slot;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -278,7 +284,7 @@ void add_upsample_logits(Net& net, const Tensor& logits, int C, int Hout, int Wo
   const float sx = static_cast<float>(logits.W) / static_cast<float>(Wout);
   Tensor l = logits;
   net.add("upsample_logits", [=](cudaStream_t s) {
-    upsample_logits_kernel<<<blocks, threads, 0, s>>>(static_cast<const float*>(l.ptr), l.ld, l.H, l.W, C, dst_slot, sigmoid_slot, l.B, Hout, Wout, sy, sx);
+    launch_pdl(upsample_logits_kernel, blocks, threads, 0, s, static_cast<const float*>(l.ptr), l.ld, l.H, l.W, C, dst_slot, sigmoid_slot, l.B, Hout, Wout, sy, sx);
   });
   net.launches_per_forward += 1;
 }
@@ -287,6 +293,52 @@ void add_upsample_logits(Net& net, const Tensor& logits, int C, int Hout, int Wo
 Net::~Net() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (cap_stream) cudaStreamDestroy(cap_stream);
+  for (int l = 0; l < kMaxLanes; ++l) {
+    if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
+    if (lane_fork[l]) cudaEventDestroy(lane_fork[l]);
+    if (lane_done[l]) cudaEventDestroy(lane_done[l]);
+  }
+}
+
+// One pass over the launch list with its parallel lanes (see Net::set_lane): fork/join through events, so the same
+// code serves eager execution and stream capture (the side streams join the capture through the event waits).
+void Net::run_eager(cudaStream_t s) {
+  long long main_ops = 0;                     // lane-0 ops issued so far
+  long long lane_synced[kMaxLanes] = {0, 0, 0, 0};  // value of main_ops each lane last synchronised with (-1: never)
+  bool lane_active[kMaxLanes] = {false, false, false, false};
+  for (int l = 0; l < kMaxLanes; ++l) lane_synced[l] = -1;
+  auto join_all = [&]() {
+    for (int l = 1; l < kMaxLanes; ++l) {
+      if (!lane_active[l]) continue;
+      PN_CUDA_CHECK(cudaEventRecord(lane_done[l], lane_stream[l]));
+      PN_CUDA_CHECK(cudaStreamWaitEvent(s, lane_done[l], 0));
+      lane_active[l] = false;
+      lane_synced[l] = -1;
+    }
+  };
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (op_join[i]) join_all();
+    const int lane = op_lane[i];
+    if (lane == 0) {
+      ops[i](s);
+      ++main_ops;
+      continue;
+    }
+    PN_REQUIRE(lane > 0 && lane < kMaxLanes, "bad lane");
+    if (!lane_stream[lane]) {
+      PN_CUDA_CHECK(cudaStreamCreateWithFlags(&lane_stream[lane], cudaStreamNonBlocking));
+      PN_CUDA_CHECK(cudaEventCreateWithFlags(&lane_fork[lane], cudaEventDisableTiming));
+      PN_CUDA_CHECK(cudaEventCreateWithFlags(&lane_done[lane], cudaEventDisableTiming));
+    }
+    if (lane_synced[lane] != main_ops) {  // see every lane-0 op that precedes this one
+      PN_CUDA_CHECK(cudaEventRecord(lane_fork[lane], s));
+      PN_CUDA_CHECK(cudaStreamWaitEvent(lane_stream[lane], lane_fork[lane], 0));
+      lane_synced[lane] = main_ops;
+    }
+    ops[i](lane_stream[lane]);
+    lane_active[lane] = true;
+  }
+  join_all();
 }
 
 // First call runs eagerly (lazy function-attribute setup, module load); the second captures the

@@ -79,12 +79,16 @@ void build_prednet(PredNet& pn_, const WeightStore& w, int B, int C, int H, int 
       int dil = dilations[li];
       if (bi == 0 && dil > 1) dil = dil / 2;  // contract_dilation (res_layer.py:69-72)
       Tensor identity = x;
-      if (bi == 0 && (stride != 1 || inplanes != planes * 4)) {
+      const bool has_down = bi == 0 && (stride != 1 || inplanes != planes * 4);
+      if (has_down) {  // the projection shortcut runs beside conv1 -> conv2 on a side lane
+        net.set_lane(1);
         identity = conv_bn(net, w, pre + ".downsample.0", pre + ".downsample.1", x,
                            spec(inplanes, planes * 4, 1, stride, 1, false));
+        net.set_lane(0);
       }
       Tensor t = conv_bn(net, w, pre + ".conv1", pre + ".bn1", x, spec(inplanes, planes, 1, 1, 1, true));
       t = conv_bn(net, w, pre + ".conv2", pre + ".bn2", t, spec(planes, planes, 3, stride, dil, true));
+      if (has_down) net.join_lanes();
       const bool last = (li == 3 && bi == blocks[li] - 1);
       Tensor dst;
       if (last) {
@@ -101,11 +105,13 @@ void build_prednet(PredNet& pn_, const WeightStore& w, int B, int C, int H, int 
   std::vector<Tensor> pooled;
   for (int s : scales) pooled.push_back(net.arena.tensor(B, s, s, inplanes, dt));
   add_ppm_pool(net, x, scales, pooled);
-  for (size_t i = 0; i < scales.size(); ++i) {
+  for (size_t i = 0; i < scales.size(); ++i) {  // the four pyramid branches are independent: one lane each
     const std::string pre = "decode_head.psp_modules." + std::to_string(i) + ".1";
+    net.set_lane(static_cast<int>(i) % Net::kMaxLanes);
     Tensor y = conv_bn(net, w, pre + ".conv", pre + ".bn", pooled[i], spec(inplanes, ppm_channels, 1, 1, 1, true));
     add_bilinear_into(net, y, concat.channels(inplanes + ppm_channels * static_cast<int>(i), ppm_channels));
   }
+  net.join_lanes();
   Tensor feats = conv_bn(net, w, "decode_head.bottleneck.conv", "decode_head.bottleneck.bn", concat,
                          spec(concat.C, ppm_channels, 3, 1, 1, true));
 

@@ -67,6 +67,7 @@ __device__ __forceinline__ int clip8(int v) {
 __global__ void k_resize_u8(const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const int* __restrict__ hb,
                             const int* __restrict__ hk, int hks, const int* __restrict__ vb, const int* __restrict__ vk, int vks,
                             uint8_t* __restrict__ resized_u8) {
+  pdl_grid_sync();
   const uint8_t* rgb = *rgb_slot;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * Hn * Wn;
@@ -100,6 +101,7 @@ __global__ void k_resize_u8(const uint8_t* const* rgb_slot, int B, int H, int W,
 template <typename T>
 __global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int Hn, int Wn, int Hp, int Wo, float3 mean_bgr,
                             float3 std_bgr, T* __restrict__ out) {
+  pdl_grid_sync();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * Hp * Wo;
   if (idx >= total) return;
@@ -144,6 +146,7 @@ __global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int H
 __global__ void k_make_obs(const float* __restrict__ depth_all, const uint8_t* __restrict__ rgb_all,
                            const float* __restrict__ sem_all, int E, int H, int W, int ds, int h, int w, int nsem, float min_d,
                            float max_d, float* __restrict__ obs) {
+  pdl_grid_sync();
   const int warps_per_block = blockDim.x >> 5;
   const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -205,16 +208,16 @@ void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H
   const long long total1 = static_cast<long long>(B) * Hn * Wn;
   const int blocks1 = static_cast<int>((total1 + threads - 1) / threads);
   net.add("resize_u8", [=](cudaStream_t s) {
-    k_resize_u8<<<blocks1, threads, 0, s>>>(rgb_slot, B, H, W, Hn, Wn, d_hb, d_hk, hks, d_vb, d_vk, vks, resized_u8);
+    launch_pdl(k_resize_u8, blocks1, threads, 0, s, rgb_slot, B, H, W, Hn, Wn, d_hb, d_hk, hks, d_vb, d_vk, vks, resized_u8);
   });
   const long long total2 = out.pixels();
   const int blocks2 = static_cast<int>((total2 + threads - 1) / threads);
   Tensor o = out;
   net.add("pack_stem", [=](cudaStream_t s) {
     if (o.dt == kBF16)
-      k_pack_stem<__nv_bfloat16><<<blocks2, threads, 0, s>>>(resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr));
+      launch_pdl(k_pack_stem<__nv_bfloat16>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr));
     else
-      k_pack_stem<float><<<blocks2, threads, 0, s>>>(resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<float*>(o.ptr));
+      launch_pdl(k_pack_stem<float>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<float*>(o.ptr));
   });
   net.launches_per_forward += 2;
 }
@@ -224,7 +227,7 @@ void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, i
   const int warps = E * w;
   const int threads = 128;
   const int blocks = (warps * 32 + threads - 1) / threads;
-  k_make_obs<<<blocks, threads, 0, s>>>(depth, rgb, sem, E, H, W, ds, h, w, nsem, min_d, max_d, obs);
+  launch_pdl(k_make_obs, blocks, threads, 0, s, depth, rgb, sem, E, H, W, ds, h, w, nsem, min_d, max_d, obs);
 }
 
 }  // namespace pn

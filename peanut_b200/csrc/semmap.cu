@@ -69,6 +69,7 @@ __device__ __forceinline__ void corner(float coord, float G, int ix, int& p, flo
 // k_points: coordinates, stair mask, column histogram.  grid = E, block = 1024.
 __global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __restrict__ obs, float* __restrict__ coords,
                                                  int* __restrict__ col_count, int* __restrict__ stair_flag) {
+  pdl_grid_sync();
   const int e = blockIdx.x;
   const int N = c.h * c.w;
   const float* depth = obs + (static_cast<size_t>(e) * c.channels + 3) * N;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __res
 // k_scan: exclusive prefix sum of the column counters; also resets the fill cursors.  grid = E, block = 1024.
 __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict__ col_count, int* __restrict__ col_start,
                                                int* __restrict__ col_fill) {
+  pdl_grid_sync();
   const int e = blockIdx.x;
   const int* cnt = col_count + static_cast<size_t>(e) * ncols;
   int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict_
 // k_fill: key = corner_xy << 22 | z-cell of the LOWER z corner << 15 | point index.
 __global__ void k_fill(SemMapCfg c, const float* __restrict__ coords, const int* __restrict__ col_start,
                        int* __restrict__ col_fill, uint32_t* __restrict__ entries) {
+  pdl_grid_sync();
   const int e = blockIdx.y;
   const int N = c.h * c.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,6 +310,7 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* keys, int n, uint
 __global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int cap, int min_count, const float* __restrict__ obs,
                                                  const float* __restrict__ coords, const int* __restrict__ col_start,
                                                  const uint32_t* __restrict__ entries, float* __restrict__ ego) {
+  pdl_grid_sync();
   extern __shared__ uint32_t keys[];
   __shared__ float red_all[4][kMaxFeat], red_agent[4][kMaxFeat];
   const int e = blockIdx.y;
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int cap, int min_c
 // k_pose: get_new_pose_batch (mapping.py:143-160) in place + sampling-grid parameters (model.py:7-43).
 __global__ void k_pose(SemMapCfg c, int E, const float* __restrict__ pose_delta, float* __restrict__ poses,
                        float* __restrict__ xf) {
+  pdl_grid_sync();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   float x = poses[e * 3], y = poses[e * 3 + 1], t = poses[e * 3 + 2];
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restri
                                               const float* __restrict__ maps_last, long long ml_env, long long ml_plane,
                                               long long ml_row, float* __restrict__ map_out,
                                               float* __restrict__ fp_out) {
+  pdl_grid_sync();
   const int e = blockIdx.z;
   const int n = c.map_cells;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -544,14 +550,14 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
   const int N = c.h * c.w;
   const int ncols = c.vr * c.vr;
   PN_CUDA_CHECK(cudaMemsetAsync(col_count, 0, static_cast<size_t>(E) * ncols * sizeof(int), s));
-  k_points<<<E, 1024, 0, s>>>(c, obs, coords, col_count, stair_flag);
-  k_scan<<<E, 1024, 0, s>>>(ncols, col_count, col_start, col_fill);
-  k_fill<<<dim3((N + 255) / 256, E), 256, 0, s>>>(c, coords, col_start, col_fill, entries);
+  launch_pdl(k_points, E, 1024, 0, s, c, obs, coords, col_count, stair_flag);
+  launch_pdl(k_scan, E, 1024, 0, s, ncols, col_count, col_start, col_fill);
+  launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
   constexpr int kSmallCap = 2048;
-  k_columns<<<dim3(ncols, E), 128, kSmallCap * 4, s>>>(c, kSmallCap, 0, obs, coords, col_start, entries, ego);
-  k_columns<<<dim3(ncols, E), 128, 32768 * 4, s>>>(c, 32768, kSmallCap + 1, obs, coords, col_start, entries, ego);
-  k_pose<<<(E + 63) / 64, 64, 0, s>>>(c, E, pose_delta, poses_inout, xf);
-  k_fuse<<<dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s>>>(c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
+  launch_pdl(k_columns, dim3(ncols, E), 128, kSmallCap * 4, s, c, kSmallCap, 0, obs, coords, col_start, entries, ego);
+  launch_pdl(k_columns, dim3(ncols, E), 128, 32768 * 4, s, c, 32768, kSmallCap + 1, obs, coords, col_start, entries, ego);
+  launch_pdl(k_pose, (E + 63) / 64, 64, 0, s, c, E, pose_delta, poses_inout, xf);
+  launch_pdl(k_fuse, dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
   PN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -316,8 +316,15 @@ def run_ours(a):
             peak, which = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0, "tf32 = half the measured bf16 sustained peak (tf32 not in MEASURED_PEAKS.json)"
         if not peaks:
             which += " [fallback]"
+        traffic, traffic_src = None, None
+        if a.workload == "cfg1" and E == 1 and a.map == "base":
+            try:  # committed ncu measurement of this exact command (profiles/)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic_cfg1.json")))
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_traffic_cfg1.json (ncu dram__bytes_read+write per conv launch, L2 flushed per kernel)"
+            except Exception:
+                pass
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "conv_umma_kernel", "launches_per_step": n_conv,
+                            "traffic": traffic, "traffic_source": traffic_src, "kernel": "conv_umma_kernel", "launches_per_step": n_conv,
                             "flops_per_step": conv_fl, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / all_ms,
                             "detections_per_frame": ndet / float(E), "peak_source": which,
                             "how": "CUDA events around every launch (eager replay of the recorded launch list after the timed region)"}

@@ -543,7 +543,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (warp == 0 && lane == 0) PN_DBG(it, 7);
     }
-    if (lane == 0) tma_store_wait_all();
+    // shared memory must outlive the bulk stores' reads; their global writes complete with the grid
+    if (lane == 0) tma_store_wait_read<0>();
   } else {
     // ------------------------------------------------------------ epilogue, direct path: TMEM -> regs -> global
     const int quarter = warp & 3;

@@ -21,6 +21,7 @@
 //
 // This translation unit is compiled with -fmad=false: the coordinate and weight arithmetic must round after
 // every multiply and add like the reference's separate torch ops do.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -205,10 +206,17 @@ __global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __res
 
 // --------------------------------------------------------------------------------------------------
 // k_scan: exclusive prefix sum of the column counters; also resets the fill cursors.  grid = E, block = 1024.
-__global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict__ col_count, int* __restrict__ col_start,
-                                               int* __restrict__ col_fill) {
+// It also compacts the non-empty columns into a work list for k_columns: columns with at most `small_cap` entries
+// from the front of col_list, larger ones from the back (list_n = {#small, #large}); the order inside the list is
+// irrelevant, every column is processed independently.
+__global__ void __launch_bounds__(1024) k_scan(int ncols, int small_cap, const int* __restrict__ col_count,
+                                               int* __restrict__ col_start, int* __restrict__ col_fill,
+                                               int* __restrict__ col_list, int* __restrict__ list_n) {
   pdl_grid_sync();
   const int e = blockIdx.x;
+  int* list = col_list + static_cast<size_t>(e) * ncols;
+  __shared__ int n_small, n_large;
+  if (threadIdx.x == 0) n_small = 0, n_large = 0;
   const int* cnt = col_count + static_cast<size_t>(e) * ncols;
   int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
   int* fill = col_fill + static_cast<size_t>(e) * ncols;
@@ -242,12 +250,19 @@ __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict_
     if (i < ncols) {
       start[i] = excl;
       fill[i] = 0;
+      if (v > 0) {
+        if (v <= small_cap) list[atomicAdd(&n_small, 1)] = i;
+        else list[ncols - 1 - atomicAdd(&n_large, 1)] = i;
+      }
     }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = excl + v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) start[ncols] = carry;
+  if (threadIdx.x == 0) {
+    start[ncols] = carry;
+    list_n[e * 2] = n_small, list_n[e * 2 + 1] = n_large;
+  }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -307,28 +322,29 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* keys, int n, uint
   return lo;
 }
 
-__global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int cap, int min_count, const float* __restrict__ obs,
+__global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int large, const float* __restrict__ obs,
                                                  const float* __restrict__ coords, const int* __restrict__ col_start,
-                                                 const uint32_t* __restrict__ entries, float* __restrict__ ego) {
+                                                 const uint32_t* __restrict__ entries, const int* __restrict__ col_list,
+                                                 const int* __restrict__ list_n, float* __restrict__ ego) {
   pdl_grid_sync();
   extern __shared__ uint32_t keys[];
   __shared__ float red_all[4][kMaxFeat], red_agent[4][kMaxFeat];
   const int e = blockIdx.y;
-  const int col = blockIdx.x;
   const int ncols = c.vr * c.vr;
   const int N = c.h * c.w;
   const int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
+  const int* list = col_list + static_cast<size_t>(e) * ncols;
+  const int n_list = list_n[e * 2 + large];
+  const int tid = threadIdx.x;
+  float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
+  // persistent over this launch's share of the non-empty columns (empty ones keep the zeros of the memset)
+  for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+  const int col = large ? list[ncols - 1 - li] : list[li];
   const int s0 = start[col];
   const int n = start[col + 1] - s0;
-  if (n < min_count || n > cap) return;  // handled by the other launch
-  const int tid = threadIdx.x;
   const int px = col / c.vr, py = col - px * c.vr;
-  float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
   const int cell = py * c.vr + px;  // voxels.transpose(2,3): row = y index, column = x index
-  if (n == 0) {
-    for (int ch = tid; ch < c.ego_channels; ch += blockDim.x) ego_e[static_cast<size_t>(ch) * ncols + cell] = 0.f;
-    return;
-  }
+  __syncthreads();  // the previous column's keys / partial sums are no longer read
   // load + bitonic sort (ascending) of the column's keys
   int npow = 1;
   while (npow < n) npow <<= 1;
@@ -415,6 +431,7 @@ __global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int cap, int min_c
     }
     ego_e[static_cast<size_t>(ch) * ncols + cell] = fminf(fmaxf(v, 0.f), 1.f);
   }
+  }  // column loop
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -539,6 +556,11 @@ void SemMap::init(const SemMapCfg& cfg, int envs) {
   col_fill = static_cast<int*>(arena.alloc(E * ncols * sizeof(int)));
   entries = static_cast<uint32_t*>(arena.alloc(E * 4 * N * sizeof(uint32_t)));
   ego = static_cast<float*>(arena.alloc(E * c.ego_channels * ncols * sizeof(float)));
+  col_list = static_cast<int*>(arena.alloc(E * ncols * sizeof(int)));
+  list_n = static_cast<int*>(arena.alloc(E * 2 * sizeof(int)));
+  int dev = 0;
+  PN_CUDA_CHECK(cudaGetDevice(&dev));
+  PN_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   xf = static_cast<float*>(arena.alloc(E * 4 * sizeof(float)));
   stair_flag = static_cast<int*>(arena.alloc(E * sizeof(int)));
   PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
@@ -550,12 +572,16 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
   const int N = c.h * c.w;
   const int ncols = c.vr * c.vr;
   PN_CUDA_CHECK(cudaMemsetAsync(col_count, 0, static_cast<size_t>(E) * ncols * sizeof(int), s));
+  PN_CUDA_CHECK(cudaMemsetAsync(ego, 0, static_cast<size_t>(E) * c.ego_channels * ncols * sizeof(float), s));
   launch_pdl(k_points, E, 1024, 0, s, c, obs, coords, col_count, stair_flag);
-  launch_pdl(k_scan, E, 1024, 0, s, ncols, col_count, col_start, col_fill);
-  launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
   constexpr int kSmallCap = 2048;
-  launch_pdl(k_columns, dim3(ncols, E), 128, kSmallCap * 4, s, c, kSmallCap, 0, obs, coords, col_start, entries, ego);
-  launch_pdl(k_columns, dim3(ncols, E), 128, 32768 * 4, s, c, 32768, kSmallCap + 1, obs, coords, col_start, entries, ego);
+  launch_pdl(k_scan, E, 1024, 0, s, ncols, kSmallCap, col_count, col_start, col_fill, col_list, list_n);
+  launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
+  // non-empty columns only, persistent CTAs: 8 KB of key storage each for the small ones, 128 KB for the rare
+  // columns that collect more than kSmallCap entries (a wall seen edge-on)
+  const int g_small = std::min(ncols, num_sms * 8), g_large = std::min(ncols, num_sms);
+  launch_pdl(k_columns, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
+  launch_pdl(k_columns, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);
   launch_pdl(k_pose, (E + 63) / 64, 64, 0, s, c, E, pose_delta, poses_inout, xf);
   launch_pdl(k_fuse, dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
   PN_CUDA_CHECK(cudaGetLastError());

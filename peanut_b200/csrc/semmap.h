@@ -30,9 +30,12 @@ struct SemMap {
   int* col_fill = nullptr;     // [E][vr*vr]
   uint32_t* entries = nullptr; // [E][4*N] bucketed (corner, z, point) keys
   float* ego = nullptr;        // [E][ego_channels][vr][vr]
+  int* col_list = nullptr;     // [E][vr*vr] non-empty columns: small ones from the front, large ones from the back
+  int* list_n = nullptr;       // [E][2] = {#small, #large}
+  int num_sms = 148;
   float* xf = nullptr;         // [E][4] cos, sin, tx, ty of the sampling grids
   int* stair_flag = nullptr;   // [E]
-  static constexpr int kLaunches = 8;  // memset + 7 kernels per forward
+  static constexpr int kLaunches = 7;  // kernels per forward (plus two memsets)
 
   void init(const SemMapCfg& cfg, int envs);
   // maps_last may be a strided view (element strides between envs, channel planes and rows; unit x stride)

@@ -77,16 +77,20 @@ CUtensorMap encode_im2col(DType dt, const Tensor& in, int channels_total, int pa
 
 // Automatic split-K (cluster reduce-scatter over distributed shared memory) for layers with too few tiles to fill the GPU.
 constexpr bool kAutoSplitK = true;
+// CTA pairs (tcgen05.mma.cta_group::2) picked by the tile model; sp.force_pair overrides (1 = on, 2 = off).
+constexpr bool kAutoPair = true;
+// per-tile fixed cost of the persistent loop (barrier round trips, TMA issue, accumulator hand-over), measured ~0.3 us
+constexpr double kTileFixed = 0.3e-6;
 
 struct ConvMaps {
   CUtensorMap a, b, out, res;
 };
 
-template <typename T, int BN, bool kSplit>
+template <typename T, int BN, bool kSplit, bool kPair>
 void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    PN_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<T, BN, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PN_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<T, BN, kSplit, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     configured = true;
   }
@@ -96,31 +100,39 @@ void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  if (kSplit) {  // one thread-block cluster per output tile
+  if (kSplit || kPair) {  // one thread-block cluster per output tile (split-K) / one SM pair per 256-row tile
     attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = p.splits, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
+    attr[1].val.clusterDim.x = kPair ? 2 : p.splits, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
   }
-  PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, BN, kSplit>, tm.a, tm.b, tm.out, tm.res, p));
+  PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, BN, kSplit, kPair>, tm.a, tm.b, tm.out, tm.res, p));
 }
 
 template <typename T>
-void launch_conv_bn(int bn, const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
+void launch_conv_bn(int bn, bool pair, const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
+  if (pair) {
+    switch (bn) {
+      case 128: launch_conv<T, 128, false, true>(tm, p, grid, smem, s); break;
+      case 256: launch_conv<T, 256, false, true>(tm, p, grid, smem, s); break;
+      default: PN_REQUIRE(false, "unsupported N tile for a CTA pair");
+    }
+    return;
+  }
   if (p.splits > 1) {
     switch (bn) {
-      case 32: launch_conv<T, 32, true>(tm, p, grid, smem, s); break;
-      case 64: launch_conv<T, 64, true>(tm, p, grid, smem, s); break;
-      case 128: launch_conv<T, 128, true>(tm, p, grid, smem, s); break;
-      case 256: launch_conv<T, 256, true>(tm, p, grid, smem, s); break;
+      case 32: launch_conv<T, 32, true, false>(tm, p, grid, smem, s); break;
+      case 64: launch_conv<T, 64, true, false>(tm, p, grid, smem, s); break;
+      case 128: launch_conv<T, 128, true, false>(tm, p, grid, smem, s); break;
+      case 256: launch_conv<T, 256, true, false>(tm, p, grid, smem, s); break;
       default: PN_REQUIRE(false, "unsupported N tile");
     }
     return;
   }
   switch (bn) {
-    case 32: launch_conv<T, 32, false>(tm, p, grid, smem, s); break;
-    case 64: launch_conv<T, 64, false>(tm, p, grid, smem, s); break;
-    case 128: launch_conv<T, 128, false>(tm, p, grid, smem, s); break;
-    case 256: launch_conv<T, 256, false>(tm, p, grid, smem, s); break;
+    case 32: launch_conv<T, 32, false, false>(tm, p, grid, smem, s); break;
+    case 64: launch_conv<T, 64, false, false>(tm, p, grid, smem, s); break;
+    case 128: launch_conv<T, 128, false, false>(tm, p, grid, smem, s); break;
+    case 256: launch_conv<T, 256, false, false>(tm, p, grid, smem, s); break;
     default: PN_REQUIRE(false, "unsupported N tile");
   }
 }
@@ -193,11 +205,28 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   // per 32-byte K step (below N = 64 the A-operand shared-memory read dominates).  Pick the tile that minimises
   // waves * max(stream time, MMA time): wide tiles for big layers, narrower ones when the grid would not fill.
   int bn = 32, splits = 1;
+  bool pair = false;
   {
     const int kblocks_total = taps * kb_per_tap;
     double best = 1e30;
     for (int cand : {256, 128, 64, 32}) {
       if (sp.force_bn ? cand != (sp.force_bn & 0x3ff) : (cand > cout32 || cout32 % cand != 0)) continue;
+      // CTA pair (cta_group::2): 256 x cand tile on two SMs, each staging 128 activation rows + cand/2 weight rows
+      if (cand >= 128 && sw == 128 && m_tiles >= 2 && sp.force_pair != 2 && sp.force_splits <= 1 && (kAutoPair || sp.force_pair == 1)) {
+        const double work = std::ceil(m_tiles / 2.0) * ((cout32 + cand - 1) / cand);
+        const double pairs = net.num_sms / 2;
+        const double active = std::min<double>(work, pairs) * 2.0;
+        const double waves = std::ceil(work / pairs);
+        const double bytes = static_cast<double>(kblocks_total) * block_k * es * (kBlockM + cand / 2);
+        const double t_mem = bytes / std::min(125e9, 14e12 / active);
+        const double t_mma = static_cast<double>(kblocks_total) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
+        // the epilogue of a 128 x cand tile takes ~0.5 us per 32 columns (shared-memory bound, measured) and overlaps
+        // the next tile's main loop; pairs only pay off where the main loop is the longer of the two
+        const double t_epi = 0.5e-6 * cand / 32.0;
+        const double t = waves * (std::max(std::max(t_mem, t_mma), t_epi) + kTileFixed) + t_epi + 0.5e-6;  // + cluster set-up / tear-down
+        if (t < best || sp.force_pair == 1) best = t, bn = cand, splits = 1, pair = true;
+      }
+      if (sp.force_pair == 1) continue;
       for (int s : {1, 2, 4, 8}) {
         if (sp.force_splits ? s != sp.force_splits : (s > 1 && (sp.no_split || !kAutoSplitK || kblocks_total / s < 4))) continue;
         if (s > kblocks_total) continue;
@@ -212,16 +241,16 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
         const double bytes = static_cast<double>(kbs) * block_k * es * (kBlockM + cand);
         const double t_mem = bytes / std::min(125e9, 14e12 / active);
         const double t_mma = static_cast<double>(kbs) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
-        const double t_epi = 0.25e-6 * cand / 32.0 / s;  // un-overlapped epilogue of the last tile
+        const double t_epi = 0.5e-6 * cand / 32.0 / s;  // epilogue of one tile (~0.5 us per 32 columns); the last one is exposed
         // split-K: park the partial tile in shared memory, cluster barrier, read one slice of every peer's tile
         const double t_red = s > 1 ? 1.5e-6 + 2.0 * kBlockM * cand * 4.0 / 200e9 : 0.0;
-        const double t = waves * (std::max(t_mem, t_mma) + t_red) + t_epi;
-        if (t < best * (s > 1 ? 0.9 : 1.0)) best = t, bn = cand, splits = s;
+        const double t = waves * (std::max(std::max(t_mem, t_mma), s > 1 ? 0.0 : t_epi) + t_red + kTileFixed) + t_epi;
+        if (t < best * (s > 1 ? 0.9 : 1.0)) best = t, bn = cand, splits = s, pair = false;
       }
     }
     PN_REQUIRE(best < 1e29, name + ": no valid tile configuration");
   }
-  net.last_bn = bn + 1000 * splits;
+  net.last_bn = bn + 1000 * splits + (pair ? 100000 : 0);
   const int cout_pad = round_up(sp.Cout, bn);
   const int n_tiles = cout_pad / bn;
 
@@ -263,7 +292,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   } else {
     tm.a = encode_im2col(dt, in, cin_pad, sp.pad, pad_w, sp.dil, sp.R, sp.S, sp.stride, stride_w, block_k, kBlockM, sw);
   }
-  tm.b = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, bn, sw);
+  tm.b = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, pair ? bn / 2 : bn, sw);
   tm.out = tm.b;
   tm.res = tm.b;
 
@@ -274,7 +303,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.stride = sp.stride, p.dil = sp.dil, p.pad = sp.pad;
   p.stride_w = stride_w, p.pad_w = pad_w;
   p.kb_per_tap = kb_per_tap, p.block_k = block_k, p.sw = sw;
-  p.m_tiles = m_tiles, p.n_tiles = n_tiles;
+  p.m_tiles = pair ? (m_tiles + 1) / 2 : m_tiles, p.n_tiles = n_tiles;  // work items along M: tiles, or 256-row tile pairs
   p.cout_store = std::min(round_up(sp.Cout, 8), out.C);
   PN_REQUIRE(p.cout_store >= sp.Cout, name + ": output view too narrow");
   p.a_tiled = a_tiled ? 1 : 0;
@@ -314,7 +343,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     }
   }
 
-  const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * sw;
+  const size_t stage_bytes = static_cast<size_t>(kBlockM + (pair ? bn / 2 : bn)) * sw;
   const int kblocks = taps * kb_per_tap;
   size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 8 * bn * sizeof(float) /*scale+bias per epilogue warp*/ + 256 /*barriers*/;
   size_t budget = 227 * 1024 - fixed_bytes;
@@ -333,7 +362,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   }
   // Single-wave layers (one tile per CTA) are latency-bound: cap the footprint at ~half an SM so that the next
   // kernel's CTA can become resident beside this one (programmatic dependent launch) and overlap its prologue.
-  if (static_cast<long long>(m_tiles) * n_tiles * splits <= net.num_sms) {
+  if (static_cast<long long>(m_tiles) * n_tiles * splits <= net.num_sms && !pair) {
     const int cap = static_cast<int>((110 * 1024 - std::min<size_t>(fixed_bytes, 100 * 1024)) / stage_bytes);
     if (cap >= 3) stages = std::min(stages, cap);
   }
@@ -347,15 +376,16 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   p.stages = stages;
   PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
   const size_t smem = fixed_bytes + stages * stage_bytes;
-  const long long tiles = static_cast<long long>(m_tiles) * n_tiles * splits;
-  const int grid = static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, net.num_sms));
+  const long long tiles = static_cast<long long>(p.m_tiles) * n_tiles * splits;
+  const int grid = pair ? 2 * static_cast<int>(std::min<long long>(tiles, net.num_sms / 2))
+                        : static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, net.num_sms));
 
   const double flops = 2.0 * static_cast<double>(M) * sp.Cout * sp.Cin * taps;
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
-      launch_conv_bn<__nv_bfloat16>(bn, tm, p, grid, smem, s);
+      launch_conv_bn<__nv_bfloat16>(bn, pair, tm, p, grid, smem, s);
     else
-      launch_conv_bn<float>(bn, tm, p, grid, smem, s);
+      launch_conv_bn<float>(bn, pair, tm, p, grid, smem, s);
   }, flops);
   net.launches_per_forward += 1;
 }

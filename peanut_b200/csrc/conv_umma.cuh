@@ -14,6 +14,10 @@
 //   memory and written back with TMA bulk stores (full 128-byte lines, M/N tails clipped by hardware).
 //   Fallback path (narrow or mixed-precision outputs): direct 16-byte global stores per thread.
 //
+// kPair: a cluster of two CTAs (one SM pair) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages its own
+// 128 activation rows and HALF of the weight rows, the leader CTA issues the MMAs for both, and each CTA's TMEM receives
+// the accumulators of its own 128 rows - the operand bytes an SM has to ingest per MAC drop by a third.
+//
 // Warp roles: 0..3 = epilogue (one per TMEM lane quarter; warpgroup 0, which takes the registers warpgroup 1 gives up
 // through setmaxnreg), 4 = TMA producer, 5 = MMA issuer + TMEM owner, 6 = residual prefetcher, 7 = idle.
 //
@@ -141,6 +145,18 @@ __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long m
   }
 }
 
+// "accumulator stage drained": local barrier, or - in a CTA pair - the leader's barrier (it gates the leader's MMA issue)
+template <bool kPair>
+__device__ __forceinline__ void arrive_tempty(uint64_t* bar, uint32_t cta_rank) {
+  if constexpr (kPair) {
+    if (cta_rank != 0) {
+      mbar_arrive_remote(leader_addr(bar));
+      return;
+    }
+  }
+  mbar_arrive(bar);
+}
+
 // Tuning aid (build with -DPN_CONV_TIMELINE, run tools/conv_one.py with PN_CONV_DBG=1): clock64 timeline of CTA 0.
 #ifdef PN_CONV_TIMELINE
 #define PN_DBG(iter, slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < 64) p.dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
@@ -159,7 +175,7 @@ __device__ __forceinline__ long long pn_globaltimer() {
 #define PN_LOG(which) do { } while (0)
 #endif
 
-template <typename T, int BN, bool kSplit>
+template <typename T, int BN, bool kSplit, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -170,8 +186,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   PN_LOG(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  static_assert(!(kSplit && kPair), "split-K and CTA pairs are separate launch modes");
+  constexpr int kBLoad = kPair ? BN / 2 : BN;  // weight rows this CTA stages per K block
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t a_bytes = kBlockM * p.sw;
-  const uint32_t b_bytes = BN * p.sw;
+  const uint32_t b_bytes = kBLoad * p.sw;
+  const uint32_t stage_tx = (kPair ? 2u : 1u) * (a_bytes + b_bytes);  // bytes that complete one (leader) full barrier
+  // persistent work items are walked by CTA (or by CTA pair)
+  const int work_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const uint32_t chunk_bytes = p.epi_tma ? kBlockM * p.cb : 0;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.stages * a_bytes;
@@ -202,7 +225,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kPair ? 8 : 4);  // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&rfull_bar[i], 1);
@@ -211,18 +234,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair(tmem_ptr, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) {  // the peer's barriers must be initialised before anything signals them
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // Weights do not depend on the previous kernel: arm the first pipeline stages of this CTA's first work item and
   // fetch their weight tiles while the previous kernel drains (its tail would otherwise hide nothing but the prologue).
   int pre_armed = 0;
-  if (warp == kProducerWarp && p.m_limit == nullptr && static_cast<int>(blockIdx.x) < p.m_tiles * p.n_tiles * p.splits) {
-    const int work0 = blockIdx.x;
+  if (warp == kProducerWarp && p.m_limit == nullptr && work_first < p.m_tiles * p.n_tiles * p.splits) {
+    const int work0 = work_first;
     const int tile0 = work0 / p.splits;
     const int split0 = work0 - tile0 * p.splits;
     const int n_tile0 = tile0 % p.n_tiles;
@@ -232,8 +264,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     pre_armed = min(p.stages, my_kb);
     if (elect_one()) {
       for (int i = 0; i < pre_armed; ++i) {
-        mbar_arrive_expect_tx(&full_bar[i], a_bytes + b_bytes);
-        tma_load_2d(&tmap_b, &full_bar[i], smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k, n_tile0 * BN);
+        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[i], stage_tx);
+        if constexpr (kPair) {
+          tma_load_2d_pair(&tmap_b, leader_addr(&full_bar[i]), smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k,
+                           n_tile0 * BN + static_cast<int>(cta_rank) * kBLoad);
+        } else {
+          tma_load_2d(&tmap_b, &full_bar[i], smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k, n_tile0 * BN);
+        }
       }
     }
   }
@@ -245,7 +282,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   int m_tiles_live = p.m_tiles;
   if (p.m_limit != nullptr) {
     const long long rows = static_cast<long long>(__ldg(p.m_limit)) * p.m_limit_rows;
-    const int t = static_cast<int>((rows + kBlockM - 1) / kBlockM);
+    constexpr int kRowsPerItem = kPair ? 2 * kBlockM : kBlockM;
+    const int t = static_cast<int>((rows + kRowsPerItem - 1) / kRowsPerItem);
     m_tiles_live = t < p.m_tiles ? t : p.m_tiles;
   }
   const int num_tiles = m_tiles_live * p.n_tiles * p.splits;  // work items: (m_tile, n_tile, split), split fastest
@@ -260,12 +298,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      for (int work = work_first; work < num_tiles; work += work_stride) {
         const int tile = work / p.splits;
         const int split = work - tile * p.splits;
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
-        const int m0 = m_tile * kBlockM;
+        const int m0 = (kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM;
         const int q = m0 % p.Wo;
         const int t = m0 / p.Wo;
         const int pp = t % p.Ho;
@@ -277,22 +315,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int tap = kb_begin / p.kb_per_tap;
         int kb = kb_begin - tap * p.kb_per_tap;
         int r = tap / p.S, sx = tap - r * p.S;
-        PN_DBG((work - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x), 0);
+        PN_DBG((work - work_first) / work_stride, 0);
         for (int kb_global = kb_begin; kb_global < kb_end; ++kb_global) {
           const bool armed = pre_armed > 0;  // stage already armed and its weight tile already in flight
           if (armed) {
             --pre_armed;
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           }
-          if (p.a_tiled) {
-            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, m0);
+          if constexpr (kPair) {  // both CTAs' bytes complete the LEADER's full barrier
+            const uint32_t fb = leader_addr(&full_bar[stage]);
+            if (p.a_tiled) {
+              tma_load_2d_pair(&tmap_a, fb, smem_a + stage * a_bytes, kb * p.block_k, m0);
+            } else {
+              tma_load_im2col_4d_pair(&tmap_a, fb, smem_a + stage * a_bytes, kb * p.block_k, w0, h0, img,
+                                      static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+            }
+            if (!armed)
+              tma_load_2d_pair(&tmap_b, fb, smem_b + stage * b_bytes, kb_global * p.block_k,
+                               n_tile * BN + static_cast<int>(cta_rank) * kBLoad);
           } else {
-            tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0, img,
-                               static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+            if (p.a_tiled) {
+              tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, m0);
+            } else {
+              tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0, img,
+                                 static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+            }
+            if (!armed) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
           }
-          if (!armed) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -306,13 +357,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer (one elected lane)
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(ElemTraits<T>::kFormat, BN);
+    if (cta_rank == 0 && elect_one()) {  // pair: the leader issues for both CTAs
+      constexpr uint32_t idesc = umma_idesc(ElemTraits<T>::kFormat, BN, kPair ? 256u : 128u);
       const int ksteps = p.sw / 32;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
+      for (int work = work_first; work < num_tiles; work += work_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         PN_DBG(it, 1);
@@ -329,16 +380,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + stage * b_bytes), p.sw);
           for (int k = 0; k < ksteps; ++k) {
             const uint32_t accum = (kb | k) ? 1u : 0u;
-            if constexpr (ElemTraits<T>::kFormat == 1) {
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            if constexpr (kPair) {
+              if constexpr (ElemTraits<T>::kFormat == 1) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+              else umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
             } else {
-              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+              if constexpr (ElemTraits<T>::kFormat == 1) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+              else umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (kPair) umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
           if (kb == 0) PN_DBG(it, 3);
           if (kb == my_kblocks - 1) {
-            umma_commit(&tfull_bar[acc]);
+            if constexpr (kPair) umma_commit_pair(&tfull_bar[acc]);
+            else umma_commit(&tfull_bar[acc]);
             PN_DBG(it, 4);
           }
           if (++stage == p.stages) {
@@ -352,7 +407,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ residual prefetcher (TMA epilogue only)
     if (p.epi_tma && p.residual != nullptr && elect_one()) {
       uint32_t g = 0;  // running chunk counter, same sequence as the epilogue warps
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = work_first; tile < num_tiles; tile += work_stride) {
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
         for (int n0 = n_tile * BN; n0 < n_tile * BN + BN && n0 < p.cout_store; n0 += cols_per_chunk, ++g) {
@@ -360,7 +415,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t ph = (g / p.res_bufs) & 1;
           mbar_wait(&rempty_bar[rb], ph ^ 1);
           mbar_arrive_expect_tx(&rfull_bar[rb], chunk_bytes);
-          tma_load_2d(&tmap_res, &rfull_bar[rb], smem_res + rb * chunk_bytes, n0, m_tile * kBlockM);
+          tma_load_2d(&tmap_res, &rfull_bar[rb], smem_res + rb * chunk_bytes, n0,
+                      (kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM);
         }
       }
     }
@@ -397,7 +453,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t rb = 0, rphase = 0;  // residual ring slot / phase of chunk g
     int it = 0;
     int cached_n_tile = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = work_first; tile < num_tiles; tile += work_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.n_tiles;
@@ -506,7 +562,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) {
             if (has_res) mbar_arrive(&rempty_bar[rb]);
             const int n0 = n_tile * BN + (grp - sub) * 32;
-            tma_store_2d_addr(&tmap_out, obuf + quarter * 32 * p.cb, n0, m_tile * kBlockM + quarter * 32);
+            tma_store_2d_addr(&tmap_out, obuf + quarter * 32 * p.cb, n0,
+                              (kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM + quarter * 32);
             tma_store_commit();
           }
           ++g;
@@ -526,7 +583,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else {  // every accumulator column this warp needs is in registers: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank);
         }
         process(va, grp);
         if (more_b) {
@@ -536,7 +593,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank);
           }
           process(vb, grp + 1);
         }
@@ -549,13 +606,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ epilogue, direct path: TMEM -> regs -> global
     const int quarter = warp & 3;
     int it = 0;
-    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++it) {
+    for (int work = work_first; work < num_tiles; work += work_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int tile = work / p.splits;
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
-      const long long m = static_cast<long long>(m_tile) * kBlockM + quarter * 32 + lane;
+      const long long m = static_cast<long long>(kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM + quarter * 32 + lane;
       const bool row_ok = m < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -596,7 +653,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank);
     }
   }
     if constexpr (kSplit) {
@@ -647,9 +704,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) {  // both CTAs are done with each other's shared memory and tensor memory
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
   PN_LOG(2);
 }

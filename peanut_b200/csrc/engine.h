@@ -199,6 +199,7 @@ struct ConvSpec {
   bool out_fp32 = false;
   int force_bn = 0;  // test hook: force the N tile
   int force_splits = 0;  // test hook: force the split-K factor
+  int force_pair = 0;    // test hook: 1 = force a CTA pair (cta_group::2), 2 = forbid it
   bool no_split = false;  // never split K (layers whose row count is dynamic keep one CTA per tile)
   long long* dbg = nullptr;  // tuning aid: per-tile clock64 timeline of CTA 0
   bool force_direct_epilogue = false;  // test hook: bypass the TMA-staged epilogue

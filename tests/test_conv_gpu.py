@@ -43,11 +43,21 @@ CASES = [
     (1, 256, 10, 10, 24, 3, 1, 1, 1, (2 << 16) | 32),    # narrow output (24 -> 32-wide tile), 16 columns per rank
 ]
 SPLIT_CASES = [c for c in CASES if c[9] >> 16]
+# CTA pairs (force_bn bit 0x2000): tcgen05.mma.cta_group::2, a 256 x N tile on two SMs, weights split between the CTAs
+PAIR = 0x2000
+PAIR_CASES = [
+    (2, 128, 30, 30, 256, 3, 1, 1, 1, PAIR | 256),   # 15 m-tiles (odd): the last pair's second CTA is out of range
+    (1, 256, 24, 24, 512, 1, 1, 1, 0, PAIR | 256),   # 1x1 (tiled A), 5 m-tiles, 2 n-tiles
+    (8, 256, 40, 40, 256, 3, 1, 1, 1, PAIR | 128),   # 50 pairs x 2 n-tiles > 74 clusters: persistent pairs
+    (6, 512, 30, 30, 2048, 1, 1, 1, 0, PAIR | 256),  # conv3-like: many chunks per tile, residual ring wraps
+    (1, 512, 19, 19, 512, 3, 1, 4, 4, PAIR | 256),   # dilation 4, 3 m-tiles
+    (1, 256, 24, 24, 512, 1, 2, 1, 0, PAIR | 128),   # 1x1 stride 2 (im2col with stride), 2 m-tiles
+]
 
 
 def _run(ctx, case, precision, with_res=True):
     B, Cin, H, W, Cout, k, stride, dil, pad, bn = case
-    g = torch.Generator().manual_seed(sum(case))
+    g = torch.Generator().manual_seed(sum(case[:9]) + (case[9] & 0x3ff))  # same data for every launch mode of a tile width
     x = torch.randn((B, Cin, H, W), generator=g)
     w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
     scale = torch.rand(Cout, generator=g) + 0.5
@@ -87,6 +97,19 @@ def test_conv_tf32(ctx, case):
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-6
     assert err <= 3e-3 * scale, f"max abs err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("precision", [_lib.PN_BF16, _lib.PN_TF32], ids=["bf16", "tf32"])
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
+def test_conv_pair(ctx, case, precision):
+    y, ref = _run(ctx, case, precision)
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= (1e-2 if precision == _lib.PN_BF16 else 3e-3) * scale, f"max abs err {err} vs scale {scale}"
+    # and bit-identical to the single-CTA kernel (same K order, same epilogue arithmetic)
+    single = (case[:9] + ((case[9] & 0x3ff) | 0x4000 | (1 << 16),))  # pairs forbidden, no split-K
+    y1, _ = _run(ctx, single, precision)
+    assert torch.equal(y, y1)
 
 
 @pytest.mark.parametrize("precision", [_lib.PN_BF16, _lib.PN_TF32])

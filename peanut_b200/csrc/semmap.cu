@@ -5,12 +5,13 @@
 // scatter-adds into it eight times and rounds the WHOLE grid after each of the eight trilinear corners
 // (depth_utils.py:241-250).  Here the grid never exists:
 //
-//   k_points   one CTA per environment: depth -> normalised point coordinates (same fp32 op order as the
-//              reference), stair-mask decision (3 % quantile by 4-pass radix select instead of a sort),
-//              masking, and a per-(x,y)-column histogram of the points' 2x2 lateral footprints;
-//   k_scan     exclusive scan of the 10 000 column counters;
+//   k_coords   one thread per depth pixel: normalised point coordinates (same fp32 op order as the reference)
+//              and the two counts of the stair-mask test;
+//   k_quantile one CTA per environment: stair-mask decision (3 % quantile by 4-pass radix select, not a sort);
+//   k_hist     one thread per pixel: stair masking and a per-(x,y)-column histogram of the 2x2 lateral footprints;
+//   k_scan     exclusive scan of the 10 000 column counters + work list of the non-empty columns;
 //   k_fill     scatter of (corner, z-cell, point) keys into their column's bucket;
-//   k_columns  one CTA per non-empty column: sorts the bucket by (corner_xy, z-cell, point), then thread z
+//   k_columns  persistent CTAs over the non-empty columns: sort the bucket by (corner_xy, z-cell, point), then thread z
 //              replays the reference's accumulation for voxel (x,y,z) exactly - eight corner groups in
 //              itertools.product order, points in index order, fp32 add, round-half-even after each group -
 //              and the 80 voxels are reduced to the two height projections, thresholded and written to a
@@ -31,7 +32,7 @@ namespace pn {
 
 namespace {
 
-constexpr int kMaxFeat = 24;  // 1 + num_sem_categories upper bound held in registers per voxel
+constexpr int kMaxFeat = 24;  // 1 + num_sem_categories upper bound held in registers per voxel (k_columns<24>)
 
 __device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving map float -> uint32
   const uint32_t u = __float_as_uint(f);
@@ -67,40 +68,48 @@ __device__ __forceinline__ void corner(float coord, float G, int ix, int& p, flo
 }
 
 // --------------------------------------------------------------------------------------------------
-// k_points: coordinates, stair mask, column histogram.  grid = E, block = 1024.
-__global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __restrict__ obs, float* __restrict__ coords,
-                                                 int* __restrict__ col_count, int* __restrict__ stair_flag) {
+// k_coords: one thread per depth pixel - splat coordinates + the two counts the stair-mask test needs
+// (qcount[e] = {#valid heights, #heights in the stair band}).  grid = (ceil(N / 256), E).
+__global__ void __launch_bounds__(256) k_coords(SemMapCfg c, const float* __restrict__ obs, float* __restrict__ coords,
+                                                uint32_t* __restrict__ qcount) {
+  pdl_grid_sync();
+  const int e = blockIdx.y;
+  const int N = c.h * c.w;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* depth = obs + (static_cast<size_t>(e) * c.channels + 3) * N;
+  float* cx = coords + static_cast<size_t>(e) * 3 * N;
+  uint32_t valid = 0, mid = 0;
+  if (i < N) {
+    float X, Y, Z;
+    point_coords(c, i / c.w, i % c.w, depth[i], X, Y, Z);
+    cx[i] = X, cx[N + i] = Y, cx[2 * N + i] = Z;
+    if (Z > -1.f && Z < 1.f) {
+      const float mz = Z * 2.f + 1.6f;
+      valid = 1;
+      mid = (mz > 0.2f && mz < 0.7f) ? 1u : 0u;
+    }
+  }
+  const uint32_t nv = __popc(__ballot_sync(0xffffffffu, valid != 0)), nm = __popc(__ballot_sync(0xffffffffu, mid != 0));
+  if ((threadIdx.x & 31) == 0 && nv) {
+    atomicAdd(&qcount[e * 2], nv);
+    if (nm) atomicAdd(&qcount[e * 2 + 1], nm);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// k_quantile: the stair-mask decision of mapping.py:90-100 (3 % quantile of the valid heights by a 4-pass radix
+// select instead of a sort).  grid = E, block = 1024.
+__global__ void __launch_bounds__(1024) k_quantile(SemMapCfg c, const float* __restrict__ coords,
+                                                   const uint32_t* __restrict__ qcount, int* __restrict__ stair_flag) {
   pdl_grid_sync();
   const int e = blockIdx.x;
   const int N = c.h * c.w;
-  const float* depth = obs + (static_cast<size_t>(e) * c.channels + 3) * N;
-  const float* toilet = obs + (static_cast<size_t>(e) * c.channels + 4 + 4) * N;
-  float* cx = coords + static_cast<size_t>(e) * 3 * N;
-  float* cy = cx + N;
-  float* cz = cy + N;
+  const float* cz = coords + static_cast<size_t>(e) * 3 * N + 2 * static_cast<size_t>(N);
   __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_k, s_n, s_mid, s_cnt_le, s_next;
-  __shared__ int s_flag;
+  __shared__ uint32_t s_prefix, s_k, s_cnt_le, s_next;
   const int tid = threadIdx.x;
-
-  // pass 0: coordinates + count of valid heights
-  if (tid == 0) s_n = 0, s_mid = 0;
-  __syncthreads();
-  uint32_t n_local = 0, mid_local = 0;
-  for (int i = tid; i < N; i += blockDim.x) {
-    float X, Y, Z;
-    point_coords(c, i / c.w, i % c.w, depth[i], X, Y, Z);
-    cx[i] = X, cy[i] = Y, cz[i] = Z;
-    if (Z > -1.f && Z < 1.f) {
-      const float mz = Z * 2.f + 1.6f;
-      ++n_local;
-      if (mz > 0.2f && mz < 0.7f) ++mid_local;
-    }
-  }
-  atomicAdd(&s_n, n_local);
-  atomicAdd(&s_mid, mid_local);
-  __syncthreads();
-  const uint32_t n = s_n;
+  const uint32_t n = qcount[e * 2];
+  const uint32_t s_mid = qcount[e * 2 + 1];
 
   // torch.quantile(my_zs, 0.03), linear interpolation: ranks = q*(n-1) in fp32 (mapping.py:94)
   bool flag = false;
@@ -119,12 +128,19 @@ __global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __res
       __syncthreads();
       const uint32_t prefix = s_prefix;
       const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-      for (int i = tid; i < N; i += blockDim.x) {
-        const float Z = cz[i];
-        if (Z > -1.f && Z < 1.f) {
-          const uint32_t key = float_key(Z * 2.f + 1.6f);
-          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      // heights cluster in a handful of bins: aggregate equal bins inside the warp before touching shared memory
+      for (int i0 = 0; i0 < N; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        uint32_t bin = 0xffffffffu;
+        if (i < N) {
+          const float Z = cz[i];
+          if (Z > -1.f && Z < 1.f) {
+            const uint32_t key = float_key(Z * 2.f + 1.6f);
+            if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+          }
         }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xffffffffu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<uint32_t>(__popc(peers)));
       }
       __syncthreads();
       if (tid == 0) {
@@ -163,16 +179,26 @@ __global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __res
     // `torch.sum(...) > 0.2 * len(my_zs)`: int64 tensor vs python float -> compared in fp32
     flag = (q > 0.2f) && (static_cast<float>(s_mid) > static_cast<float>(0.2 * static_cast<double>(n)));
   }
-  if (tid == 0) {
-    s_flag = flag ? 1 : 0;
-    stair_flag[e] = s_flag;
-  }
-  __syncthreads();
-  const bool mask_stairs = s_flag != 0;
+  if (tid == 0) stair_flag[e] = flag ? 1 : 0;
+}
 
-  // masking + column histogram
+// --------------------------------------------------------------------------------------------------
+// k_hist: stair masking + per-(x,y)-column histogram of the points' 2 x 2 lateral footprints.
+// grid = (ceil(N / 256), E), one thread per depth pixel.
+__global__ void __launch_bounds__(256) k_hist(SemMapCfg c, const float* __restrict__ obs, float* __restrict__ coords,
+                                              const int* __restrict__ stair_flag, int* __restrict__ col_count) {
+  pdl_grid_sync();
+  const int e = blockIdx.y;
+  const int N = c.h * c.w;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* toilet = obs + (static_cast<size_t>(e) * c.channels + 4 + 4) * N;
+  float* cx = coords + static_cast<size_t>(e) * 3 * N;
+  float* cy = cx + N;
+  float* cz = cy + N;
+  const bool mask_stairs = stair_flag[e] != 0;
   int* counts = col_count + static_cast<size_t>(e) * c.vr * c.vr;
-  for (int i = tid; i < N; i += blockDim.x) {
+  {
     float X = cx[i], Y = cy[i], Z = cz[i];
     if (mask_stairs && (Z * 2.f + 1.6f < 0.7f) && toilet[i] == 0.f) {
       X = Y = Z = 99999.f;
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(1024) k_points(SemMapCfg c, const float* __res
     bool sz0, sz1;
     corner(Z, c.nz_f, 0, pz0, wz0, sz0);
     corner(Z, c.nz_f, 1, pz1, wz1, sz1);
-    if (!sz0 && !sz1) continue;
+    if (!sz0 && !sz1) return;
 #pragma unroll
     for (int ix = 0; ix < 2; ++ix) {
       int px;
@@ -322,13 +348,16 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* keys, int n, uint
   return lo;
 }
 
-__global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int large, const float* __restrict__ obs,
+template <int kF>  // register budget for the per-voxel features: 12 (the reference's 10 categories + count) or kF
+__global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, const float* __restrict__ obs,
                                                  const float* __restrict__ coords, const int* __restrict__ col_start,
                                                  const uint32_t* __restrict__ entries, const int* __restrict__ col_list,
                                                  const int* __restrict__ list_n, float* __restrict__ ego) {
   pdl_grid_sync();
   extern __shared__ uint32_t keys[];
-  __shared__ float red_all[4][kMaxFeat], red_agent[4][kMaxFeat];
+  __shared__ float red_all[kF], red_agent[kF];
+  __shared__ uint32_t raw[128];
+  __shared__ uint32_t zbits[4];  // z cells (0 .. nz, biased) that occur in the column's keys
   const int e = blockIdx.y;
   const int ncols = c.vr * c.vr;
   const int N = c.h * c.w;
@@ -345,33 +374,57 @@ __global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int large, const f
   const int px = col / c.vr, py = col - px * c.vr;
   const int cell = py * c.vr + px;  // voxels.transpose(2,3): row = y index, column = x index
   __syncthreads();  // the previous column's keys / partial sums are no longer read
-  // load + bitonic sort (ascending) of the column's keys
-  int npow = 1;
-  while (npow < n) npow <<= 1;
+  if (tid < 4) zbits[tid] = 0u;
+  if (tid < kF) red_all[tid] = 0.f, red_agent[tid] = 0.f;
   const uint32_t* ent = entries + static_cast<size_t>(e) * 4 * N + s0;
-  for (int i = tid; i < npow; i += blockDim.x) keys[i] = i < n ? ent[i] : 0xffffffffu;
-  __syncthreads();
-  for (int k = 2; k <= npow; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < npow; i += blockDim.x) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint32_t a = keys[i], b = keys[l];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) keys[i] = b, keys[l] = a;
+  if (n <= 128) {
+    // small column (the common case): rank sort - keys are unique (they embed the point index), so the number of
+    // smaller keys is the sorted position; two barriers instead of the ~log^2 n of the bitonic network
+    if (tid < n) raw[tid] = ent[tid];
+    __syncthreads();
+    if (tid < n) {
+      const uint32_t k = raw[tid];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += raw[j] < k ? 1 : 0;
+      keys[rank] = k;
+      atomicOr(&zbits[(k >> 20) & 3u], 1u << ((k >> 15) & 31u));  // z cell (7 bits at 15..21) seen in this column
+    }
+    __syncthreads();
+  } else {
+    // load + bitonic sort (ascending) of the column's keys
+    int npow = 1;
+    while (npow < n) npow <<= 1;
+    for (int i = tid; i < npow; i += blockDim.x) {
+      const uint32_t k = i < n ? ent[i] : 0xffffffffu;
+      keys[i] = k;
+      if (i < n) atomicOr(&zbits[(k >> 20) & 3u], 1u << ((k >> 15) & 31u));
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < npow; i += blockDim.x) {
+          const int l = i ^ j;
+          if (l > i) {
+            const uint32_t a = keys[i], b = keys[l];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) keys[i] = b, keys[l] = a;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
 
   // thread z replays the accumulation of voxel (px, py, z)
   const int z = tid;
   const int nf = c.nf;
-  float acc[kMaxFeat];
+  float acc[kF];
 #pragma unroll
-  for (int f = 0; f < kMaxFeat; ++f) acc[f] = 0.f;
-  if (z > 0 && z < c.nz) {
+  for (int f = 0; f < kF; ++f) acc[f] = 0.f;
+  // voxel z receives entries whose lower z cell (biased by +1 in the key) is z + 1 (corner iz = 0) or z (iz = 1)
+  const bool touched = z > 0 && z < c.nz &&
+                       (((zbits[(z + 1) >> 5] >> ((z + 1) & 31)) | (zbits[z >> 5] >> (z & 31))) & 1u) != 0u;
+  if (touched) {
     const float* cx = coords + static_cast<size_t>(e) * 3 * N;
     const float* feat = obs + (static_cast<size_t>(e) * c.channels + 4) * N;  // semantic channels
     for (int ixy = 0; ixy < 4; ++ixy) {
@@ -381,47 +434,65 @@ __global__ void __launch_bounds__(128) k_columns(SemMapCfg c, int large, const f
         const uint32_t kbase = (static_cast<uint32_t>(ixy) << 22) | (static_cast<uint32_t>(z - iz + 1) << 15);
         const int lo = lower_bound_key(keys, n, kbase);
         const int hi = lower_bound_key(keys, n, kbase + (1u << 15));
-        for (int t = lo; t < hi; ++t) {
-          const int i = static_cast<int>(keys[t] & 0x7fffu);
-          int p;
-          float wx, wy, wz;
-          bool s;
-          corner(cx[i], c.vr_f, ix, p, wx, s);
-          corner(cx[N + i], c.vr_f, iy, p, wy, s);
-          corner(cx[2 * N + i], c.nz_f, iz, p, wz, s);
-          const float w = ((1.f * wx) * wy) * wz;
-          acc[0] = acc[0] + 1.f * w;
+        // two entries in flight (their coordinate and feature loads are independent of the running sums); the adds
+        // stay in entry order, as the reference's index_add does
+        for (int t0 = lo; t0 < hi; t0 += 2) {
+          int idx[2];
+          float cxv[2], cyv[2], czv[2], wv[2];
+          float fv[2][kF];
 #pragma unroll
-          for (int f = 1; f < kMaxFeat; ++f) {
-            if (f < nf) acc[f] = acc[f] + feat[static_cast<size_t>(f - 1) * N + i] * w;
+          for (int u = 0; u < 2; ++u) idx[u] = static_cast<int>(keys[min(t0 + u, hi - 1)] & 0x7fffu);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) cxv[u] = cx[idx[u]], cyv[u] = cx[N + idx[u]], czv[u] = cx[2 * N + idx[u]];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int f = 1; f < kF; ++f) fv[u][f] = (f < nf) ? feat[static_cast<size_t>(f - 1) * N + idx[u]] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            int p;
+            float wx, wy, wz;
+            bool s;
+            corner(cxv[u], c.vr_f, ix, p, wx, s);
+            corner(cyv[u], c.vr_f, iy, p, wy, s);
+            corner(czv[u], c.nz_f, iz, p, wz, s);
+            wv[u] = ((1.f * wx) * wy) * wz;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (t0 + u < hi) {
+              acc[0] = acc[0] + 1.f * wv[u];
+#pragma unroll
+              for (int f = 1; f < kF; ++f) {
+                if (f < nf) acc[f] = acc[f] + fv[u][f] * wv[u];
+              }
+            }
           }
         }
         // grid_flat = torch.round(grid_flat) after every corner (depth_utils.py:250): half-to-even
 #pragma unroll
-        for (int f = 0; f < kMaxFeat; ++f) acc[f] = rintf(acc[f]);
+        for (int f = 0; f < kF; ++f) acc[f] = rintf(acc[f]);
       }
     }
   }
-  // height projections (mapping.py:102-113): exact integer sums, order-free
-  const bool in_agent = (z >= c.min_z && z < c.max_z);
-  const int lane = tid & 31, wid = tid >> 5;
+  // height projections (mapping.py:102-113): sums of integer-valued floats - exact, hence order-free
+  if (touched) {
+    const bool in_agent = (z >= c.min_z && z < c.max_z);
 #pragma unroll
-  for (int f = 0; f < kMaxFeat; ++f) {
-    float a = acc[f], g = in_agent ? acc[f] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      g += __shfl_xor_sync(0xffffffffu, g, o);
+    for (int f = 0; f < kF; ++f) {
+      if (f < nf && acc[f] != 0.f) {
+        atomicAdd(&red_all[f], acc[f]);
+        if (in_agent) atomicAdd(&red_agent[f], acc[f]);
+      }
     }
-    if (lane == 0) red_all[wid][f] = a, red_agent[wid][f] = g;
   }
   __syncthreads();
   if (tid < c.ego_channels) {
     // ego channel 0 = obstacle, 1 = explored, 2.. = categories (local-map channels 4..)
     const int ch = tid;
     const int f = ch < 2 ? 0 : ch - 1;
-    const float all_h = red_all[0][f] + red_all[1][f] + red_all[2][f] + red_all[3][f];
-    const float agent_h = red_agent[0][f] + red_agent[1][f] + red_agent[2][f] + red_agent[3][f];
+    const float all_h = red_all[f], agent_h = red_agent[f];
     float v;
     if (ch == 0) v = agent_h / c.map_thr;
     else if (ch == 1) v = all_h / c.exp_thr;
@@ -547,11 +618,12 @@ void SemMap::init(const SemMapCfg& cfg, int envs) {
   c = cfg;
   E = envs;
   PN_REQUIRE(c.nf <= kMaxFeat, "semmap: too many semantic categories");
-  PN_REQUIRE(c.nz <= 128 && c.h * c.w <= 32767, "semmap: geometry out of range");
+  PN_REQUIRE(c.nz <= 126 && c.h * c.w <= 32767, "semmap: geometry out of range");
   const size_t N = static_cast<size_t>(c.h) * c.w;
   const size_t ncols = static_cast<size_t>(c.vr) * c.vr;
   coords = static_cast<float*>(arena.alloc(E * 3 * N * sizeof(float)));
-  col_count = static_cast<int*>(arena.alloc(E * ncols * sizeof(int)));
+  col_count = static_cast<int*>(arena.alloc((E * ncols + 2 * E) * sizeof(int)));  // [E][vr*vr] + qcount[E][2]
+  qcount = reinterpret_cast<uint32_t*>(col_count + E * ncols);
   col_start = static_cast<int*>(arena.alloc(E * (ncols + 1) * sizeof(int)));
   col_fill = static_cast<int*>(arena.alloc(E * ncols * sizeof(int)));
   entries = static_cast<uint32_t*>(arena.alloc(E * 4 * N * sizeof(uint32_t)));
@@ -563,7 +635,8 @@ void SemMap::init(const SemMapCfg& cfg, int envs) {
   PN_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   xf = static_cast<float*>(arena.alloc(E * 4 * sizeof(float)));
   stair_flag = static_cast<int*>(arena.alloc(E * sizeof(int)));
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns<kMaxFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
 }
 
 void SemMap::forward(const float* obs, const float* pose_delta, const float* maps_last, long long ml_env,
@@ -571,17 +644,24 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
                      cudaStream_t s) {
   const int N = c.h * c.w;
   const int ncols = c.vr * c.vr;
-  PN_CUDA_CHECK(cudaMemsetAsync(col_count, 0, static_cast<size_t>(E) * ncols * sizeof(int), s));
+  PN_CUDA_CHECK(cudaMemsetAsync(col_count, 0, (static_cast<size_t>(E) * ncols + 2 * E) * sizeof(int), s));  // + qcount
   PN_CUDA_CHECK(cudaMemsetAsync(ego, 0, static_cast<size_t>(E) * c.ego_channels * ncols * sizeof(float), s));
-  launch_pdl(k_points, E, 1024, 0, s, c, obs, coords, col_count, stair_flag);
+  launch_pdl(k_coords, dim3((N + 255) / 256, E), 256, 0, s, c, obs, coords, qcount);
+  launch_pdl(k_quantile, E, 1024, 0, s, c, coords, qcount, stair_flag);
+  launch_pdl(k_hist, dim3((N + 255) / 256, E), 256, 0, s, c, obs, coords, stair_flag, col_count);
   constexpr int kSmallCap = 2048;
   launch_pdl(k_scan, E, 1024, 0, s, ncols, kSmallCap, col_count, col_start, col_fill, col_list, list_n);
   launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
   // non-empty columns only, persistent CTAs: 8 KB of key storage each for the small ones, 128 KB for the rare
   // columns that collect more than kSmallCap entries (a wall seen edge-on)
   const int g_small = std::min(ncols, num_sms * 8), g_large = std::min(ncols, num_sms);
-  launch_pdl(k_columns, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
-  launch_pdl(k_columns, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);
+  if (c.nf <= 12) {
+    launch_pdl(k_columns<12>, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns<12>, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);
+  } else {
+    launch_pdl(k_columns<kMaxFeat>, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns<kMaxFeat>, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);
+  }
   launch_pdl(k_pose, (E + 63) / 64, 64, 0, s, c, E, pose_delta, poses_inout, xf);
   launch_pdl(k_fuse, dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
   PN_CUDA_CHECK(cudaGetLastError());

@@ -26,6 +26,7 @@ struct SemMap {
   Arena arena;
   float* coords = nullptr;     // [E][3][N] normalised splat coordinates
   int* col_count = nullptr;    // [E][vr*vr]
+  uint32_t* qcount = nullptr;  // [E][2] valid heights / heights in the stair band (same allocation as col_count)
   int* col_start = nullptr;    // [E][vr*vr + 1]
   int* col_fill = nullptr;     // [E][vr*vr]
   uint32_t* entries = nullptr; // [E][4*N] bucketed (corner, z, point) keys
@@ -35,7 +36,7 @@ struct SemMap {
   int num_sms = 148;
   float* xf = nullptr;         // [E][4] cos, sin, tx, ty of the sampling grids
   int* stair_flag = nullptr;   // [E]
-  static constexpr int kLaunches = 7;  // kernels per forward (plus two memsets)
+  static constexpr int kLaunches = 9;  // kernels per forward (plus two memsets)
 
   void init(const SemMapCfg& cfg, int envs);
   // maps_last may be a strided view (element strides between envs, channel planes and rows; unit x stride)

@@ -84,7 +84,9 @@ def test_tf32_vs_fp32_oracle(weights, oracle_model):
 
 
 def test_batch_and_graph_replay(weights, oracle_model):
-    """B=3: per-sample results equal the B=1 results; repeated calls (CUDA-graph replay) are bit-stable."""
+    """B=3: repeated calls (CUDA-graph replay) are bit-stable; per-sample results agree with a B=1 engine up to the launch
+    configuration (the measured tile / split-K choice depends on the batch's tile count, so fp32 sums are associated
+    differently and bf16 roundings may flip)."""
     xs = np.stack([oracle.synth_partial_map(14, 96, 96, seed=s) for s in (1, 2, 3)])
     seg = _segmentor(weights, "bf16")
     xd = torch.from_numpy(xs).cuda()
@@ -96,7 +98,7 @@ def test_batch_and_graph_replay(weights, oracle_model):
     seg1 = _segmentor(weights, "bf16")
     for i in range(3):
         one = seg1.forward_device(xd[i:i + 1])
-        assert torch.equal(one[0], a[i])
+        assert (one[0] - a[i]).abs().max().item() <= 2e-2 * a[i].abs().max().item()
 
 
 def test_wrong_channels_raises(weights):

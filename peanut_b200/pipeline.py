@@ -53,7 +53,7 @@ class PerceptionPipeline:
         self.obs = torch.zeros((E, 4 + nsem, a.frame_height, a.frame_width), dtype=torch.float32, device=d)
         self.pred_out = torch.zeros((E, num_pred_classes) + self.map_shape[1:], dtype=torch.float32, device=d)
         self._side = torch.cuda.Stream(device=d)
-        self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+        self._fork, self._join, self._join_d2h = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         # staging for the host entry point
         self._dev_in = None
         self._host_out = None
@@ -103,14 +103,22 @@ class PerceptionPipeline:
             self._host_out = (torch.empty(self.pred_out.shape, dtype=torch.float32).pin_memory(),
                               torch.empty((self.E, 3), dtype=torch.float32).pin_memory(),
                               torch.empty((self.E, self.args.vision_range, self.args.vision_range), dtype=torch.float32).pin_memory())
-        for dst, src in zip(self._dev_in, (rgb_h, depth_h, pose_delta_h, partial_map_h)):
+        # the partial map (the largest input) is only read by the map-completion net, which runs on the side stream:
+        # its copy goes there too and overlaps Mask-RCNN instead of delaying it
+        for dst, src in zip(self._dev_in[:3], (rgb_h, depth_h, pose_delta_h)):
             dst.copy_(src, non_blocking=True)
+        with torch.cuda.stream(self._side):
+            self._dev_in[3].copy_(partial_map_h, non_blocking=True)
         rgb, depth, delta, pmap = self._dev_in
         _, fp, new_map, poses, pred = self.step_device(rgb, depth, delta, local_map, poses, pmap)
-        self._host_out[0].copy_(pred, non_blocking=True)
+        main = torch.cuda.current_stream(d)
+        with torch.cuda.stream(self._side):  # the predicted map leaves on the side stream as soon as it exists
+            self._host_out[0].copy_(pred, non_blocking=True)
+            self._join_d2h.record(self._side)
         self._host_out[1].copy_(poses, non_blocking=True)
         self._host_out[2].copy_(fp, non_blocking=True)
-        torch.cuda.current_stream(d).synchronize()
+        main.wait_event(self._join_d2h)
+        main.synchronize()
         return self._host_out[0], self._host_out[1], self._host_out[2], new_map
 
     def h2d_bytes(self, rgb_h, depth_h, pose_delta_h, partial_map_h):

@@ -98,9 +98,13 @@ def _frozen_bn(w, prefix):
 
 
 def _conv_bn(x, w, name, stride=1, padding=0, relu=False, emulate=False):
-    y = F.conv2d(x, _r(w[name + ".weight"], emulate), None, stride, padding)
     s, b = _frozen_bn(w, name + ".norm")
-    y = y * s[None, :, None, None] + b[None, :, None, None]
+    if emulate:  # the CUDA path stores bf16(weight * scale) and adds the shift in the epilogue
+        y = F.conv2d(x, _r(w[name + ".weight"] * s[:, None, None, None], True), None, stride, padding)
+        y = y + b[None, :, None, None]
+    else:
+        y = F.conv2d(x, w[name + ".weight"], None, stride, padding)
+        y = y * s[None, :, None, None] + b[None, :, None, None]
     return F.relu(y) if relu else y
 
 

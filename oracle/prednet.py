@@ -214,11 +214,14 @@ def _r(t, emulate):
 
 
 def _conv_bn(x, conv, bn, relu, emulate, residual=None):
-    w = _r(conv.weight, emulate)
-    y = F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation)
     scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
     bias = bn.bias - bn.running_mean * scale
-    y = y * scale[None, :, None, None] + bias[None, :, None, None]
+    if emulate:  # the CUDA path stores bf16(weight * scale) and adds the shift in the epilogue
+        y = F.conv2d(x, _r(conv.weight * scale[:, None, None, None], True), None, conv.stride, conv.padding, conv.dilation)
+        y = y + bias[None, :, None, None]
+    else:
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation)
+        y = y * scale[None, :, None, None] + bias[None, :, None, None]
     if residual is not None:
         y = y + residual
     if relu:

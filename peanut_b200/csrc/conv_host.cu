@@ -296,14 +296,15 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   // weights / scale / bias are padded to a multiple of the widest tile, so every launch configuration can use them
   const int cout_pad = round_up(sp.Cout, 256);
 
-  // Pack weights [cout_pad][taps][cin_pad] in the activation dtype.
+  // Pack weights [cout_pad][taps][cin_pad] in the activation dtype; the per-channel scale (folded BatchNorm gamma / sigma)
+  // is multiplied in BEFORE the rounding to bf16 / tf32, so the epilogue only adds the bias.
   std::vector<float> wp(static_cast<size_t>(cout_pad) * ktot, 0.f);
   for (int co = 0; co < sp.Cout; ++co)
     for (int ci = 0; ci < sp.Cin; ++ci)
       for (int r = 0; r < sp.R; ++r)
         for (int s = 0; s < sp.S; ++s)
           wp[(static_cast<size_t>(co) * taps + r * sp.S + s) * cin_pad + ci] =
-              weight[((static_cast<size_t>(co) * sp.Cin + ci) * sp.R + r) * sp.S + s];
+              weight[((static_cast<size_t>(co) * sp.Cin + ci) * sp.R + r) * sp.S + s] * (scale ? scale[co] : 1.f);
   void* w_dev = nullptr;
   if (dt == kBF16) {
     std::vector<uint16_t> wb(wp.size());
@@ -319,12 +320,8 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     }
     w_dev = net.arena.upload(wp);
   }
-  std::vector<float> sc(cout_pad, 0.f), bi(cout_pad, 0.f);
-  for (int i = 0; i < sp.Cout; ++i) {
-    sc[i] = scale ? scale[i] : 1.f;
-    bi[i] = bias ? bias[i] : 0.f;
-  }
-  const float* sc_dev = net.arena.upload(sc);
+  std::vector<float> bi(cout_pad, 0.f);
+  for (int i = 0; i < sp.Cout; ++i) bi[i] = bias ? bias[i] : 0.f;
   const float* bi_dev = net.arena.upload(bi);
 
   struct Variant {
@@ -360,7 +357,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     p.cout_store = std::min(round_up(sp.Cout, 8), out.C);
     PN_REQUIRE(p.cout_store >= sp.Cout, name + ": output view too narrow");
     p.a_tiled = a_tiled ? 1 : 0;
-    p.scale = sc_dev, p.bias = bi_dev;
+    p.bias = bi_dev;
     p.residual = residual ? residual->ptr : nullptr;
     p.ldr = residual ? residual->ld : 0;
     if (residual) PN_REQUIRE(residual->dt == dt && residual->pixels() == M, name + ": residual mismatch");
@@ -398,7 +395,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
 
     const size_t stage_bytes = static_cast<size_t>(kBlockM + (pair ? bn / 2 : bn)) * sw;
     const int kblocks = taps * kb_per_tap;
-    size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 8 * bn * sizeof(float) /*scale+bias per epilogue warp*/ + 256 /*barriers*/;
+    size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 4 * bn * sizeof(float) /*bias per epilogue warp*/ + 256 /*barriers*/;
     size_t budget = 227 * 1024 - fixed_bytes;
     int stages = static_cast<int>(budget / stage_bytes);
     if (p.epi_tma && kblocks >= 32) {

@@ -8,7 +8,8 @@
 // * weights are packed [Cout_pad][R*S*Cin_pad] (K-major) and fetched by tiled 2-D TMA;
 // * tcgen05.mma (M=128, N=BN, K=32 bytes) accumulates in TMEM, two accumulator stages so that the
 //   epilogue of tile i overlaps the main loop of tile i+1; the kernel is persistent (grid = #SMs);
-// * the epilogue fuses folded BatchNorm (per-channel scale/bias), residual add and ReLU and writes NHWC.
+// * the epilogue adds the per-channel bias (BatchNorm is folded: its scale into the weights, its shift into the bias),
+//   the residual and the ReLU, and writes NHWC.
 //   Fast path: the residual tile is prefetched by TMA into shared memory by a dedicated warp (it does not
 //   depend on the accumulators, so it runs ahead of the MMAs), results are staged in swizzled shared
 //   memory and written back with TMA bulk stores (full 128-byte lines, M/N tails clipped by hardware).
@@ -42,7 +43,6 @@ struct ConvParams {
   int m_tiles, n_tiles;
   int cout_store;  // channels actually written per pixel (multiple of 8)
   int a_tiled;     // 1: A is a plain [M, K] matrix fetched with tiled 2-D TMA
-  const float* scale;  // [n_tiles * BN]
   const float* bias;   // [n_tiles * BN]
   const void* residual;  // optional, same dtype as the activations, row stride ldr
   long long ldr;
@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t r, uint32_t j, uint32_t cb)
   return off ^ (((off >> 7) & ((cb >> 4) - 1)) << 4);
 }
 
-// Direct epilogue tail for 8 consecutive output channels of row m: y already holds scale*acc + bias.
+// Direct epilogue tail for 8 consecutive output channels of row m: y already holds acc + bias.
 template <typename T>
 __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long m, int n0, float* y) {
   if (p.residual != nullptr) {
@@ -230,7 +230,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem_out = smem_b + p.stages * b_bytes;
   uint8_t* smem_res = smem_out + p.out_bufs * chunk_bytes;
   float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * chunk_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_scale + 8 * BN);  // one [scale BN][bias BN] copy per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_scale + 4 * BN);  // one bias[BN] copy per epilogue warp
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -461,7 +461,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr int kUnits = 32 * sizeof(T) / 16;  // 16-byte units per 32 columns
     const int subs_per_chunk = cols_per_chunk / 32;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t sb_addr = smem_u32(smem_scale) + quarter * (2 * BN * 4);  // [scale BN][bias BN] of this warp
+    const uint32_t sb_addr = smem_u32(smem_scale) + quarter * (BN * 4);  // bias[BN] of this warp
     const uint32_t out_addr = smem_u32(smem_out);
     const uint32_t res_addr = smem_u32(smem_res);
     const bool has_res = p.residual != nullptr;
@@ -480,10 +480,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (n_tile != cached_n_tile) {
         __syncwarp();
         for (int i = lane * 4; i < BN; i += 128) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n_tile * BN + i));
           const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n_tile * BN + i));
-          sts_v4(sb_addr + i * 4, __float_as_uint(sc.x), __float_as_uint(sc.y), __float_as_uint(sc.z), __float_as_uint(sc.w));
-          sts_v4(sb_addr + (BN + i) * 4, __float_as_uint(bi.x), __float_as_uint(bi.y), __float_as_uint(bi.z), __float_as_uint(bi.w));
+          sts_v4(sb_addr + i * 4, __float_as_uint(bi.x), __float_as_uint(bi.y), __float_as_uint(bi.z), __float_as_uint(bi.w));
         }
         cached_n_tile = n_tile;
         __syncwarp();
@@ -513,12 +511,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // All shared-memory loads of the group are issued back to back (the asm statements keep program order, so
         // interleaving them with the stores would serialise one load-compute-store chain per 16-byte unit).
         const uint32_t sb = sb_addr + grp * 32 * 4;
-        float4 sc[8], bi[8];
+        float4 bi[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sc[j] = lds_f4(sb + j * 16);
-          bi[j] = lds_f4(sb + BN * 4 + j * 16);
-        }
+        for (int j = 0; j < 8; ++j) bi[j] = lds_f4(sb + j * 16);
         uint4 rv[kUnits];
         if (has_res) {
           const uint32_t rbuf = res_addr + rb * chunk_bytes + row_off;
@@ -528,10 +523,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float y[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          y[4 * j] = fmaf(__uint_as_float(v[4 * j]), sc[j].x, bi[j].x);
-          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc[j].y, bi[j].y);
-          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc[j].z, bi[j].z);
-          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc[j].w, bi[j].w);
+          y[4 * j] = __uint_as_float(v[4 * j]) + bi[j].x;
+          y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bi[j].y;
+          y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bi[j].z;
+          y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bi[j].w;
         }
         if (has_res) {
 #pragma unroll
@@ -661,7 +656,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float y[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              y[j] = fmaf(__uint_as_float(v[j]), __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
+              y[j] = __uint_as_float(v[j]) + __ldg(p.bias + n0 + j);
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -708,7 +703,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               y[4] += b1.x, y[5] += b1.y, y[6] += b1.z, y[7] += b1.w;
             }
   #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], __ldg(p.scale + n0 + j), __ldg(p.bias + n0 + j));
+            for (int j = 0; j < 8; ++j) y[j] = y[j] + __ldg(p.bias + n0 + j);
             epilogue_store8<T>(p, m, n0, y);
           }
         }

@@ -298,13 +298,32 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
 
   // Pack weights [cout_pad][taps][cin_pad] in the activation dtype; the per-channel scale (folded BatchNorm gamma / sigma)
   // is multiplied in BEFORE the rounding to bf16 / tf32, so the epilogue only adds the bias.
-  std::vector<float> wp(static_cast<size_t>(cout_pad) * ktot, 0.f);
+  // + one extra K block per output channel: (bias_hi, bias_lo, 0, ...), used when the bias rides through the tensor core
+  const long long ktot_w = ktot + block_k;
+  std::vector<float> wp(static_cast<size_t>(cout_pad) * ktot_w, 0.f);
   for (int co = 0; co < sp.Cout; ++co)
     for (int ci = 0; ci < sp.Cin; ++ci)
       for (int r = 0; r < sp.R; ++r)
         for (int s = 0; s < sp.S; ++s)
-          wp[(static_cast<size_t>(co) * taps + r * sp.S + s) * cin_pad + ci] =
+          wp[static_cast<size_t>(co) * ktot_w + static_cast<size_t>(r * sp.S + s) * cin_pad + ci] =
               weight[((static_cast<size_t>(co) * sp.Cin + ci) * sp.R + r) * sp.S + s] * (scale ? scale[co] : 1.f);
+  for (int co = 0; co < sp.Cout && bias; ++co) {  // hi + lo in the storage precision: exact to ~2^-17 (bf16) / 2^-21 (tf32)
+    const float b = bias[co];
+    float hi, lo;
+    if (dt == kBF16) {
+      const uint32_t h = static_cast<uint32_t>(f32_to_bf16(b)) << 16;
+      std::memcpy(&hi, &h, 4);
+      lo = b - hi;
+    } else {
+      uint32_t u;
+      std::memcpy(&u, &b, 4);
+      if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+      std::memcpy(&hi, &u, 4);
+      lo = b - hi;
+    }
+    wp[static_cast<size_t>(co) * ktot_w + ktot] = hi;
+    wp[static_cast<size_t>(co) * ktot_w + ktot + 1] = lo;
+  }
   void* w_dev = nullptr;
   if (dt == kBF16) {
     std::vector<uint16_t> wb(wp.size());
@@ -342,7 +361,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     } else {
       tm.a = encode_im2col(dt, in, cin_pad, sp.pad, pad_w, sp.dil, sp.R, sp.S, sp.stride, stride_w, block_k, kBlockM, sw);
     }
-    tm.b = encode_tiled_2d(dt, w_dev, ktot, cout_pad, static_cast<uint64_t>(ktot) * es, block_k, pair ? bn / 2 : bn, sw);
+    tm.b = encode_tiled_2d(dt, w_dev, ktot_w, cout_pad, static_cast<uint64_t>(ktot_w) * es, block_k, pair ? bn / 2 : bn, sw);
     tm.out = tm.b;
     tm.res = tm.b;
 
@@ -393,9 +412,13 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
       }
     }
 
+    // worth it where the epilogue is exposed (one tile per CTA: nothing overlaps it); persistent multi-tile launches hide
+    // the epilogue behind the next tile's main loop and would only pay for the extra K block
+    const bool one_tile_per_cta = static_cast<long long>(pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles <= (pair ? net.num_sms / 2 : net.num_sms);
+    p.bias_block = (p.epi_tma && splits == 1 && bias != nullptr && one_tile_per_cta) ? 1 : 0;
     const size_t stage_bytes = static_cast<size_t>(kBlockM + (pair ? bn / 2 : bn)) * sw;
     const int kblocks = taps * kb_per_tap;
-    size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 4 * bn * sizeof(float) /*bias per epilogue warp*/ + 256 /*barriers*/;
+    size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 4 * bn * sizeof(float) /*bias per epilogue warp*/ + kBlockM * 32 /*ones tile*/ + 256 /*barriers*/;
     size_t budget = 227 * 1024 - fixed_bytes;
     int stages = static_cast<int>(budget / stage_bytes);
     if (p.epi_tma && kblocks >= 32) {

@@ -44,6 +44,10 @@ struct ConvParams {
   int cout_store;  // channels actually written per pixel (multiple of 8)
   int a_tiled;     // 1: A is a plain [M, K] matrix fetched with tiled 2-D TMA
   const float* bias;   // [n_tiles * BN]
+  // 1: the bias rides through the tensor core - the packed weights carry one extra K block per output channel holding
+  // (bias_hi, bias_lo, 0, ...), multiplied by a constant tile of ones; the epilogue then adds nothing.  Fast epilogue,
+  // no split-K only.
+  int bias_block;
   const void* residual;  // optional, same dtype as the activations, row stride ldr
   long long ldr;
   void* out;
@@ -230,7 +234,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem_out = smem_b + p.stages * b_bytes;
   uint8_t* smem_res = smem_out + p.out_bufs * chunk_bytes;
   float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * chunk_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_scale + 4 * BN);  // one bias[BN] copy per epilogue warp
+  uint8_t* smem_ones = reinterpret_cast<uint8_t*>(smem_scale + 4 * BN);  // [128 rows][32 B], 32-byte swizzle: ones at k = 0, 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + kBlockM * 32);  // (smem_scale: one bias[BN] copy per epilogue warp)
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -261,6 +266,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&rempty_bar[i], 4);
     }
     fence_barrier_init();
+  }
+  if (p.bias_block && threadIdx.x < kBlockM) {
+    // A operand of the bias block: row r = (1, 1, 0, ...) in K; 32-byte rows, 32-byte swizzle (16-byte unit j of row r
+    // sits at unit j ^ ((r >> 2) & 1))
+    const uint32_t r = threadIdx.x;
+    uint4 one = make_uint4(0u, 0u, 0u, 0u), zero = one;
+    if constexpr (sizeof(T) == 2) one.x = 0x3f803f80u;            // two bf16 ones
+    else one.x = 0x3f800000u, one.y = 0x3f800000u;                  // two fp32 (tf32) ones
+    const uint32_t u = (r >> 2) & 1u;
+    *reinterpret_cast<uint4*>(smem_ones + r * 32 + (u << 4)) = one;
+    *reinterpret_cast<uint4*>(smem_ones + r * 32 + ((u ^ 1u) << 4)) = zero;
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
   }
   if (warp == kMmaWarp) {
     if constexpr (kPair) {
@@ -372,6 +389,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (++sx == p.S) sx = 0, ++r;
           }
         }
+        if (p.bias_block) {  // the bias block: weights' extra K block only (its A operand is the constant ones tile)
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (kPair ? 2u : 1u) * b_bytes);
+          if constexpr (kPair) {
+            tma_load_2d_pair(&tmap_b, leader_addr(&full_bar[stage]), smem_b + stage * b_bytes, kblocks * p.block_k,
+                             n_tile * BN + static_cast<int>(cta_rank) * kBLoad);
+          } else {
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kblocks * p.block_k, n_tile * BN);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -410,16 +441,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if constexpr (kPair) umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
           else umma_commit(&empty_bar[stage]);
           if (kb == 0) PN_DBG(it, 3);
-          if (kb == my_kblocks - 1) {
-            if constexpr (kPair) umma_commit_pair(&tfull_bar[acc]);
-            else umma_commit(&tfull_bar[acc]);
-            PN_DBG(it, 4);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (p.bias_block) {  // D += ones[128 x 2] * (bias_hi, bias_lo)[BN x 2]^T: one K step of the extra block
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc(smem_u32(smem_ones), 32);
+          const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + stage * b_bytes), p.sw);
+          if constexpr (kPair) {
+            if constexpr (ElemTraits<T>::kFormat == 1) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, 1u);
+            else umma_tf32_pair(d_tmem, adesc, bdesc, idesc, 1u);
+            umma_commit_pair(&empty_bar[stage]);
+          } else {
+            if constexpr (ElemTraits<T>::kFormat == 1) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+            else umma_tf32(d_tmem, adesc, bdesc, idesc, 1u);
+            umma_commit(&empty_bar[stage]);
           }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
+        if constexpr (kPair) umma_commit_pair(&tfull_bar[acc]);  // every MMA of this tile has retired
+        else umma_commit(&tfull_bar[acc]);
+        PN_DBG(it, 4);
       }
     }
   } else if (warp == kResidualWarp) {
@@ -477,7 +525,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
-      if (n_tile != cached_n_tile) {
+      if (n_tile != cached_n_tile && !p.bias_block) {
         __syncwarp();
         for (int i = lane * 4; i < BN; i += 128) {
           const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n_tile * BN + i));
@@ -512,8 +560,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // interleaving them with the stores would serialise one load-compute-store chain per 16-byte unit).
         const uint32_t sb = sb_addr + grp * 32 * 4;
         float4 bi[8];
+        if (!p.bias_block) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bi[j] = lds_f4(sb + j * 16);
+          for (int j = 0; j < 8; ++j) bi[j] = lds_f4(sb + j * 16);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bi[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         uint4 rv[kUnits];
         if (has_res) {
           const uint32_t rbuf = res_addr + rb * chunk_bytes + row_off;

@@ -143,14 +143,26 @@ __global__ void __launch_bounds__(1024) k_quantile(SemMapCfg c, const float* __r
         if (bin != 0xffffffffu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<uint32_t>(__popc(peers)));
       }
       __syncthreads();
-      if (tid == 0) {
-        uint32_t k = s_k, b = 0;
-        for (; b < 256; ++b) {
-          if (k < hist[b]) break;
-          k -= hist[b];
+      if (tid < 32) {
+        // warp-parallel search of the bin that holds rank s_k: lane l owns bins [8l, 8l + 8)
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = hist[tid * 8 + j], sum += c[j];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += y;
         }
-        s_k = k;
-        s_prefix = prefix | (b << shift);
+        const uint32_t before = incl - sum, k = s_k;
+        __syncwarp();
+        if (k >= before && k < incl) {
+          uint32_t kk = k - before;
+          int j = 0;
+          while (kk >= c[j]) kk -= c[j], ++j;
+          s_k = kk;
+          s_prefix = prefix | (static_cast<uint32_t>(tid * 8 + j) << shift);
+        }
       }
       __syncthreads();
     }
@@ -357,6 +369,8 @@ __global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, cons
   extern __shared__ uint32_t keys[];
   __shared__ float red_all[kF], red_agent[kF];
   __shared__ uint32_t raw[128];
+  // small columns: per-entry lateral weight, both z weights and the feature vector, staged by one thread per entry
+  __shared__ float e_wxy[128], e_wz0[128], e_wz1[128], e_feat[128][kF];
   __shared__ uint32_t zbits[4];  // z cells (0 .. nz, biased) that occur in the column's keys
   const int e = blockIdx.y;
   const int ncols = c.vr * c.vr;
@@ -388,6 +402,24 @@ __global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, cons
       for (int j = 0; j < n; ++j) rank += raw[j] < k ? 1 : 0;
       keys[rank] = k;
       atomicOr(&zbits[(k >> 20) & 3u], 1u << ((k >> 15) & 31u));  // z cell (7 bits at 15..21) seen in this column
+      // this entry's weights and features, once, in parallel over the column's entries (the voxel threads below would
+      // otherwise each walk a chain of dependent global loads per entry)
+      const float* cxp = coords + static_cast<size_t>(e) * 3 * N;
+      const float* featp = obs + (static_cast<size_t>(e) * c.channels + 4) * N;
+      const int i = static_cast<int>(k & 0x7fffu);
+      const int ixy = static_cast<int>(k >> 22);
+      int pp;
+      float wx, wy, wz0, wz1;
+      bool ss;
+      corner(cxp[i], c.vr_f, ixy >> 1, pp, wx, ss);
+      corner(cxp[N + i], c.vr_f, ixy & 1, pp, wy, ss);
+      const float zc = cxp[2 * N + i];
+      corner(zc, c.nz_f, 0, pp, wz0, ss);
+      corner(zc, c.nz_f, 1, pp, wz1, ss);
+      e_wxy[rank] = (1.f * wx) * wy;
+      e_wz0[rank] = wz0, e_wz1[rank] = wz1;
+#pragma unroll
+      for (int f = 1; f < kF; ++f) e_feat[rank][f] = (f < c.nf) ? featp[static_cast<size_t>(f - 1) * N + i] : 0.f;
     }
     __syncthreads();
   } else {
@@ -434,6 +466,16 @@ __global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, cons
         const uint32_t kbase = (static_cast<uint32_t>(ixy) << 22) | (static_cast<uint32_t>(z - iz + 1) << 15);
         const int lo = lower_bound_key(keys, n, kbase);
         const int hi = lower_bound_key(keys, n, kbase + (1u << 15));
+        if (n <= 128) {  // staged column: everything is in shared memory
+          for (int t = lo; t < hi; ++t) {
+            const float w = e_wxy[t] * (iz ? e_wz1[t] : e_wz0[t]);
+            acc[0] = acc[0] + 1.f * w;
+#pragma unroll
+            for (int f = 1; f < kF; ++f) {
+              if (f < nf) acc[f] = acc[f] + e_feat[t][f] * w;
+            }
+          }
+        } else
         // two entries in flight (their coordinate and feature loads are independent of the running sums); the adds
         // stay in entry order, as the reference's index_add does
         for (int t0 = lo; t0 < hi; t0 += 2) {
@@ -601,13 +643,22 @@ __global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restri
   const size_t pix = static_cast<size_t>(y) * n + x;
   const float* ml = maps_last + static_cast<size_t>(e) * ml_env + static_cast<size_t>(y) * ml_row + x;
   float* mo = map_out + static_cast<size_t>(e) * c.channels * plane + pix;
-  for (int ch = 0; ch < c.channels; ++ch) {
-    float v = 0.f;
-    if (ntaps > 0 && ch != 2 && ch != 3) {
-      const float* src = ego_e + static_cast<size_t>(ch < 2 ? ch : ch - 2) * ncols;
-      for (int k = 0; k < ntaps; ++k) v += src[tap_idx[k]] * tap_w[k];
+  // the map is streamed once (read maps_last, write map_out): keep eight channel loads in flight per thread
+  for (int ch0 = 0; ch0 < c.channels; ch0 += 8) {
+    float last[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) last[u] = (ch0 + u < c.channels) ? __ldg(ml + (ch0 + u) * ml_plane) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ch = ch0 + u;
+      if (ch >= c.channels) break;
+      float v = 0.f;
+      if (ntaps > 0 && ch != 2 && ch != 3) {
+        const float* src = ego_e + static_cast<size_t>(ch < 2 ? ch : ch - 2) * ncols;
+        for (int k = 0; k < ntaps; ++k) v += src[tap_idx[k]] * tap_w[k];
+      }
+      mo[ch * plane] = fmaxf(last[u], v);
     }
-    mo[ch * plane] = fmaxf(__ldg(ml + ch * ml_plane), v);
   }
 }
 

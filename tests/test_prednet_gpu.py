@@ -131,3 +131,14 @@ def test_tf32_vs_reference_golden(path):
     decided = (top2[1] - top2[0]) > 2 * tol
     assert decided.mean() > 0.5
     assert np.array_equal(got.argmax(0)[decided], ref.argmax(0)[decided])
+
+
+def test_tf32_reference_shape_720(weights, oracle_model):
+    """The reference's own geometry (14 x 720 x 720, nav/arguments.py:40,74): tf32 path vs the fp32 oracle."""
+    x = oracle.synth_partial_map(14, 720, 720, seed=21)
+    seg = _segmentor(weights, "tf32")
+    got = prediction.run_inference(seg, x)[0]
+    ref = oracle.run_inference(oracle_model, x)[0]
+    rng = float(np.abs(ref).max())
+    assert got.shape == (6, 720, 720)
+    assert float(np.abs(got - ref).max()) <= 5e-3 * rng

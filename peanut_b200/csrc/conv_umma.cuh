@@ -149,6 +149,91 @@ __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long m
   }
 }
 
+// Residual of 8 consecutive channels of row m as raw 16-byte registers (bf16: r0 only; fp32: r0, r1).
+template <typename T>
+__device__ __forceinline__ void load_residual8(const ConvParams& p, long long m, int n0, uint4& r0, uint4& r1) {
+  const T* rp = reinterpret_cast<const T*>(p.residual) + m * p.ldr + n0;
+  r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+  if constexpr (sizeof(T) == 4) r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+}
+// y (acc + bias) + residual registers -> ReLU -> store, 8 channels of row m.
+template <typename T>
+__device__ __forceinline__ void finish_store8(const ConvParams& p, long long m, int n0, float* y, bool has_res, const uint4& r0,
+                                              const uint4& r1) {
+  if (has_res) {
+    if constexpr (sizeof(T) == 2) {
+      const uint32_t w[4] = {r0.x, r0.y, r0.z, r0.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        y[2 * e] += __uint_as_float(w[e] << 16);
+        y[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+      }
+    } else {
+      y[0] += __uint_as_float(r0.x), y[1] += __uint_as_float(r0.y), y[2] += __uint_as_float(r0.z), y[3] += __uint_as_float(r0.w);
+      y[4] += __uint_as_float(r1.x), y[5] += __uint_as_float(r1.y), y[6] += __uint_as_float(r1.z), y[7] += __uint_as_float(r1.w);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+  }
+  if (sizeof(T) == 2 && !p.out_fp32) {
+    uint4 o;
+    o.x = pack_bf16(y[0], y[1]), o.y = pack_bf16(y[2], y[3]), o.z = pack_bf16(y[4], y[5]), o.w = pack_bf16(y[6], y[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0) = o;
+  } else {
+    if (p.round_tf32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = round_tf32(y[j]);
+    }
+    float* op = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
+    *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
+// Split-K tail of CTA `rank`: sum column slice `rank` of every CTA's parked partial tile over distributed shared memory
+// (fixed order: split 0, 1, ...), add bias / residual, ReLU, store.  8 columns per step with the distributed-smem loads
+// of all splits, the bias and the NEXT step's residual in flight together.
+template <typename T, int BN, int kSplits>
+__device__ __forceinline__ void splitk_reduce(const ConvParams& p, uint32_t part0, int rank, long long m, int row, int n_tile) {
+  constexpr int kCols = BN / kSplits;  // columns this rank finishes (multiple of 8)
+  uint32_t peer[kSplits];
+#pragma unroll
+  for (int s0 = 0; s0 < kSplits; ++s0) peer[s0] = map_shared_rank(part0, s0);
+  const bool has_res = p.residual != nullptr;
+  const int c_begin = rank * kCols;
+  uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+  if (has_res && n_tile * BN + c_begin < p.cout_store) load_residual8<T>(p, m, n_tile * BN + c_begin, r0, r1);
+#pragma unroll 1
+  for (int c = c_begin; c < c_begin + kCols; c += 8) {
+    const int n0 = n_tile * BN + c;
+    if (n0 >= p.cout_store) break;
+    const uint32_t off = static_cast<uint32_t>(((c >> 2) * kBlockM + row) * 16);
+    float4 lo[kSplits], hi[kSplits];
+#pragma unroll
+    for (int s0 = 0; s0 < kSplits; ++s0) {
+      lo[s0] = ld_dsmem_v4(peer[s0] + off);
+      hi[s0] = ld_dsmem_v4(peer[s0] + off + kBlockM * 16);
+    }
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 1);
+    uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;  // residual of the next step
+    const bool more = (c + 8 < c_begin + kCols) && (n0 + 8 < p.cout_store);
+    if (has_res && more) load_residual8<T>(p, m, n0 + 8, q0, q1);
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s0 = 0; s0 < kSplits; ++s0) {
+      y[0] += lo[s0].x, y[1] += lo[s0].y, y[2] += lo[s0].z, y[3] += lo[s0].w;
+      y[4] += hi[s0].x, y[5] += hi[s0].y, y[6] += hi[s0].z, y[7] += hi[s0].w;
+    }
+    y[0] += b0.x, y[1] += b0.y, y[2] += b0.z, y[3] += b0.w;
+    y[4] += b1.x, y[5] += b1.y, y[6] += b1.z, y[7] += b1.w;
+    finish_store8<T>(p, m, n0, y, has_res, r0, r1);
+    r0 = q0, r1 = q1;
+  }
+}
+
 // "accumulator stage drained": local barrier, or - in a CTA pair - the leader's barrier (it gates the leader's MMA issue)
 template <bool kPair>
 __device__ __forceinline__ void arrive_tempty(uint64_t* bar, uint32_t cta_rank) {
@@ -685,17 +770,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       if constexpr (kSplit) {
         // park the partial tile in the (now idle) operand ring: 16-byte unit (column group g, row) at (g*128 + row)*16
-        float4* part = reinterpret_cast<float4*>(smem_a);
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + chunk * 32, v);
-          tmem_ld_wait();
+        const uint32_t part_addr = smem_u32(smem_a) + (quarter * 32 + lane) * 16;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+        auto park = [&](const uint32_t (&v)[32], int chunk) {
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            part[(chunk * 8 + g) * kBlockM + quarter * 32 + lane] =
-                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
-                            __uint_as_float(v[g * 4 + 3]));
+            sts_v4(part_addr + (chunk * 8 + g) * (kBlockM * 16), v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        };
+        uint32_t va[32], vb[32];  // one 32-column load in flight while the previous one is written out
+        tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; chunk += 2) {
+          tmem_ld_wait();
+          if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, vb);
+          park(va, chunk);
+          if (chunk + 1 < BN / 32) {
+            tmem_ld_wait();
+            if (chunk + 2 < BN / 32) tmem_ld_32x32(taddr + (chunk + 2) * 32, va);
+            park(vb, chunk + 1);
+          }
         }
         // the tile is finished after the cluster barrier below
       } else {
@@ -735,29 +828,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int n_tile = tile - m_tile * p.n_tiles;
         const int row = warp * 32 + lane;
         const long long m = static_cast<long long>(m_tile) * kBlockM + row;
-        const int cols_per_rank = BN / p.splits;
         const uint32_t part0 = smem_u32(smem_a);
         if (m < p.M) {
-  #pragma unroll 1
-          for (int c = rank * cols_per_rank; c < (rank + 1) * cols_per_rank; c += 8) {
-            const int n0 = n_tile * BN + c;
-            if (n0 >= p.cout_store) break;
-            float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const uint32_t off = static_cast<uint32_t>(((c >> 2) * kBlockM + row) * 16);
-  #pragma unroll 1
-            for (int s0 = 0; s0 < p.splits; s0 += 2) {  // fixed summation order: split 0, 1, 2, ...
-              const uint32_t ra = map_shared_rank(part0, s0) + off;
-              const uint32_t rb = map_shared_rank(part0, s0 + 1) + off;
-              const float4 a0 = ld_dsmem_v4(ra), a1 = ld_dsmem_v4(ra + kBlockM * 16);
-              const float4 b0 = ld_dsmem_v4(rb), b1 = ld_dsmem_v4(rb + kBlockM * 16);
-              y[0] += a0.x, y[1] += a0.y, y[2] += a0.z, y[3] += a0.w;
-              y[4] += a1.x, y[5] += a1.y, y[6] += a1.z, y[7] += a1.w;
-              y[0] += b0.x, y[1] += b0.y, y[2] += b0.z, y[3] += b0.w;
-              y[4] += b1.x, y[5] += b1.y, y[6] += b1.z, y[7] += b1.w;
-            }
-  #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = y[j] + __ldg(p.bias + n0 + j);
-            epilogue_store8<T>(p, m, n0, y);
+          switch (p.splits) {
+            case 2: splitk_reduce<T, BN, 2>(p, part0, rank, m, row, n_tile); break;
+            case 4: splitk_reduce<T, BN, 4>(p, part0, rank, m, row, n_tile); break;
+            default:
+              if constexpr (BN >= 64) splitk_reduce<T, BN, 8>(p, part0, rank, m, row, n_tile);
+              break;
           }
         }
       }

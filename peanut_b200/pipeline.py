@@ -54,6 +54,7 @@ class PerceptionPipeline:
         self.pred_out = torch.zeros((E, num_pred_classes) + self.map_shape[1:], dtype=torch.float32, device=d)
         self._side = torch.cuda.Stream(device=d)
         self._fork, self._join, self._join_d2h = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self._depth_ev, self._h2d_fence, self._depth_ready = torch.cuda.Event(), torch.cuda.Event(), None
         # staging for the host entry point
         self._dev_in = None
         self._host_out = None
@@ -75,12 +76,15 @@ class PerceptionPipeline:
         # mapper (at small E every layer is a single wave of CTAs that leaves room for a second resident CTA per SM).
         main = torch.cuda.current_stream(self.device)
         self._fork.record(main)
+        # the critical chain is enqueued first; the side stream's work follows a few microseconds of host time later
+        self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
         with torch.cuda.stream(self._side):
             self._side.wait_event(self._fork)
             pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
             self._join.record(self._side)
         partial_map.record_stream(self._side)
-        self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
+        if self._depth_ready is not None:  # step_host copies depth / pose delta beside Mask-RCNN
+            main.wait_event(self._depth_ready)
         stream = main.cuda_stream
         lib = self.seg.ctx.lib
         _lib.check(lib.pn_make_obs(self.seg.ctx.handle, depth.data_ptr(), rgb.data_ptr(), self.sem.data_ptr(), self.E,
@@ -103,15 +107,24 @@ class PerceptionPipeline:
             self._host_out = (torch.empty(self.pred_out.shape, dtype=torch.float32).pin_memory(),
                               torch.empty((self.E, 3), dtype=torch.float32).pin_memory(),
                               torch.empty((self.E, self.args.vision_range, self.args.vision_range), dtype=torch.float32).pin_memory())
-        # the partial map (the largest input) is only read by the map-completion net, which runs on the side stream:
-        # its copy goes there too and overlaps Mask-RCNN instead of delaying it
-        for dst, src in zip(self._dev_in[:3], (rgb_h, depth_h, pose_delta_h)):
-            dst.copy_(src, non_blocking=True)
+        # Only the frame gates Mask-RCNN.  Depth and the pose delta (needed after it, by the glue and the mapper) and the
+        # partial map (the largest input, read only by the map-completion net on the side stream) are copied on the side
+        # stream, beside Mask-RCNN instead of ahead of it.
+        self._dev_in[0].copy_(rgb_h, non_blocking=True)
+        main = torch.cuda.current_stream(d)
+        self._h2d_fence.record(main)   # earlier work on the caller's stream (e.g. the previous step) precedes the copies
         with torch.cuda.stream(self._side):
+            self._side.wait_event(self._h2d_fence)
+            self._dev_in[1].copy_(depth_h, non_blocking=True)
+            self._dev_in[2].copy_(pose_delta_h, non_blocking=True)
+            self._depth_ev.record(self._side)
             self._dev_in[3].copy_(partial_map_h, non_blocking=True)
         rgb, depth, delta, pmap = self._dev_in
-        _, fp, new_map, poses, pred = self.step_device(rgb, depth, delta, local_map, poses, pmap)
-        main = torch.cuda.current_stream(d)
+        self._depth_ready = self._depth_ev
+        try:
+            _, fp, new_map, poses, pred = self.step_device(rgb, depth, delta, local_map, poses, pmap)
+        finally:
+            self._depth_ready = None
         with torch.cuda.stream(self._side):  # the predicted map leaves on the side stream as soon as it exists
             self._host_out[0].copy_(pred, non_blocking=True)
             self._join_d2h.record(self._side)

@@ -286,3 +286,23 @@ def test_batch_equals_single(weights):
         agree = float((one[0] == both[i]).float().mean())
         assert agree >= 0.85, f"frame {i}: batch-1 and batch-2 engines agree on {agree:.4f} of the category-mask cells"
     assert both.sum() > 0
+
+
+def test_no_detections_and_blank_frame(weights):
+    """Edge cases of the device-side control flow: an unreachable score threshold leaves zero detections (the mask head's
+    live-row count is 0, every tile is skipped) and the category stack is all zeros; a blank frame runs through the same
+    launch list without NaNs; the engine then still produces the normal result for a normal frame (no stale state)."""
+    e = _engine(weights, "bf16", batch=2)
+    frames = np.stack([O.synth_rgb(s, H, W) for s in (5, 6)])
+    normal = e.forward_device(torch.from_numpy(frames).cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR).clone()
+    assert normal.sum() > 0
+    none = e.forward_device(torch.from_numpy(frames).cuda(), score_thresh=2.0, sem_pred_prob_thr=2.0, goal_thr=2.0).clone()
+    torch.cuda.synchronize()
+    assert float(none.abs().sum()) == 0.0
+    assert e.read_tap("det_count", (2,), torch.int32).cpu().tolist() == [0, 0]
+    blank = np.zeros_like(frames)
+    blank[1] = 255
+    out = e.forward_device(torch.from_numpy(blank).cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR).clone()
+    assert torch.isfinite(out).all() and float(out.min()) >= 0.0
+    again = e.forward_device(torch.from_numpy(frames).cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR)
+    assert torch.equal(again, normal)

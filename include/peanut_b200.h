@@ -121,6 +121,15 @@ int pn_maskrcnn_tap(pn_ctx* ctx, const char* name, int write, int channels, void
  * coeffs_out [out_size][*ksize_out] 22-bit fixed point; *ksize_out: in = row width of coeffs_out, out = taps. */
 int pn_pil_bilinear_coeffs(int in_size, int out_size, int* bounds_out, int* coeffs_out, int* ksize_out);
 
+/* ---- Glue after stage C: the tail of Agent_State.update_prediction
+ * (nav/agent/agent_state.py:357-372).  pred [num_classes, window, window] = stage C output for the prediction window whose
+ * origin in the full map is (x1, y1) ((0, 0) when the window is the full map); the goal category's plane is embedded into
+ * a zero canvas, cut to the local-map bounds rows [r0, r0+local_w) x columns [c0, c0+local_h), and cells whose explored
+ * value (local_map[1], row stride in elements) is >= 0.5 are zeroed.  target_out [local_w, local_h] fp32. */
+int pn_target_pred(pn_ctx* ctx, const float* pred_dev, int num_classes, int window, int x1, int y1, int goal_cat, int r0,
+                   int c0, int local_w, int local_h, const float* explored_dev, int64_t explored_row_stride,
+                   float* target_out_dev, void* stream);
+
 /* ---- Glue between stages A and B: Agent_Helper._preprocess_obs / _preprocess_depth
  * (nav/agent/agent_helper.py:175-217).  depth [E,H,W] fp32 as the simulator emits it (0 = invalid, 1 = max range),
  * rgb [E,H,W,3] uint8 (may be NULL: channels 0-2 are unused by the mapper), sem [E,H,W,num_sem] fp32 (stage A output)

@@ -563,6 +563,21 @@ int pn_make_obs(pn_ctx* ctx, const float* depth_dev, const uint8_t* rgb_dev, con
   PN_API_END
 }
 
+int pn_target_pred(pn_ctx* ctx, const float* pred_dev, int num_classes, int window, int x1, int y1, int goal_cat, int r0,
+                   int c0, int local_w, int local_h, const float* explored_dev, int64_t explored_row_stride,
+                   float* target_out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(pred_dev && explored_dev && target_out_dev, "pn_target_pred: null buffer");
+  PN_REQUIRE(goal_cat >= 0 && goal_cat < num_classes, "pn_target_pred: goal category out of range");
+  PN_REQUIRE(window > 0 && local_w > 0 && local_h > 0 && explored_row_stride >= local_h, "pn_target_pred: bad geometry");
+  launch_target_pred(pred_dev, window, x1, y1, goal_cat, r0, c0, local_w, local_h, explored_dev, explored_row_stride,
+                     target_out_dev, static_cast<cudaStream_t>(stream));
+  PN_CUDA_CHECK(cudaGetLastError());
+  PN_API_END
+}
+
 int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,
               const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
               int stride, int dil, int pad, int relu, int force_bn, float* y_dev) {

@@ -95,6 +95,8 @@ void resized_shape(int h, int w, int min_size, int max_size, int& newh, int& new
 void pil_bilinear_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk, int& ksize);
 void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
                           uint8_t* resized_u8, const float mean_bgr[3], const float std_bgr[3]);
+void launch_target_pred(const float* pred, int win, int x1, int y1, int goal_cat, int r0, int c0, int lw, int lh,
+                        const float* explored, long long explored_row_stride, float* out, cudaStream_t s);
 void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, int E, int H, int W, int ds, int h, int w,
                      int nsem, float min_d, float max_d, float* obs, cudaStream_t s);
 

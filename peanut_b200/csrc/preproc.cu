@@ -230,4 +230,29 @@ void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, i
   launch_pdl(k_make_obs, blocks, threads, 0, s, depth, rgb, sem, E, H, W, ds, h, w, nsem, min_d, max_d, obs);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Glue after stage C: Agent_State.update_prediction (nav/agent/agent_state.py:357-372).  The predicted maps cover the
+// prediction window [x1, x1+win) x [y1, y1+win) of the full map; the reference embeds them into a full-size zero canvas,
+// cuts the goal category's plane to the local-map bounds and keeps unexplored cells only.  One thread per local cell.
+__global__ void k_target_pred(const float* __restrict__ pred, int win, int x1, int y1, int goal_cat, int r0, int c0,
+                              int lw, int lh, const float* __restrict__ explored, long long explored_row_stride,
+                              float* __restrict__ out) {
+  pdl_grid_sync();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= lw * lh) return;
+  const int r = idx / lh, c = idx - r * lh;
+  const int pr = r0 + r - x1, pc = c0 + c - y1;  // position inside the prediction window
+  float v = 0.f;
+  if (pr >= 0 && pr < win && pc >= 0 && pc < win) v = pred[(static_cast<size_t>(goal_cat) * win + pr) * win + pc];
+  out[idx] = (explored[static_cast<size_t>(r) * explored_row_stride + c] < 0.5f) ? v : 0.f * v;  // x * False keeps the sign of zero / NaN
+}
+
+void launch_target_pred(const float* pred, int win, int x1, int y1, int goal_cat, int r0, int c0, int lw, int lh,
+                        const float* explored, long long explored_row_stride, float* out, cudaStream_t s) {
+  const int n = lw * lh;
+  launch_pdl(k_target_pred, (n + 255) / 256, 256, 0, s, pred, win, x1, y1, goal_cat, r0, c0, lw, lh, explored,
+             explored_row_stride, out);
+}
+
 }  // namespace pn

@@ -130,6 +130,46 @@ int pn_target_pred(pn_ctx* ctx, const float* pred_dev, int num_classes, int wind
                    int c0, int local_w, int local_h, const float* explored_dev, int64_t explored_row_stride,
                    float* target_out_dev, void* stream);
 
+/* ---- Map bookkeeping, batched over E environments with every field in DEVICE memory:
+ * Agent_State.get_local_map_boundaries / init_map_and_pose / init_with_obs (stamp) / update_local_map (after the mapper
+ * call) / update_full_map, nav/agent/agent_state.py:153-211, 116-122, 276-303, 308-338.  The reference derives every cell
+ * index on the host (pose `.cpu().numpy()` at :276, :315, :335); here nothing synchronises. */
+typedef struct pn_map_cfg {
+  int num_channels;        /* nc = 4 + num_sem_categories           agent_state.py:39 */
+  int full_w, full_h;      /* map_size_cm / map_resolution          :41-42 */
+  int local_w, local_h;    /* full / global_downscaling             :43-44 */
+  int map_resolution;      /* 5 (cm per cell) */
+  int map_size_cm;         /* 4800 */
+  int global_downscaling;  /* 2 */
+  int grid_resolution;     /* 24   arguments.py:95 */
+  int col_rad;             /* 4    arguments.py:86 (integer-valued); the explored disk has radius col_rad + 1 */
+  float goal_reached_dist; /* 75   arguments.py:102 */
+  int f64_cells;           /* 0: int(r * 100.0 / res) in float32 (numpy >= 2 scalar rules), 1: in float64 (numpy < 2) */
+} pn_map_cfg;
+
+typedef struct pn_map_arrays {
+  float* full_map;             /* [E, nc, full_w, full_h] */
+  float* local_map;            /* [E, nc, local_w, local_h]  (the mapper's map_out) */
+  float* full_pose;            /* [E, 3] x m, y m, theta deg */
+  float* local_pose;           /* [E, 3]  (the mapper's poses_inout) */
+  double* origins;             /* [E, 3] */
+  int* lmb;                    /* [E, 4] local-map bounds: row0, row1, col0, col1 */
+  double* planner_pose_inputs; /* [E, 7] */
+  int* loc;                    /* [E, 2] loc_r, loc_c */
+  double* dist_to_goal;        /* [E] */
+  const int* global_goal;      /* [E, 2] global_goals[0] (read by update_local) */
+} pn_map_arrays;
+
+/* init_map_and_pose (:180-211): zero full_map, pose = map centre, 3x3 stamp, first window, local map and pose. */
+int pn_map_init(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream);
+/* init_with_obs (:116-122): 3x3 stamp on local_map[2:4] at the cell of local_pose (after the first mapper call). */
+int pn_map_stamp_initial(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream);
+/* update_local_map after the mapper call (:276-303): planner pose, channel-2 reset, 5x5 trajectory stamp, explored disk
+ * under the agent and (once dist_to_goal < goal_reached_dist) at the goal; writes loc and dist_to_goal. */
+int pn_map_update_local(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream);
+/* update_full_map (:308-338): window written back, window recentred on the agent, local map and pose re-cut. */
+int pn_map_update_full(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream);
+
 /* ---- Glue between stages A and B: Agent_Helper._preprocess_obs / _preprocess_depth
  * (nav/agent/agent_helper.py:175-217).  depth [E,H,W] fp32 as the simulator emits it (0 = invalid, 1 = max range),
  * rgb [E,H,W,3] uint8 (may be NULL: channels 0-2 are unused by the mapper), sem [E,H,W,num_sem] fp32 (stage A output)

@@ -53,6 +53,10 @@ PROTOTYPES = {
                     [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "pn_target_pred": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 9 +
                        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_map_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_map_stamp_initial": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_map_update_local": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_map_update_full": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_semmap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
     "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),
@@ -71,6 +75,20 @@ class SemMapCfg(ctypes.Structure):
                 ("du_scale", ctypes.c_int), ("num_sem_categories", ctypes.c_int), ("hfov", ctypes.c_float),
                 ("camera_height", ctypes.c_float), ("cat_pred_threshold", ctypes.c_float),
                 ("exp_pred_threshold", ctypes.c_float), ("map_pred_threshold", ctypes.c_float)]
+
+
+class MapCfg(ctypes.Structure):
+    """struct pn_map_cfg"""
+    _fields_ = [("num_channels", ctypes.c_int), ("full_w", ctypes.c_int), ("full_h", ctypes.c_int), ("local_w", ctypes.c_int),
+                ("local_h", ctypes.c_int), ("map_resolution", ctypes.c_int), ("map_size_cm", ctypes.c_int),
+                ("global_downscaling", ctypes.c_int), ("grid_resolution", ctypes.c_int), ("col_rad", ctypes.c_int),
+                ("goal_reached_dist", ctypes.c_float), ("f64_cells", ctypes.c_int)]
+
+
+class MapArrays(ctypes.Structure):
+    """struct pn_map_arrays (device pointers)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("full_map", "local_map", "full_pose", "local_pose", "origins", "lmb",
+                                               "planner_pose_inputs", "loc", "dist_to_goal", "global_goal")]
 
 
 class MaskRcnnCfg(ctypes.Structure):

@@ -578,6 +578,37 @@ int pn_target_pred(pn_ctx* ctx, const float* pred_dev, int num_classes, int wind
   PN_API_END
 }
 
+namespace {
+int map_call(pn_ctx* ctx, int op, const pn_map_cfg* cfg, const pn_map_arrays* a, int E, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(cfg && a && E > 0, "pn_map_*: null configuration / arrays or no environments");
+  PN_REQUIRE(a->full_map && a->local_map && a->full_pose && a->local_pose && a->origins && a->lmb && a->planner_pose_inputs &&
+                 a->loc && a->dist_to_goal,
+             "pn_map_*: null state array");
+  PN_REQUIRE(op != 2 || a->global_goal, "pn_map_update_local: global_goal is required");
+  PN_REQUIRE(cfg->num_channels >= 4 && cfg->local_w > 0 && cfg->local_h > 0 && cfg->local_w <= cfg->full_w &&
+                 cfg->local_h <= cfg->full_h && cfg->map_resolution > 0 && cfg->grid_resolution > 0 && cfg->col_rad >= 0,
+             "pn_map_*: bad geometry");
+  map_bookkeeping(op, *cfg, *a, E, static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+}  // namespace
+
+int pn_map_init(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream) {
+  return map_call(ctx, 0, cfg, arrays, E, stream);
+}
+int pn_map_stamp_initial(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream) {
+  return map_call(ctx, 1, cfg, arrays, E, stream);
+}
+int pn_map_update_local(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream) {
+  return map_call(ctx, 2, cfg, arrays, E, stream);
+}
+int pn_map_update_full(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream) {
+  return map_call(ctx, 3, cfg, arrays, E, stream);
+}
+
 int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,
               const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
               int stride, int dil, int pad, int relu, int force_bn, float* y_dev) {

@@ -1,0 +1,250 @@
+// Map bookkeeping on the device, batched over environments:
+//   Agent_State.get_local_map_boundaries   nav/agent/agent_state.py:153-177
+//   Agent_State.init_map_and_pose          :180-211
+//   Agent_State.init_with_obs (3x3 stamp)  :116-122
+//   Agent_State.update_local_map (tail)    :276-303
+//   Agent_State.update_full_map            :308-338
+// The reference keeps poses in device tensors but derives every cell index on the host (`.cpu().numpy()` at :276, :315,
+// :335 - three blocking syncs per step and environment) and writes the stamps as tiny indexed tensor ops.  Here all of
+// that state (poses, window bounds, origins, planner pose vector, agent cell, distance to goal) lives in device arrays;
+// one kernel per call does the cell arithmetic and the map writes for all environments, nothing synchronises.
+//
+// These kernels are HBM-bound byte movers (window copies: 2 x nc x local_w x local_h x 4 bytes per environment) or
+// latency-bound scalar updates; compiled with -fmad=false so the pose arithmetic rounds like the reference's separate ops.
+#include "engine.h"
+#include "maskrcnn.h"
+
+namespace pn {
+
+namespace {
+
+struct MapCfg {
+  int nc, full_w, full_h, local_w, local_h;
+  int res, size_cm, gds, grid, col_rad;
+  float goal_dist;
+  int f64_cells;
+};
+
+struct MapArrays {
+  float* full_map;
+  float* local_map;
+  float* full_pose;
+  float* local_pose;
+  double* origins;
+  int* lmb;
+  double* planner;
+  int* loc;
+  double* dist_to_goal;
+  const int* global_goal;
+};
+
+// int(r * 100.0 / map_resolution) with r a numpy float32 scalar: float32 arithmetic under numpy >= 2, float64 before.
+__device__ __forceinline__ int cell_of(float v, const MapCfg& c) {
+  if (c.f64_cells) return static_cast<int>(static_cast<double>(v) * 100.0 / static_cast<double>(c.res));
+  return static_cast<int>(__fdiv_rn(__fmul_rn(v, 100.f), static_cast<float>(c.res)));
+}
+
+// Python slice start:stop on an axis of n elements -> [lo, hi) (possibly empty)
+__device__ __forceinline__ void py_slice(int start, int stop, int n, int& lo, int& hi) {
+  start = start < 0 ? max(start + n, 0) : min(start, n);
+  stop = stop < 0 ? max(stop + n, 0) : min(stop, n);
+  lo = start;
+  hi = max(stop, start);
+}
+
+__device__ __forceinline__ int floor_mod(int a, int m) {
+  const int r = a % m;
+  return r < 0 ? r + m : r;
+}
+
+// get_local_map_boundaries (:153-177)
+__device__ void boundaries(int loc_r, int loc_c, const MapCfg& c, int* lmb) {
+  int gx1, gx2, gy1, gy2;
+  if (c.gds > 1) {
+    gx1 = loc_r - c.local_w / 2, gy1 = loc_c - c.local_h / 2;
+    gx1 -= floor_mod(gx1, c.grid), gy1 -= floor_mod(gy1, c.grid);
+    gx2 = gx1 + c.local_w, gy2 = gy1 + c.local_h;
+    if (gx1 < 0) gx1 = 0, gx2 = c.local_w;
+    if (gx2 > c.full_w) gx1 = c.full_w - c.local_w, gx2 = c.full_w;
+    if (gy1 < 0) gy1 = 0, gy2 = c.local_h;
+    if (gy2 > c.full_h) gy1 = c.full_h - c.local_h, gy2 = c.full_h;
+  } else {
+    gx1 = 0, gx2 = c.full_w, gy1 = 0, gy2 = c.full_h;
+  }
+  lmb[0] = gx1, lmb[1] = gx2, lmb[2] = gy1, lmb[3] = gy2;
+}
+
+// Is (r, c) written by local_map[1][(selem_idx[0] - R + r0, selem_idx[1] - R + c0)] = 1 ?  Negative indices wrap once
+// (Python), indices >= n are an IndexError in the reference and are skipped.
+__device__ __forceinline__ bool in_disk(int r, int c, int r0, int c0, int R, int nr, int ncol) {
+  bool hit = false;
+#pragma unroll
+  for (int wr = 0; wr < 2; ++wr) {
+    const int dr = r - (wr ? nr : 0) - r0;  // index r (wr = 0) or r - nr < 0 (wr = 1)
+    if (dr < -R || dr > R) continue;
+#pragma unroll
+    for (int wc = 0; wc < 2; ++wc) {
+      const int dc = c - (wc ? ncol : 0) - c0;
+      if (dc < -R || dc > R) continue;
+      hit |= (dr * dr + dc * dc <= R * R);
+    }
+  }
+  return hit;
+}
+
+// update_local_map after the mapper call (:276-303).  grid (x, E); every thread derives the agent cell from the pose.
+__global__ void __launch_bounds__(256) k_map_update_local(MapCfg cfg, MapArrays a) {
+  pdl_grid_sync();
+  const int e = blockIdx.y;
+  const float px = a.local_pose[e * 3 + 0], py = a.local_pose[e * 3 + 1];
+  const int loc_r = cell_of(py, cfg), loc_c = cell_of(px, cfg);
+  const int g0 = a.global_goal[e * 2 + 0], g1 = a.global_goal[e * 2 + 1];
+  const long long d2 = static_cast<long long>(loc_r - g0) * (loc_r - g0) + static_cast<long long>(loc_c - g1) * (loc_c - g1);
+  const double dist = sqrt(static_cast<double>(d2)) * static_cast<double>(cfg.res);
+  const bool at_goal = dist < static_cast<double>(cfg.goal_dist);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double* org = a.origins + e * 3;
+    double* pl = a.planner + e * 7;
+    pl[0] = static_cast<double>(px) + org[0];
+    pl[1] = static_cast<double>(py) + org[1];
+    pl[2] = static_cast<double>(a.local_pose[e * 3 + 2]) + org[2];
+    a.loc[e * 2 + 0] = loc_r, a.loc[e * 2 + 1] = loc_c;
+    a.dist_to_goal[e] = dist;
+  }
+  int rlo, rhi, clo, chi;
+  py_slice(loc_r - 2, loc_r + 3, cfg.local_w, rlo, rhi);
+  py_slice(loc_c - 2, loc_c + 3, cfg.local_h, clo, chi);
+  const int R = cfg.col_rad + 1;
+  const size_t plane = static_cast<size_t>(cfg.local_w) * cfg.local_h;
+  float* lm = a.local_map + static_cast<size_t>(e) * cfg.nc * plane;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < plane; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cfg.local_h), c = static_cast<int>(i - static_cast<size_t>(r) * cfg.local_h);
+    const bool traj = r >= rlo && r < rhi && c >= clo && c < chi;
+    lm[2 * plane + i] = traj ? 1.f : 0.f;  // channel 2 reset, then the 5x5 stamp
+    if (traj) lm[3 * plane + i] = 1.f;
+    if (in_disk(r, c, loc_r, loc_c, R, cfg.local_w, cfg.local_h) || (at_goal && in_disk(r, c, g0, g1, R, cfg.local_w, cfg.local_h)))
+      lm[1 * plane + i] = 1.f;
+  }
+}
+
+// init_with_obs (:116-122): 3x3 stamp on local_map[2:4] at the cell of the local pose.  One block per environment.
+__global__ void k_map_stamp_initial(MapCfg cfg, MapArrays a) {
+  pdl_grid_sync();
+  const int e = blockIdx.x;
+  const int loc_r = cell_of(a.local_pose[e * 3 + 1], cfg), loc_c = cell_of(a.local_pose[e * 3 + 0], cfg);
+  int rlo, rhi, clo, chi;
+  py_slice(loc_r - 1, loc_r + 2, cfg.local_w, rlo, rhi);
+  py_slice(loc_c - 1, loc_c + 2, cfg.local_h, clo, chi);
+  const size_t plane = static_cast<size_t>(cfg.local_w) * cfg.local_h;
+  float* lm = a.local_map + static_cast<size_t>(e) * cfg.nc * plane;
+  const int t = threadIdx.x;  // 18 = 2 channels x 3 x 3
+  if (t < 18) {
+    const int ch = 2 + t / 9, r = rlo + (t % 9) / 3, c = clo + t % 3;
+    if (r < rhi && c < chi) lm[ch * plane + static_cast<size_t>(r) * cfg.local_h + c] = 1.f;
+  }
+}
+
+// Window copy between full_map[:, lmb0:lmb1, lmb2:lmb3] and local_map.  grid (x, nc, E); kToFull: local -> full.
+template <bool kToFull, typename V>
+__global__ void __launch_bounds__(256) k_map_window(MapCfg cfg, MapArrays a) {
+  pdl_grid_sync();
+  constexpr int kVec = sizeof(V) / 4;
+  const int e = blockIdx.z, ch = blockIdx.y;
+  const int r0 = a.lmb[e * 4 + 0], c0 = a.lmb[e * 4 + 2];
+  const int wv = cfg.local_h / kVec;
+  const size_t n = static_cast<size_t>(cfg.local_w) * wv;
+  float* full = a.full_map + (static_cast<size_t>(e) * cfg.nc + ch) * cfg.full_w * cfg.full_h;
+  float* local = a.local_map + (static_cast<size_t>(e) * cfg.nc + ch) * cfg.local_w * cfg.local_h;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / wv), c = static_cast<int>(i - static_cast<size_t>(r) * wv) * kVec;
+    V* pf = reinterpret_cast<V*>(full + static_cast<size_t>(r0 + r) * cfg.full_h + c0 + c);
+    V* pl = reinterpret_cast<V*>(local + static_cast<size_t>(r) * cfg.local_h + c);
+    if (kToFull) *pf = *pl;
+    else *pl = *pf;
+  }
+}
+
+// Pose / window update, one thread per environment.  mode 0: update_full_map :311-338 (full pose from the local pose, new
+// window, new local pose, agent cell); mode 1: init_map_and_pose :186-211 (pose = map centre, 3x3 stamp on full_map[2:4]).
+__global__ void k_map_recentre(MapCfg cfg, MapArrays a, int E, int mode) {
+  pdl_grid_sync();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float* fp = a.full_pose + e * 3;
+  float* lp = a.local_pose + e * 3;
+  double* org = a.origins + e * 3;
+  double* pl = a.planner + e * 7;
+  if (mode == 1) {
+    const float centre = static_cast<float>(static_cast<double>(cfg.size_cm) / 100.0 / 2.0);
+    fp[0] = centre, fp[1] = centre, fp[2] = 0.f;
+    pl[0] = centre, pl[1] = centre, pl[2] = 0.0;
+  } else {
+    for (int i = 0; i < 3; ++i) fp[i] = __fadd_rn(lp[i], static_cast<float>(org[i]));
+  }
+  const int loc_r = cell_of(fp[1], cfg), loc_c = cell_of(fp[0], cfg);
+  if (mode == 1) {
+    int rlo, rhi, clo, chi;
+    py_slice(loc_r - 1, loc_r + 2, cfg.full_w, rlo, rhi);
+    py_slice(loc_c - 1, loc_c + 2, cfg.full_h, clo, chi);
+    const size_t plane = static_cast<size_t>(cfg.full_w) * cfg.full_h;
+    float* fm = a.full_map + static_cast<size_t>(e) * cfg.nc * plane;
+    for (int ch = 2; ch < 4; ++ch)
+      for (int r = rlo; r < rhi; ++r)
+        for (int c = clo; c < chi; ++c) fm[ch * plane + static_cast<size_t>(r) * cfg.full_h + c] = 1.f;
+  }
+  int* lmb = a.lmb + e * 4;
+  boundaries(loc_r, loc_c, cfg, lmb);
+  for (int i = 0; i < 4; ++i) pl[3 + i] = static_cast<double>(lmb[i]);
+  org[0] = static_cast<double>(lmb[2] * cfg.res) / 100.0;
+  org[1] = static_cast<double>(lmb[0] * cfg.res) / 100.0;
+  org[2] = 0.0;
+  for (int i = 0; i < 3; ++i) lp[i] = __fsub_rn(fp[i], static_cast<float>(org[i]));
+  if (mode == 0) {
+    a.loc[e * 2 + 0] = cell_of(lp[1], cfg);
+    a.loc[e * 2 + 1] = cell_of(lp[0], cfg);
+  }
+}
+
+template <bool kToFull>
+void launch_window(const MapCfg& cfg, const MapArrays& a, int E, cudaStream_t s) {
+  const bool vec = cfg.local_h % 4 == 0 && cfg.full_h % 4 == 0 && cfg.grid % 4 == 0 && (cfg.full_h - cfg.local_h) % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.full_map) | reinterpret_cast<uintptr_t>(a.local_map)) % 16 == 0;
+  const size_t n = static_cast<size_t>(cfg.local_w) * cfg.local_h / (vec ? 4 : 1);
+  const dim3 grid(static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 64)), cfg.nc, E);
+  if (vec) launch_pdl(k_map_window<kToFull, float4>, grid, dim3(256), 0, s, cfg, a);
+  else launch_pdl(k_map_window<kToFull, float>, grid, dim3(256), 0, s, cfg, a);
+}
+
+}  // namespace
+
+void map_bookkeeping(int op, const pn_map_cfg& c, const pn_map_arrays& arr, int E, cudaStream_t s) {
+  MapCfg cfg{c.num_channels, c.full_w, c.full_h, c.local_w, c.local_h, c.map_resolution, c.map_size_cm, c.global_downscaling,
+             c.grid_resolution, c.col_rad, c.goal_reached_dist, c.f64_cells};
+  MapArrays a{arr.full_map, arr.local_map, arr.full_pose, arr.local_pose, arr.origins, arr.lmb, arr.planner_pose_inputs,
+              arr.loc, arr.dist_to_goal, arr.global_goal};
+  const size_t plane = static_cast<size_t>(cfg.local_w) * cfg.local_h;
+  switch (op) {
+    case 0:  // init_map_and_pose
+      PN_CUDA_CHECK(cudaMemsetAsync(a.full_map, 0, sizeof(float) * E * cfg.nc * static_cast<size_t>(cfg.full_w) * cfg.full_h, s));
+      launch_pdl(k_map_recentre, dim3((E + 63) / 64), dim3(64), 0, s, cfg, a, E, 1);
+      launch_window<false>(cfg, a, E, s);
+      break;
+    case 1:  // init_with_obs stamp
+      launch_pdl(k_map_stamp_initial, dim3(E), dim3(32), 0, s, cfg, a);
+      break;
+    case 2:  // update_local_map tail
+      launch_pdl(k_map_update_local, dim3(static_cast<unsigned>(std::min<size_t>((plane + 255) / 256, 296)), E), dim3(256), 0, s,
+                 cfg, a);
+      break;
+    case 3:  // update_full_map
+      launch_window<true>(cfg, a, E, s);
+      launch_pdl(k_map_recentre, dim3((E + 63) / 64), dim3(64), 0, s, cfg, a, E, 0);
+      launch_window<false>(cfg, a, E, s);
+      break;
+    default:
+      PN_REQUIRE(false, "map_bookkeeping: unknown op");
+  }
+  PN_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace pn

@@ -1,5 +1,6 @@
 // Stage A (Mask-RCNN R101-FPN -> per-category mask stack) network instance and the non-GEMM kernels it uses.
 #pragma once
+#include "../../include/peanut_b200.h"
 #include "engine.h"
 
 namespace pn {
@@ -99,6 +100,9 @@ void launch_target_pred(const float* pred, int win, int x1, int y1, int goal_cat
                         const float* explored, long long explored_row_stride, float* out, cudaStream_t s);
 void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, int E, int H, int W, int ds, int h, int w,
                      int nsem, float min_d, float max_d, float* obs, cudaStream_t s);
+
+// mapstate.cu: op 0 init_map_and_pose, 1 init_with_obs stamp, 2 update_local_map tail, 3 update_full_map
+void map_bookkeeping(int op, const pn_map_cfg& cfg, const pn_map_arrays& arrays, int E, cudaStream_t s);
 
 // detect.cu
 void add_upsample2x_add(Net& net, const Tensor& prev, const Tensor& lat);   // lat += nearest_up2(prev)

@@ -1,0 +1,93 @@
+"""Device-resident map bookkeeping of ``Agent_State`` (nav/agent/agent_state.py) - SURVEY.md section 8(f), N3.
+
+Mirrors, for E environments at once, the fields and methods of the reference class that sit between the mapper (stage B)
+and the planner: ``full_map`` / ``local_map``, ``full_pose`` / ``local_pose``, ``origins``, ``lmb``,
+``planner_pose_inputs``, ``loc_r`` / ``loc_c``, ``dist_to_goal`` and
+
+    init_map_and_pose()      agent_state.py:180-211
+    stamp_initial()          agent_state.py:116-122   (the stamp of init_with_obs, after the first mapper call)
+    update_local_map()       agent_state.py:276-303   (everything after the sem_map_module call)
+    update_full_map()        agent_state.py:308-338
+
+The reference computes every cell index on the host from ``pose.cpu().numpy()`` (three blocking device syncs per step and
+environment) and applies the stamps as small indexed tensor writes.  Here every field is a CUDA tensor, each method is one
+call into libpeanut_b200.so (``pn_map_*``) for all environments, and nothing synchronises; ``planner_inputs()`` is the one
+place that reads the small state back.  There is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class MapState:
+    """E environments' worth of Agent_State map fields on one device.  ``ctx`` is a ``_lib.Context``."""
+
+    def __init__(self, ctx, num_envs, num_sem_categories=10, map_size_cm=4800, map_resolution=5, global_downscaling=2,
+                 grid_resolution=24, col_rad=4, goal_reached_dist=75.0, f64_cells=False, device=None):
+        if float(col_rad) != int(col_rad):
+            raise ValueError("col_rad must be integer-valued (the reference indexes with selem_idx - (col_rad + 1))")
+        self.ctx = ctx
+        self.E = int(num_envs)
+        self.nc = 4 + int(num_sem_categories)                                  # agent_state.py:39
+        self.full_w = self.full_h = int(map_size_cm) // int(map_resolution)    # :41-42
+        self.local_w = int(self.full_w / global_downscaling)                   # :43-44
+        self.local_h = int(self.full_h / global_downscaling)
+        dev = torch.device(device if device is not None else f"cuda:{ctx.device}")
+        E = self.E
+        self.full_map = torch.zeros((E, self.nc, self.full_w, self.full_h), dtype=torch.float32, device=dev)
+        self.local_map = torch.zeros((E, self.nc, self.local_w, self.local_h), dtype=torch.float32, device=dev)
+        self.full_pose = torch.zeros((E, 3), dtype=torch.float32, device=dev)
+        self.local_pose = torch.zeros((E, 3), dtype=torch.float32, device=dev)
+        self.origins = torch.zeros((E, 3), dtype=torch.float64, device=dev)
+        self.lmb = torch.zeros((E, 4), dtype=torch.int32, device=dev)
+        self.planner_pose_inputs = torch.zeros((E, 7), dtype=torch.float64, device=dev)
+        self.loc = torch.zeros((E, 2), dtype=torch.int32, device=dev)          # loc_r, loc_c
+        self.dist_to_goal = torch.zeros((E,), dtype=torch.float64, device=dev)
+        self.global_goals = torch.zeros((E, 2), dtype=torch.int32, device=dev)  # global_goals[0] per environment
+        self.cfg = _lib.MapCfg(self.nc, self.full_w, self.full_h, self.local_w, self.local_h, int(map_resolution),
+                               int(map_size_cm), int(global_downscaling), int(grid_resolution), int(col_rad),
+                               float(goal_reached_dist), 1 if f64_cells else 0)
+
+    def _arrays(self):
+        for t in (self.full_map, self.local_map, self.full_pose, self.local_pose, self.origins, self.lmb,
+                  self.planner_pose_inputs, self.loc, self.dist_to_goal, self.global_goals):
+            if not (t.is_cuda and t.is_contiguous()):
+                raise TypeError("MapState fields must stay contiguous CUDA tensors")
+        if tuple(self.local_map.shape) != (self.E, self.nc, self.local_w, self.local_h) or self.local_map.dtype != torch.float32:
+            raise TypeError("local_map must be float32 [E, nc, local_w, local_h]")
+        return _lib.MapArrays(self.full_map.data_ptr(), self.local_map.data_ptr(), self.full_pose.data_ptr(),
+                              self.local_pose.data_ptr(), self.origins.data_ptr(), self.lmb.data_ptr(),
+                              self.planner_pose_inputs.data_ptr(), self.loc.data_ptr(), self.dist_to_goal.data_ptr(),
+                              self.global_goals.data_ptr())
+
+    def _call(self, fn):
+        arrays = self._arrays()
+        stream = torch.cuda.current_stream(self.full_map.device).cuda_stream
+        _lib.check(fn(self.ctx.handle, ctypes.byref(self.cfg), ctypes.byref(arrays), self.E, ctypes.c_void_p(stream)))
+
+    def init_map_and_pose(self):
+        self._call(self.ctx.lib.pn_map_init)
+
+    def stamp_initial(self):
+        self._call(self.ctx.lib.pn_map_stamp_initial)
+
+    def update_local_map(self, local_map=None, local_pose=None):
+        """Bookkeeping after the mapper call.  ``local_map`` / ``local_pose``: the mapper's outputs when it did not write
+        into ``self.local_map`` / ``self.local_pose`` directly (adopted without a copy if contiguous)."""
+        if local_map is not None:
+            self.local_map = local_map.contiguous()
+        if local_pose is not None:
+            self.local_pose = local_pose.contiguous()
+        self._call(self.ctx.lib.pn_map_update_local)
+
+    def update_full_map(self):
+        self._call(self.ctx.lib.pn_map_update_full)
+
+    def planner_inputs(self):
+        """One readback of the small per-environment state (the reference's host-side fields)."""
+        packed = torch.cat([self.planner_pose_inputs, self.loc.double(), self.dist_to_goal[:, None], self.lmb.double(),
+                            self.origins], dim=1).cpu().numpy()
+        return {"pose_pred": packed[:, :7], "loc": packed[:, 7:9].astype(int), "dist_to_goal": packed[:, 9],
+                "lmb": packed[:, 10:14].astype(int), "origins": packed[:, 14:17]}

@@ -170,6 +170,16 @@ int pn_map_update_local(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays*
 /* update_full_map (:308-338): window written back, window recentred on the agent, local map and pose re-cut. */
 int pn_map_update_full(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream);
 
+/* Agent_State.update_goal_map (:423-452), every step, for E environments: goal_map_out [E, local_w, local_h] fp32 = the
+ * cells of category channel goal_cat + 4 (binarised; eroded goal_erode times and dilated once with the 4-neighbour cross
+ * unless skip_morph[e] != 0, the reference's "'tv' in goal_name") that carry no OTHER category of channels 4..9;
+ * found_goal_out [E] = 1 if any such cell exists, else 0 and goal_map_out = a single 1 at global_goal[e].  All pointers are
+ * device pointers.  Assumes map values >= 0 (the mapper clamps to [0, 1]), which makes the reference's two `.sum() != 0`
+ * tests equivalent to "any cell set". */
+int pn_goal_map(pn_ctx* ctx, const float* local_map_dev, int E, int num_channels, int local_w, int local_h,
+                const int* goal_cat_dev, const int* skip_morph_dev, const int* global_goal_dev, int goal_erode,
+                float* goal_map_out_dev, int* found_goal_out_dev, void* stream);
+
 /* ---- Glue between stages A and B: Agent_Helper._preprocess_obs / _preprocess_depth
  * (nav/agent/agent_helper.py:175-217).  depth [E,H,W] fp32 as the simulator emits it (0 = invalid, 1 = max range),
  * rgb [E,H,W,3] uint8 (may be NULL: channels 0-2 are unused by the mapper), sem [E,H,W,num_sem] fp32 (stage A output)

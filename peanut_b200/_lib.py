@@ -57,6 +57,8 @@ PROTOTYPES = {
     "pn_map_stamp_initial": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_map_update_local": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_map_update_full": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_goal_map": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3 + [ctypes.c_int] +
+                    [ctypes.c_void_p] * 3),
     "pn_semmap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
     "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),

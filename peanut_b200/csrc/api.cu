@@ -609,6 +609,20 @@ int pn_map_update_full(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* 
   return map_call(ctx, 3, cfg, arrays, E, stream);
 }
 
+int pn_goal_map(pn_ctx* ctx, const float* local_map_dev, int E, int num_channels, int local_w, int local_h,
+                const int* goal_cat_dev, const int* skip_morph_dev, const int* global_goal_dev, int goal_erode,
+                float* goal_map_out_dev, int* found_goal_out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(local_map_dev && goal_cat_dev && skip_morph_dev && global_goal_dev && goal_map_out_dev && found_goal_out_dev,
+             "pn_goal_map: null buffer");
+  PN_REQUIRE(E > 0 && num_channels >= 5 && local_w > 0 && local_h > 0, "pn_goal_map: bad geometry");
+  launch_goal_map(local_map_dev, E, num_channels, local_w, local_h, goal_cat_dev, skip_morph_dev, global_goal_dev, goal_erode,
+                  goal_map_out_dev, found_goal_out_dev, static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
 int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, int H, int W, const float* w_host,
               const float* scale_host, const float* bias_host, const float* residual_dev, int Cout, int R, int S,
               int stride, int dil, int pad, int relu, int force_bn, float* y_dev) {

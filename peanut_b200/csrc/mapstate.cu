@@ -205,6 +205,93 @@ __global__ void k_map_recentre(MapCfg cfg, MapArrays a, int E, int mode) {
   }
 }
 
+
+// ---- Agent_State.update_goal_map (:423-452), every step: where the goal category is on the map (and no other category
+// of channels 4..9 is), eroded goal_erode times with the 4-neighbour cross (outside the map counts as set, skimage's
+// border_value=True) and dilated once (outside counts as clear).  n cross erosions = one erosion by the diamond
+// |dr| + |dc| <= n, so a cell of the result depends on a (2n+3)^2 neighbourhood: each block stages the binarised goal
+// channel of a 32 x 32 tile plus halo in shared memory, erodes into a 34 x 34 tile, dilates from there.
+constexpr int kGoalTile = 32;
+constexpr int kGoalMaxErode = 12;
+
+__global__ void __launch_bounds__(256) k_goal_candidates(int nc, int w, int h, int erode, const float* __restrict__ local_map,
+                                                         const int* __restrict__ goal_cat, const int* __restrict__ skip_morph,
+                                                         float* __restrict__ goal_map, int* __restrict__ found) {
+  pdl_grid_sync();
+  extern __shared__ unsigned char sm[];
+  const int e = blockIdx.z;
+  const int cn = goal_cat[e] + 4;
+  const size_t plane = static_cast<size_t>(w) * h;
+  const float* lm = local_map + static_cast<size_t>(e) * nc * plane;
+  float* out = goal_map + static_cast<size_t>(e) * plane;
+  const int r_base = blockIdx.y * kGoalTile, c_base = blockIdx.x * kGoalTile;
+  const bool valid_cat = cn >= 4 && cn < nc;  // the reference raises IndexError otherwise
+  const bool morph = skip_morph[e] == 0;
+  const int halo = erode + 1, s1 = kGoalTile + 2 * halo, s2 = kGoalTile + 2;
+  unsigned char* bin = sm;             // s1 x s1: 0 clear, 1 set, 2 outside the map
+  unsigned char* ero = sm + s1 * s1;   // s2 x s2
+  if (morph && valid_cat) {
+    for (int i = threadIdx.x; i < s1 * s1; i += blockDim.x) {
+      const int r = r_base - halo + i / s1, c = c_base - halo + i % s1;
+      unsigned char v = 2;
+      if (r >= 0 && r < w && c >= 0 && c < h) v = lm[cn * plane + static_cast<size_t>(r) * h + c] != 0.f ? 1 : 0;
+      bin[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s2 * s2; i += blockDim.x) {
+      const int lr = i / s2, lc = i % s2;           // eroded-tile coordinates; (lr + erode, lc + erode) in the bin tile
+      const int r = r_base - 1 + lr, c = c_base - 1 + lc;
+      bool v = r >= 0 && r < w && c >= 0 && c < h;  // nothing outside the map for the dilation to pick up
+      for (int dr = -erode; dr <= erode && v; ++dr) {
+        const int span = erode - (dr < 0 ? -dr : dr);
+        for (int dc = -span; dc <= span; ++dc) v = v && bin[(lr + erode + dr) * s1 + lc + erode + dc] != 0;
+      }
+      ero[i] = v ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  bool any = false;
+  for (int i = threadIdx.x; i < kGoalTile * kGoalTile; i += blockDim.x) {
+    const int lr = i / kGoalTile, lc = i % kGoalTile;
+    const int r = r_base + lr, c = c_base + lc;
+    if (r >= w || c >= h) continue;
+    const size_t idx = static_cast<size_t>(r) * h + c;
+    float t = 0.f;
+    if (valid_cat) {
+      const float x = lm[cn * plane + idx];
+      if (morph) {
+        const int p = (lr + 1) * s2 + lc + 1;
+        t = (ero[p] | ero[p - 1] | ero[p + 1] | ero[p - s2] | ero[p + s2]) ? 1.f : 0.f;
+      } else {
+        t = x > 0.f ? 1.f : x;
+      }
+      float others = nc > 4 ? lm[4 * plane + idx] : 0.f;  // torch.sum(local_map[4:10], dim=0): channel after channel
+      for (int ch = 5; ch < 10 && ch < nc; ++ch) others = __fadd_rn(others, lm[ch * plane + idx]);
+      t = (__fsub_rn(others, x) == 0.f) ? t : 0.f * t;
+    }
+    out[idx] = t;
+    any |= (t != 0.f);
+  }
+  if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(found + e, 1);
+}
+
+// not found: goal_map = the long-term goal cell (:429-430)
+__global__ void __launch_bounds__(256) k_goal_finalize(int w, int h, const int* __restrict__ global_goal, const int* __restrict__ found,
+                                                       float* __restrict__ goal_map) {
+  pdl_grid_sync();
+  const int e = blockIdx.y;
+  if (found[e]) return;
+  int g0 = global_goal[e * 2 + 0], g1 = global_goal[e * 2 + 1];
+  if (g0 < 0) g0 += w;
+  if (g1 < 0) g1 += h;
+  const size_t plane = static_cast<size_t>(w) * h;
+  float* out = goal_map + static_cast<size_t>(e) * plane;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < plane; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / h), c = static_cast<int>(i - static_cast<size_t>(r) * h);
+    out[i] = (r == g0 && c == g1) ? 1.f : 0.f;
+  }
+}
+
 template <bool kToFull>
 void launch_window(const MapCfg& cfg, const MapArrays& a, int E, cudaStream_t s) {
   const bool vec = cfg.local_h % 4 == 0 && cfg.full_h % 4 == 0 && cfg.grid % 4 == 0 && (cfg.full_h - cfg.local_h) % 4 == 0 &&
@@ -244,6 +331,20 @@ void map_bookkeeping(int op, const pn_map_cfg& c, const pn_map_arrays& arr, int 
     default:
       PN_REQUIRE(false, "map_bookkeeping: unknown op");
   }
+  PN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_goal_map(const float* local_map, int E, int nc, int w, int h, const int* goal_cat, const int* skip_morph,
+                     const int* global_goal, int goal_erode, float* goal_map, int* found, cudaStream_t s) {
+  PN_REQUIRE(goal_erode >= 0 && goal_erode <= kGoalMaxErode, "pn_goal_map: goal_erode out of range (0..12)");
+  PN_CUDA_CHECK(cudaMemsetAsync(found, 0, sizeof(int) * E, s));
+  const int halo = goal_erode + 1, s1 = kGoalTile + 2 * halo, s2 = kGoalTile + 2;
+  const size_t smem = static_cast<size_t>(s1) * s1 + static_cast<size_t>(s2) * s2;
+  const dim3 grid((h + kGoalTile - 1) / kGoalTile, (w + kGoalTile - 1) / kGoalTile, E);
+  launch_pdl(k_goal_candidates, grid, dim3(256), smem, s, nc, w, h, goal_erode, local_map, goal_cat, skip_morph, goal_map, found);
+  const size_t plane = static_cast<size_t>(w) * h;
+  launch_pdl(k_goal_finalize, dim3(static_cast<unsigned>(std::min<size_t>((plane + 255) / 256, 148)), E), dim3(256), 0, s, w, h,
+             global_goal, found, goal_map);
   PN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -103,6 +103,8 @@ void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, i
 
 // mapstate.cu: op 0 init_map_and_pose, 1 init_with_obs stamp, 2 update_local_map tail, 3 update_full_map
 void map_bookkeeping(int op, const pn_map_cfg& cfg, const pn_map_arrays& arrays, int E, cudaStream_t s);
+void launch_goal_map(const float* local_map, int E, int nc, int w, int h, const int* goal_cat, const int* skip_morph,
+                     const int* global_goal, int goal_erode, float* goal_map, int* found, cudaStream_t s);
 
 // detect.cu
 void add_upsample2x_add(Net& net, const Tensor& prev, const Tensor& lat);   // lat += nearest_up2(prev)

@@ -8,6 +8,7 @@ and the planner: ``full_map`` / ``local_map``, ``full_pose`` / ``local_pose``, `
     stamp_initial()          agent_state.py:116-122   (the stamp of init_with_obs, after the first mapper call)
     update_local_map()       agent_state.py:276-303   (everything after the sem_map_module call)
     update_full_map()        agent_state.py:308-338
+    update_goal_map()        agent_state.py:423-452   (goal found on the map? erode / dilate / no-other-category mask)
 
 The reference computes every cell index on the host from ``pose.cpu().numpy()`` (three blocking device syncs per step and
 environment) and applies the stamps as small indexed tensor writes.  Here every field is a CUDA tensor, each method is one
@@ -84,6 +85,37 @@ class MapState:
 
     def update_full_map(self):
         self._call(self.ctx.lib.pn_map_update_full)
+
+    def update_goal_map(self, goal_cat, goal_names, goal_erode=3, only_explore=0):
+        """``goal_cat``: per-environment goal category ids (sequence of ints or an int32 CUDA tensor [E]); ``goal_names``:
+        the ``infos['goal_name']`` strings (erosion / dilation are skipped where 'tv' is in the name) or an int32 CUDA tensor
+        of 0/1 skip flags.  Sets and returns ``self.goal_map`` [E, local_w, local_h] float32 and ``self.found_goal`` [E]
+        int32, both on the device (the reference's goal_map is float64, or float32 in the 'tv' branch: same 0/1 values)."""
+        dev = self.full_map.device
+        E = self.E
+        if not hasattr(self, "goal_map"):
+            self.goal_map = torch.empty((E, self.local_w, self.local_h), dtype=torch.float32, device=dev)
+            self.found_goal = torch.zeros((E,), dtype=torch.int32, device=dev)
+        if only_explore != 0:                                                  # agent_state.py:433
+            self.found_goal.zero_()
+            self.goal_map.zero_()
+            idx = torch.arange(E, device=dev)
+            self.goal_map[idx, self.global_goals[:, 0].long(), self.global_goals[:, 1].long()] = 1.0
+            return self.goal_map, self.found_goal
+        if not torch.is_tensor(goal_cat):
+            goal_cat = torch.tensor([int(g) for g in goal_cat], dtype=torch.int32, device=dev)
+        if not torch.is_tensor(goal_names):
+            goal_names = torch.tensor([1 if "tv" in str(n) else 0 for n in goal_names], dtype=torch.int32, device=dev)
+        for t in (goal_cat, goal_names):
+            if not (t.is_cuda and t.dtype == torch.int32 and t.numel() == E and t.is_contiguous()):
+                raise TypeError("goal_cat / goal_names must be int32 CUDA tensors of E elements (or host sequences)")
+        self._arrays()  # validates the state tensors
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.ctx.lib.pn_goal_map(self.ctx.handle, self.local_map.data_ptr(), E, self.nc, self.local_w, self.local_h,
+                                            goal_cat.data_ptr(), goal_names.data_ptr(), self.global_goals.data_ptr(),
+                                            int(goal_erode), self.goal_map.data_ptr(), self.found_goal.data_ptr(),
+                                            ctypes.c_void_p(stream)))
+        return self.goal_map, self.found_goal
 
     def planner_inputs(self):
         """One readback of the small per-environment state (the reference's host-side fields)."""

@@ -38,9 +38,15 @@ def main():
     t_local = timed(d.update_local_map)
     t_full = timed(d.update_full_map)
     t_init = timed(d.init_map_and_pose)
+    d.global_goals.fill_(100)
+    cats = torch.arange(E, dtype=torch.int32, device="cuda") % 6
+    skip = torch.zeros(E, dtype=torch.int32, device="cuda")
+    d.local_map[:, 4:] *= (d.local_map[:, 4:] > 0.7)
+    t_goal = timed(lambda: d.update_goal_map(cats, skip))
     print(f"# map bookkeeping, E={E}, full {tuple(d.full_map.shape)}, local {tuple(d.local_map.shape)}")
     print(f"update_local_map  {t_local:8.1f} us   (writes channel 2: {local_bytes / d.nc / 1e6:.2f} MB)")
     print(f"update_full_map   {t_full:8.1f} us   ({4 * local_bytes / 1e6:.1f} MB moved -> {4 * local_bytes / t_full / 1e3:.0f} GB/s)")
+    print(f"update_goal_map   {t_goal:8.1f} us   (reads 7 channels: {7 * local_bytes / d.nc / 1e6:.1f} MB, writes {local_bytes / d.nc / 1e6:.2f} MB)")
     print(f"init_map_and_pose {t_init:8.1f} us   (memset {d.full_map.numel() * 4 / 1e6:.1f} MB + window)")
 
 

@@ -108,7 +108,7 @@ void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem,
   cfg.attrs = attr, cfg.numAttrs = 1;
   if (kSplit || kPair) {  // one thread-block cluster per output tile (split-K) / one SM pair per 256-row tile
     attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = kPair ? 2 : p.splits, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
+    attr[1].val.clusterDim.x = (kPair ? 2 : 1) * (kSplit ? p.splits : 1), attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
   }
   PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, BN, kSplit, kPair>, tm.a, tm.b, tm.out, tm.res, p));
@@ -116,6 +116,14 @@ void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem,
 
 template <typename T>
 void launch_conv_bn(int bn, bool pair, const ConvMaps& tm, const ConvParams& p, int grid, size_t smem, cudaStream_t s) {
+  if (pair && p.splits > 1) {  // a cluster of `splits` SM pairs per 256-row tile
+    switch (bn) {
+      case 128: launch_conv<T, 128, true, true>(tm, p, grid, smem, s); break;
+      case 256: launch_conv<T, 256, true, true>(tm, p, grid, smem, s); break;
+      default: PN_REQUIRE(false, "unsupported N tile for a CTA pair");
+    }
+    return;
+  }
   if (pair) {
     switch (bn) {
       case 128: launch_conv<T, 128, false, true>(tm, p, grid, smem, s); break;
@@ -253,20 +261,31 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     for (int cand : {256, 128, 64, 32}) {
       if (sp.force_bn ? cand != (sp.force_bn & 0x3ff) : (cand > cout32 || cout32 % cand != 0)) continue;
       // CTA pair (cta_group::2): 256 x cand tile on two SMs, each staging 128 activation rows + cand/2 weight rows
-      if (cand >= 128 && sw == 128 && m_tiles >= 2 && sp.force_pair != 2 && sp.force_splits <= 1 && (kAutoPair || sp.force_pair == 1)) {
-        const double work = std::ceil(m_tiles / 2.0) * ((cout32 + cand - 1) / cand);
-        const double pairs = net.num_sms / 2;
-        const double active = std::min<double>(work, pairs) * 2.0;
-        const double waves = std::ceil(work / pairs);
-        const double bytes = static_cast<double>(kblocks_total) * block_k * es * (kBlockM + cand / 2);
-        const double t_mem = bytes / std::min(125e9, 14e12 / active);
-        const double t_mma = static_cast<double>(kblocks_total) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
-        // the epilogue of a 128 x cand tile takes ~0.5 us per 32 columns (shared-memory bound, measured) and overlaps
-        // the next tile's main loop; pairs only pay off where the main loop is the longer of the two
-        const double t_epi = 0.5e-6 * cand / 32.0;
-        const double t = waves * (std::max(std::max(t_mem, t_mma), t_epi) + kTileFixed) + t_epi + 0.5e-6;  // + cluster set-up / tear-down
-        cands.push_back({t, cand, 1, true});
-        if (t < best || sp.force_pair == 1) best = t, bn = cand, splits = 1, pair = true;
+      if (cand >= 128 && sw == 128 && m_tiles >= 2 && sp.force_pair != 2 && (kAutoPair || sp.force_pair == 1)) {
+        for (int s : {1, 2, 4}) {  // s > 1: split-K over a cluster of s pairs (2 s CTAs, at most 8)
+          if (sp.force_splits ? s != sp.force_splits
+                              : (s > 1 && (sp.force_pair == 1 || sp.no_split || !kAutoSplitK || kblocks_total / s < 4)))
+            continue;
+          if (s > kblocks_total) continue;
+          const int kbs = (kblocks_total + s - 1) / s;
+          if (s > 1 && kbs * (s - 1) >= kblocks_total) continue;
+          if (s > 1 && ((cand / s) % 8 != 0 || 8 * (kBlockM + cand / 2) * sw < kBlockM * cand * 4)) continue;
+          const double work = std::ceil(m_tiles / 2.0) * ((cout32 + cand - 1) / cand);  // 256-row tiles
+          const double slots = s > 1 ? std::floor(128.0 / (2 * s)) : net.num_sms / 2;     // clusters resident at once
+          const double active = std::min<double>(work, slots) * 2.0 * s;
+          const double waves = std::ceil(work / slots);
+          const double bytes = static_cast<double>(kbs) * block_k * es * (kBlockM + cand / 2);
+          const double t_mem = bytes / std::min(125e9, 14e12 / active);
+          const double t_mma = static_cast<double>(kbs) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
+          // the epilogue of a 128 x cand tile takes ~0.5 us per 32 columns (shared-memory bound, measured) and overlaps
+          // the next tile's main loop; pairs only pay off where the main loop is the longer of the two
+          const double t_epi = 0.5e-6 * cand / 32.0 / s;
+          const double t_red = s > 1 ? 1.5e-6 + 2.0 * kBlockM * cand * 4.0 / 200e9 : 0.0;
+          const double t = waves * (std::max(std::max(t_mem, t_mma), s > 1 ? 0.0 : t_epi) + t_red + kTileFixed) + t_epi +
+                           0.5e-6;  // + cluster set-up / tear-down
+          cands.push_back({t, cand, s, true});
+          if (t < best || sp.force_pair == 1) best = t, bn = cand, splits = s, pair = true;
+        }
       }
       if (sp.force_pair == 1) continue;
       for (int s : {1, 2, 4, 8}) {
@@ -450,7 +469,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
     const size_t smem = fixed_bytes + stages * stage_bytes;
     const long long tiles = static_cast<long long>(p.m_tiles) * n_tiles * splits;
-    const int grid = pair ? 2 * static_cast<int>(std::min<long long>(tiles, net.num_sms / 2))
+    const int grid = pair ? 2 * static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, net.num_sms / 2))
                           : static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, net.num_sms));
 
     Variant v;
@@ -481,6 +500,11 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
       bool has_model = false;
       for (const Cand& c : shortlist) has_model |= (c.bn == bn && c.splits == splits && c.pair == pair);
       if (!has_model) shortlist.push_back({0.0, bn, splits, pair});
+      for (const Cand& c : cands) {  // the model is least certain about split-K over pairs: always time those
+        bool listed = false;
+        for (const Cand& l : shortlist) listed |= (l.bn == c.bn && l.splits == c.splits && l.pair == c.pair);
+        if (c.pair && c.splits > 1 && !listed) shortlist.push_back(c);
+      }
       Cand best_c{1e30, bn, splits, pair};
       for (const Cand& c : shortlist) {
         float ms = 0.f;

@@ -195,12 +195,15 @@ __device__ __forceinline__ void finish_store8(const ConvParams& p, long long m, 
 // Split-K tail of CTA `rank`: sum column slice `rank` of every CTA's parked partial tile over distributed shared memory
 // (fixed order: split 0, 1, ...), add bias / residual, ReLU, store.  8 columns per step with the distributed-smem loads
 // of all splits, the bias and the NEXT step's residual in flight together.
+// peer_stride / peer_first: cluster rank of split s0's CTA = peer_first + s0 * peer_stride (1, 0 without CTA pairs; 2, half
+// with pairs: the partial tiles of the same 128-row half).
 template <typename T, int BN, int kSplits>
-__device__ __forceinline__ void splitk_reduce(const ConvParams& p, uint32_t part0, int rank, long long m, int row, int n_tile) {
+__device__ __forceinline__ void splitk_reduce(const ConvParams& p, uint32_t part0, int rank, long long m, int row, int n_tile,
+                                              int peer_first, int peer_stride) {
   constexpr int kCols = BN / kSplits;  // columns this rank finishes (multiple of 8)
   uint32_t peer[kSplits];
 #pragma unroll
-  for (int s0 = 0; s0 < kSplits; ++s0) peer[s0] = map_shared_rank(part0, s0);
+  for (int s0 = 0; s0 < kSplits; ++s0) peer[s0] = map_shared_rank(part0, peer_first + s0 * peer_stride);
   const bool has_res = p.residual != nullptr;
   const int c_begin = rank * kCols;
   uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
@@ -236,10 +239,10 @@ __device__ __forceinline__ void splitk_reduce(const ConvParams& p, uint32_t part
 
 // "accumulator stage drained": local barrier, or - in a CTA pair - the leader's barrier (it gates the leader's MMA issue)
 template <bool kPair>
-__device__ __forceinline__ void arrive_tempty(uint64_t* bar, uint32_t cta_rank) {
+__device__ __forceinline__ void arrive_tempty(uint64_t* bar, uint32_t cta_rank, uint32_t pair_leader) {
   if constexpr (kPair) {
     if (cta_rank != 0) {
-      mbar_arrive_remote(leader_addr(bar));
+      mbar_arrive_remote(leader_addr(bar, pair_leader));
       return;
     }
   }
@@ -304,9 +307,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   PN_LOG(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  static_assert(!(kSplit && kPair), "split-K and CTA pairs are separate launch modes");
   constexpr int kBLoad = kPair ? BN / 2 : BN;  // weight rows this CTA stages per K block
-  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  // pair: rank within the SM pair; with split-K the cluster holds `splits` pairs (cluster ranks 2s, 2s + 1)
+  const uint32_t cluster_rank = (kPair || kSplit) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = kPair ? (cluster_rank & 1u) : 0u;
+  const uint32_t pair_leader = cluster_rank & ~1u;
+  const uint32_t pair_mask = 3u << pair_leader;
   const uint32_t a_bytes = kBlockM * p.sw;
   const uint32_t b_bytes = kBLoad * p.sw;
   const uint32_t stage_tx = (kPair ? 2u : 1u) * (a_bytes + b_bytes);  // bytes that complete one (leader) full barrier
@@ -397,7 +403,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int i = 0; i < pre_armed; ++i) {
         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[i], stage_tx);
         if constexpr (kPair) {
-          tma_load_2d_pair(&tmap_b, leader_addr(&full_bar[i]), smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k,
+          tma_load_2d_pair(&tmap_b, leader_addr(&full_bar[i], pair_leader), smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k,
                            n_tile0 * BN + static_cast<int>(cta_rank) * kBLoad);
         } else {
           tma_load_2d(&tmap_b, &full_bar[i], smem_b + i * b_bytes, (kb_begin0 + i) * p.block_k, n_tile0 * BN);
@@ -446,7 +452,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           }
           if constexpr (kPair) {  // both CTAs' bytes complete the LEADER's full barrier
-            const uint32_t fb = leader_addr(&full_bar[stage]);
+            const uint32_t fb = leader_addr(&full_bar[stage], pair_leader);
             if (p.a_tiled) {
               tma_load_2d_pair(&tmap_a, fb, smem_a + stage * a_bytes, kb * p.block_k, m0);
             } else {
@@ -478,7 +484,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (kPair ? 2u : 1u) * b_bytes);
           if constexpr (kPair) {
-            tma_load_2d_pair(&tmap_b, leader_addr(&full_bar[stage]), smem_b + stage * b_bytes, kblocks * p.block_k,
+            tma_load_2d_pair(&tmap_b, leader_addr(&full_bar[stage], pair_leader), smem_b + stage * b_bytes, kblocks * p.block_k,
                              n_tile * BN + static_cast<int>(cta_rank) * kBLoad);
           } else {
             tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kblocks * p.block_k, n_tile * BN);
@@ -523,7 +529,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               else umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
             }
           }
-          if constexpr (kPair) umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+          if constexpr (kPair) umma_commit_pair(&empty_bar[stage], pair_mask);  // frees the stage in both CTAs
           else umma_commit(&empty_bar[stage]);
           if (kb == 0) PN_DBG(it, 3);
           if (++stage == p.stages) {
@@ -539,7 +545,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if constexpr (kPair) {
             if constexpr (ElemTraits<T>::kFormat == 1) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, 1u);
             else umma_tf32_pair(d_tmem, adesc, bdesc, idesc, 1u);
-            umma_commit_pair(&empty_bar[stage]);
+            umma_commit_pair(&empty_bar[stage], pair_mask);
           } else {
             if constexpr (ElemTraits<T>::kFormat == 1) umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
             else umma_tf32(d_tmem, adesc, bdesc, idesc, 1u);
@@ -550,7 +556,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             phase ^= 1;
           }
         }
-        if constexpr (kPair) umma_commit_pair(&tfull_bar[acc]);  // every MMA of this tile has retired
+        if constexpr (kPair) umma_commit_pair(&tfull_bar[acc], pair_mask);  // every MMA of this tile has retired
         else umma_commit(&tfull_bar[acc]);
         PN_DBG(it, 4);
       }
@@ -735,7 +741,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else {  // every accumulator column this warp needs is in registers: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank);
+          if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank, pair_leader);
         }
         process(va, grp);
         if (more_b) {
@@ -745,7 +751,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank);
+            if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank, pair_leader);
           }
           process(vb, grp + 1);
         }
@@ -813,7 +819,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank);
+      if (lane == 0) arrive_tempty<kPair>(&tempty_bar[acc], cta_rank, pair_leader);
     }
   }
     if constexpr (kSplit) {
@@ -821,20 +827,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       cluster_arrive_release();
       cluster_wait_acquire();
-      if (static_cast<int>(blockIdx.x) < num_tiles) {
-        const int tile = blockIdx.x / p.splits;
-        const int rank = blockIdx.x - tile * p.splits;  // == %cluster_ctarank for 1-D clusters of `splits` CTAs
+      if (work_first < num_tiles) {
+        const int tile = work_first / p.splits;
+        const int rank = work_first - tile * p.splits;  // this CTA's split == the column slice it finishes
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
         const int row = warp * 32 + lane;
-        const long long m = static_cast<long long>(m_tile) * kBlockM + row;
+        const long long m = static_cast<long long>(kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM + row;
         const uint32_t part0 = smem_u32(smem_a);
+        const int peer_first = kPair ? static_cast<int>(cta_rank) : 0, peer_stride = kPair ? 2 : 1;
         if (m < p.M) {
           switch (p.splits) {
-            case 2: splitk_reduce<T, BN, 2>(p, part0, rank, m, row, n_tile); break;
-            case 4: splitk_reduce<T, BN, 4>(p, part0, rank, m, row, n_tile); break;
+            case 2: splitk_reduce<T, BN, 2>(p, part0, rank, m, row, n_tile, peer_first, peer_stride); break;
+            case 4: splitk_reduce<T, BN, 4>(p, part0, rank, m, row, n_tile, peer_first, peer_stride); break;
             default:
-              if constexpr (BN >= 64) splitk_reduce<T, BN, 8>(p, part0, rank, m, row, n_tile);
+              if constexpr (BN >= 64 && !kPair) splitk_reduce<T, BN, 8>(p, part0, rank, m, row, n_tile, peer_first, peer_stride);
               break;
           }
         }

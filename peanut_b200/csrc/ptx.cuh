@@ -115,8 +115,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 // forward declaration (defined with the cluster helpers below)
 __device__ __forceinline__ uint32_t map_shared_rank(uint32_t saddr, int rank);
-// shared::cluster address of the same object in the pair's leader CTA (cluster rank 0)
-__device__ __forceinline__ uint32_t leader_addr(const void* p) { return map_shared_rank(smem_u32(p), 0); }
+// shared::cluster address of the same object in the pair's leader CTA (the even cluster rank of the pair)
+__device__ __forceinline__ uint32_t leader_addr(const void* p, uint32_t leader_rank) {
+  return map_shared_rank(smem_u32(p), static_cast<int>(leader_rank));
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -148,9 +150,9 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
 // commit of the leader's MMAs: one arrival on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint32_t pair_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(pair_mask))
                : "memory");
 }
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

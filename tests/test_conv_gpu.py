@@ -52,6 +52,10 @@ PAIR_CASES = [
     (6, 512, 30, 30, 2048, 1, 1, 1, 0, PAIR | 256),  # conv3-like: many chunks per tile, residual ring wraps
     (1, 512, 19, 19, 512, 3, 1, 4, 4, PAIR | 256),   # dilation 4, 3 m-tiles
     (1, 256, 24, 24, 512, 1, 2, 1, 0, PAIR | 128),   # 1x1 stride 2 (im2col with stride), 2 m-tiles
+    # split-K over a cluster of SM pairs (2 x splits CTAs): same reduce-scatter, peers = the same 128-row half of every pair
+    (1, 256, 50, 68, 256, 3, 1, 1, 1, PAIR | (4 << 16) | 256),   # res4.conv2 at the 800 x 1088 input: 14 pairs x 4 splits
+    (2, 1024, 13, 17, 512, 1, 1, 1, 0, PAIR | (2 << 16) | 128),  # 1x1, 4 m-tiles (last one partial), 4 n-tiles, 2 splits
+    (1, 512, 19, 19, 512, 3, 1, 2, 2, PAIR | (4 << 16) | 128),   # dilated, 3 m-tiles: the last pair's second CTA has no rows
 ]
 
 
@@ -107,7 +111,8 @@ def test_conv_pair(ctx, case, precision):
     scale = ref.abs().max().item() + 1e-6
     assert err <= (1e-2 if precision == _lib.PN_BF16 else 3e-3) * scale, f"max abs err {err} vs scale {scale}"
     # and bit-identical to the single-CTA kernel (same K order, same epilogue arithmetic)
-    single = (case[:9] + ((case[9] & 0x3ff) | 0x4000 | (1 << 16),))  # pairs forbidden, no split-K
+    # pairs forbidden, same split-K factor (1 = none): the K order and the reduction order are then identical
+    single = (case[:9] + ((case[9] & 0x3ff) | 0x4000 | (max(case[9] >> 16, 1) << 16),))
     y1, _ = _run(ctx, single, precision)
     assert torch.equal(y, y1)
 

@@ -9,6 +9,7 @@ pname = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 prec = {"bf16": 0, "tf32": 1}[pname]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 # (name, Cin, H, W, Cout, k, stride, dil, pad, residual)
+ONLY = os.environ.get("PN_SWEEP_ONLY", "")  # comma-separated name prefixes
 SHAPES = [
     ("A.res2.conv1", 256, 200, 272, 64, 1, 1, 1, 0, 0), ("A.res2.conv2", 64, 200, 272, 64, 3, 1, 1, 1, 0),
     ("A.res2.conv3", 64, 200, 272, 256, 1, 1, 1, 0, 1),
@@ -30,10 +31,12 @@ SHAPES = [
 ]
 ctx = _lib.Context(0)
 ms, bn = ctypes.c_float(), ctypes.c_int()
-combos = [(b, s) for b in (64, 128, 256) for s in (1, 2, 4, 8)] + [(128, -1), (256, -1)]  # s = -1: CTA pair
+combos = [(b, s) for b in (64, 128, 256) for s in (1, 2, 4, 8)] + [(b, s) for b in (128, 256) for s in (-1, -2, -4)]  # s < 0: CTA pairs, -s splits
 print(f"# precision={pname} batch={B}; us per launch (back-to-back launches, L2-hot): auto | " +
-      " ".join(f"{b}/{'P' if s < 0 else s}" for b, s in combos))
+       " ".join(f"{b}/{'P' + str(-s) if s < 0 else s}" for b, s in combos))
 for name, cin, h, w, cout, k, st, dil, pad, res in SHAPES:
+    if ONLY and not any(name.startswith(o) for o in ONLY.split(",")):
+        continue
     bb, hh = (1, h * B) if name.startswith("A.fc") else (B, h)
     ho = (hh + 2 * pad - dil * (k - 1) - 1) // st + 1
     wo = (w + 2 * pad - dil * (k - 1) - 1) // st + 1
@@ -44,11 +47,11 @@ for name, cin, h, w, cout, k, st, dil, pad, res in SHAPES:
         if b and (b > cout or cout % b):
             row.append("   -")
             continue
-        force = (b | 0x2000) if s < 0 else (b | 0x4000 | (s << 16)) if b else 0   # pair / single CTA with s splits / auto
+        force = (b | 0x2000 | (-s << 16)) if s < 0 else (b | 0x4000 | (s << 16)) if b else 0   # pairs / single CTAs with s splits / auto
         rc = ctx.lib.pn_conv_bench(ctx.handle, prec, bb, cin, hh, w, cout, k, k, st, dil, pad, res, force,
                                    20, ctypes.byref(ms), ctypes.byref(bn))
         if rc != 0:
             row.append("   x")
             continue
-        row.append(f"{ms.value * 1000:5.1f}" + (f"({bn.value % 1000}/{'P' if bn.value >= 100000 else (bn.value // 1000) % 100})" if b == 0 else ""))
+        row.append(f"{ms.value * 1000:5.1f}" + (f"({bn.value % 1000}/{'P' if bn.value >= 100000 else ''}{(bn.value // 1000) % 100})" if b == 0 else ""))
     print(f"{name:18s} M={bb * ho * wo:6d} N={cout:5d} K={cin * k * k:6d} {gf:6.2f}GF " + " ".join(row), flush=True)

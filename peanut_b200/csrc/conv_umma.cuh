@@ -65,6 +65,7 @@ struct ConvParams {
   // (one tile per cluster, grid = tiles * splits).  Each CTA parks its fp32 partial tile in its own shared memory
   // (the operand ring, idle by then), and after a cluster barrier CTA r sums column slice r of all partial tiles
   // over distributed shared memory in a fixed order (bit-reproducible) and applies the epilogue to that slice.
+  int dbg_skip;      // tuning aid (PN_CONV_TIMELINE builds only): epilogue parts to skip, see PN_SKIP
   long long* dbg;    // optional per-tile timeline of CTA 0 (tuning aid; nullptr in production): 16 clock64 slots per tile
   int splits;        // >= 1; BN / splits is a multiple of 8
   int kb_per_split;  // K blocks per split (the last split may be shorter)
@@ -291,7 +292,11 @@ __device__ __forceinline__ long long pn_globaltimer() {
 #define PN_LOG(which) do { if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { \
     const long long n_ = p.dbg[1024]; if (n_ < 64) p.dbg[1025 + 4 * n_ + (which)] = pn_globaltimer(); \
     if ((which) == 2) p.dbg[1024] = n_ + 1; } } while (0)
+// epilogue attribution by elimination (results are wrong, timings tell): 1 TMA store + its wait, 2 st.shared, 4 residual
+// (wait + loads + adds), 8 bias loads, 16 tcgen05.ld double buffering (wait right after issue)
+#define PN_SKIP(bit) ((p.dbg_skip & (bit)) != 0)
 #else
+#define PN_SKIP(bit) false
 #define PN_DBG(iter, slot) do { } while (0)
 #define PN_LOG(which) do { } while (0)
 #endif
@@ -640,18 +645,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t buf = (p.out_bufs == 2) ? (g & 1u) : 0u;
         const uint32_t obuf = out_addr + buf * chunk_bytes;
         if (sub == 0) {
-          if (lane == 0) {  // this warp's earlier store out of this buffer has been read
+          if (lane == 0 && !PN_SKIP(1)) {  // this warp's earlier store out of this buffer has been read
             if (p.out_bufs == 2) tma_store_wait_read<1>();
             else tma_store_wait_read<0>();
           }
           __syncwarp();
-          if (has_res) mbar_wait(&rfull_bar[rb], rphase);
+          if (has_res && !PN_SKIP(4)) mbar_wait(&rfull_bar[rb], rphase);
         }
         // All shared-memory loads of the group are issued back to back (the asm statements keep program order, so
         // interleaving them with the stores would serialise one load-compute-store chain per 16-byte unit).
         const uint32_t sb = sb_addr + grp * 32 * 4;
         float4 bi[8];
-        if (!p.bias_block) {
+        if (!p.bias_block && !PN_SKIP(8)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) bi[j] = lds_f4(sb + j * 16);
         } else {
@@ -659,7 +664,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int j = 0; j < 8; ++j) bi[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         uint4 rv[kUnits];
-        if (has_res) {
+        if (has_res && !PN_SKIP(4)) {
           const uint32_t rbuf = res_addr + rb * chunk_bytes + row_off;
 #pragma unroll
           for (int u = 0; u < kUnits; ++u) rv[u] = lds_v4(rbuf + ((static_cast<uint32_t>(sub * kUnits + u) ^ row_xor) << 4));
@@ -672,7 +677,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bi[j].z;
           y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bi[j].w;
         }
-        if (has_res) {
+        if (has_res && !PN_SKIP(4)) {
 #pragma unroll
           for (int u = 0; u < kUnits; ++u) {
             if constexpr (sizeof(T) == 2) {
@@ -708,7 +713,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ov[u].x = __float_as_uint(a), ov[u].y = __float_as_uint(b), ov[u].z = __float_as_uint(c), ov[u].w = __float_as_uint(d);
           }
         }
-        {
+        if (!PN_SKIP(2)) {
           const uint32_t ob = obuf + row_off;
 #pragma unroll
           for (int u = 0; u < kUnits; ++u)
@@ -720,9 +725,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) {
             if (has_res) mbar_arrive(&rempty_bar[rb]);
             const int n0 = n_tile * BN + (grp - sub) * 32;
-            tma_store_2d_addr(&tmap_out, obuf + quarter * 32 * p.cb, n0,
-                              (kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM + quarter * 32);
-            tma_store_commit();
+            if (!PN_SKIP(1)) {
+              tma_store_2d_addr(&tmap_out, obuf + quarter * 32 * p.cb, n0,
+                                (kPair ? m_tile * 2 + static_cast<int>(cta_rank) : m_tile) * kBlockM + quarter * 32);
+              tma_store_commit();
+            }
           }
           ++g;
           if (has_res && ++rb == static_cast<uint32_t>(p.res_bufs)) rb = 0, rphase ^= 1;
@@ -738,6 +745,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool more_b = grp + 1 < ngroups;
         if (more_b) {
           tmem_ld_32x32(acc_taddr + (grp + 1) * 32, vb);
+          if (PN_SKIP(16)) tmem_ld_wait();
         } else {  // every accumulator column this warp needs is in registers: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();

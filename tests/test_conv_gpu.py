@@ -43,6 +43,15 @@ CASES = [
     (1, 256, 10, 10, 24, 3, 1, 1, 1, (2 << 16) | 32),    # narrow output (24 -> 32-wide tile), 16 columns per rank
 ]
 SPLIT_CASES = [c for c in CASES if c[9] >> 16]
+# two CTAs per SM (force_bn bits 24..25 = 1): half-size shared-memory footprint (one staging buffer, two residual buffers,
+# 64-byte chunks in bf16), grid of 2 x SM count; 0x4000 | 1 << 16 = single CTA tiles, no split-K
+TWO = (1 << 24) | 0x4000 | (1 << 16)
+TWO_CTA_CASES = [
+    (8, 256, 40, 40, 256, 3, 1, 1, 1, TWO | 128),    # 100 m-tiles x 2 n-tiles on 296 CTAs: one tile each, co-resident pairs
+    (6, 512, 30, 30, 2048, 1, 1, 1, 0, TWO | 128),   # conv3-like with residual: 43 x 16 tiles, residual ring of two
+    (8, 64, 100, 136, 64, 3, 1, 1, 1, TWO | 64),     # res2.conv2-like: 850 tiles of 64 columns, several tiles per CTA
+    (4, 64, 48, 48, 256, 1, 1, 1, 0, TWO | 64),      # K = one block
+]
 # CTA pairs (force_bn bit 0x2000): tcgen05.mma.cta_group::2, a 256 x N tile on two SMs, weights split between the CTAs
 PAIR = 0x2000
 PAIR_CASES = [
@@ -114,6 +123,20 @@ def test_conv_pair(ctx, case, precision):
     # pairs forbidden, same split-K factor (1 = none): the K order and the reduction order are then identical
     single = (case[:9] + ((case[9] & 0x3ff) | 0x4000 | (max(case[9] >> 16, 1) << 16),))
     y1, _ = _run(ctx, single, precision)
+    assert torch.equal(y, y1)
+
+
+@pytest.mark.parametrize("precision", [_lib.PN_BF16, _lib.PN_TF32], ids=["bf16", "tf32"])
+@pytest.mark.parametrize("case", TWO_CTA_CASES, ids=[str(c) for c in TWO_CTA_CASES])
+def test_conv_two_ctas_per_sm(ctx, case, precision):
+    if precision == _lib.PN_TF32 and (case[9] & 0x3ff) == 128:
+        pytest.skip("tf32 staging buffers + two 32 KB stages exceed half an SM's shared memory at 128 columns with a residual")
+    y, ref = _run(ctx, case, precision)
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= (1e-2 if precision == _lib.PN_BF16 else 3e-3) * scale, f"max abs err {err} vs scale {scale}"
+    # same tiles, same K order, same epilogue arithmetic as the one-CTA-per-SM launch: bit-identical
+    y1, _ = _run(ctx, case[:9] + ((case[9] & 0x3ff) | 0x4000 | (1 << 16),), precision)
     assert torch.equal(y, y1)
 
 

@@ -545,11 +545,19 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
       Cand best_c{1e30, bn, splits, pair};
       for (const Cand& c : shortlist) {
         float ms = 0.f;
+        static const bool log = std::getenv("PN_CONV_TUNE_LOG") != nullptr;  // one line per timed configuration (stderr)
         try {
           Variant v = make_variant(c.bn, c.splits, c.pair, c.opt);
           v.p.m_limit = nullptr;  // time the full-capacity launch
+          if (log) {
+            std::fprintf(stderr, "[tune] %s M=%lld: tile %d splits %d pair %d opt %d grid %d smem %zu stages %d ...", name.c_str(), M,
+                         c.bn, c.splits, c.pair ? 1 : 0, c.opt, v.grid, v.smem, v.p.stages);
+            std::fflush(stderr);
+          }
           ms = time_launches([&](cudaStream_t s) { launch_variant(v, s); });
-        } catch (const std::exception&) {
+          if (log) std::fprintf(stderr, " %.1f us\n", ms * 1e3f);
+        } catch (const std::exception& e) {
+          if (log) std::fprintf(stderr, " skipped (%s)\n", e.what());
           cudaGetLastError();
           continue;
         }

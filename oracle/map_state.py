@@ -32,22 +32,24 @@ def disk_idx(radius):
     return np.where((xx ** 2 + yy ** 2) <= radius ** 2)
 
 
+def _window_start(centre, local_n, full_n, grid):
+    """One axis of the window: centred on the agent, snapped down to the grid, pushed back inside the full map."""
+    start = centre - local_n // 2
+    start -= start % grid            # Python modulo: non-negative, so this snaps DOWN also for negative starts
+    if start < 0:
+        start = 0
+    if start + local_n > full_n:
+        start = full_n - local_n
+    return start
+
+
 def boundaries(loc_r, loc_c, local_w, local_h, full_w, full_h, global_downscaling, grid_resolution):
-    if global_downscaling > 1:
-        gx1, gy1 = loc_r - local_w // 2, loc_c - local_h // 2
-        gx1, gy1 = gx1 - gx1 % grid_resolution, gy1 - gy1 % grid_resolution
-        gx2, gy2 = gx1 + local_w, gy1 + local_h
-        if gx1 < 0:
-            gx1, gx2 = 0, local_w
-        if gx2 > full_w:
-            gx1, gx2 = full_w - local_w, full_w
-        if gy1 < 0:
-            gy1, gy2 = 0, local_h
-        if gy2 > full_h:
-            gy1, gy2 = full_h - local_h, full_h
-    else:
-        gx1, gx2, gy1, gy2 = 0, full_w, 0, full_h
-    return [gx1, gx2, gy1, gy2]
+    """[row0, row1, col0, col1] of the local window (agent_state.py:153-177)."""
+    if global_downscaling <= 1:
+        return [0, full_w, 0, full_h]
+    r0 = _window_start(loc_r, local_w, full_w, grid_resolution)
+    c0 = _window_start(loc_c, local_h, full_h, grid_resolution)
+    return [r0, r0 + local_w, c0, c0 + local_h]
 
 
 class MapState:

@@ -292,7 +292,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
           const double bytes = static_cast<double>(kbs) * block_k * es * (kBlockM + cand / 2);
           const double t_mem = bytes / std::min(125e9, 14e12 / active);
           const double t_mma = static_cast<double>(kbs) * block_k * es / 32.0 * std::max(cand / 2.0, 32.0) / 1.9e9;
-          // the epilogue of a 128 x cand tile takes ~0.5 us per 32 columns (shared-memory bound, measured) and overlaps
+          // the epilogue of a 128 x cand tile takes ~0.5 us per 32 columns (issue-bound: one epilogue warp per SM sub-partition, measured) and overlaps
           // the next tile's main loop; pairs only pay off where the main loop is the longer of the two
           const double t_epi = 0.5e-6 * cand / 32.0 / s;
           const double t_red = s > 1 ? 1.5e-6 + 2.0 * kBlockM * cand * 4.0 / 200e9 : 0.0;

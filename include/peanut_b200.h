@@ -170,6 +170,16 @@ int pn_map_update_local(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays*
 /* update_full_map (:308-338): window written back, window recentred on the agent, local map and pose re-cut. */
 int pn_map_update_full(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* arrays, int E, void* stream);
 
+/* Head of Agent_State.update_prediction (:350-360), for E environments, without the reference's device->host->device round
+ * trip of the window.  pn_map_stamp_local: full_map[e, :, lmb0:lmb1, lmb2:lmb3] = local_map[e] (:350-351; lmb [E,4] device).
+ * pn_map_crop_window: window_out[e, c] = full_map[e, c, x1:x1+win_w, y1:y1+win_h] for c < copy_channels (:357-360, or the whole
+ * map when the window is the map, :353-354); window_out is [E, out_channels, win_w, win_h] and its planes >= copy_channels are
+ * left untouched (a caller whose completion net takes more input planes than the map has keeps its own there). */
+int pn_map_stamp_local(pn_ctx* ctx, const float* local_map_dev, float* full_map_dev, const int* lmb_dev, int E, int num_channels,
+                       int local_w, int local_h, int full_w, int full_h, void* stream);
+int pn_map_crop_window(pn_ctx* ctx, const float* full_map_dev, int E, int num_channels, int full_w, int full_h, int x1, int y1,
+                       int win_w, int win_h, int copy_channels, float* window_out_dev, int out_channels, void* stream);
+
 /* Agent_State.update_goal_map (:423-452), every step, for E environments: goal_map_out [E, local_w, local_h] fp32 = the
  * cells of category channel goal_cat + 4 (binarised; eroded goal_erode times and dilated once with the 4-neighbour cross
  * unless skip_morph[e] != 0, the reference's "'tv' in goal_name") that carry no OTHER category of channels 4..9;
@@ -200,8 +210,8 @@ typedef struct pn_semmap_cfg {
   int vision_range;        /* 100 */
   int du_scale;            /* 1 (only value supported) */
   int num_sem_categories;  /* 10 */
-  float hfov;              /* 79 */
-  float camera_height;     /* 0.88 (m) */
+  double hfov;             /* 79; double: f = (w/2) / tan(deg2rad(hfov/2)) is evaluated in Python float (depth_utils.py:31, mapping.py:36) */
+  double camera_height;    /* 0.88 (m); double: max_z = int((camera_height*100 + 1)/res - min_h) (mapping.py:33, 103) */
   float cat_pred_threshold; /* 5.0 */
   float exp_pred_threshold; /* 1.0 */
   float map_pred_threshold; /* 0.1 */
@@ -219,6 +229,18 @@ int pn_semmap_forward(pn_ctx* ctx, const float* obs_dev, const float* pose_delta
  * stair-mask decision (mapping.py:94).  Either pointer may be NULL. */
 int pn_semmap_read_ego(pn_ctx* ctx, float* ego_out_dev, int* stair_flags_out_dev, void* stream);
 int pn_semmap_num_launches(pn_ctx* ctx);
+
+/* ---- Launch-configuration table of the tensor-core conv kernel.  At *_build time every conv layer picks its launch
+ * configuration (N tile, split-K factor, CTA pair, CTAs per SM) from this process-wide table; a layer that is not in it
+ * times a shortlist on its own buffers and adds the winner (PN_CONV_AUTOTUNE=table: never time, use the tile model's
+ * choice instead; =0: ignore the table too).  Different configurations differ in fp32 summation order, so processes that
+ * must produce bit-identical results (the ranks of one job) import the same table before building: text = lines
+ * "key bn splits pair opt" as written by pn_conv_tuning_export ('#' starts a comment).  There is no reference counterpart
+ * (cuDNN picks its algorithms behind mmcv / detectron2). */
+int pn_conv_tuning_import(const char* text, int* entries_out);
+/* Writes the table as text into buf (NUL-terminated); *needed_out = bytes required.  buf may be NULL to query the size. */
+int pn_conv_tuning_export(char* buf, int64_t buf_bytes, int64_t* needed_out);
+int pn_conv_tuning_clear(void);
 
 /* ---- Single fused convolution (conv + per-channel scale/bias + optional residual + ReLU), used by the
  * parity tests of the tensor-core kernel against torch.nn.functional.conv2d.

@@ -16,6 +16,18 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 PN_BF16 = 0
 PN_TF32 = 1
 
+
+
+def precision_code(precision):
+    """"tf32" (fp32 storage, tf32 tensor-core operands, fp32 accumulate: the fp32-parity path) or "bf16" (throughput path).
+    There is no plain-fp32 arithmetic on the tensor cores, so "fp32" is rejected instead of being silently mapped to tf32."""
+    try:
+        return {"bf16": PN_BF16, "tf32": PN_TF32}[precision]
+    except KeyError:
+        raise ValueError(f"precision must be 'tf32' or 'bf16', got {precision!r} "
+                         "(the fp32-parity path computes with tf32 operands; ask for it as 'tf32')") from None
+
+
 _c_float_p = ctypes.POINTER(ctypes.c_float)
 _c_i64_p = ctypes.POINTER(ctypes.c_int64)
 
@@ -57,12 +69,18 @@ PROTOTYPES = {
     "pn_map_stamp_initial": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_map_update_local": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_map_update_full": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pn_map_stamp_local": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "pn_map_crop_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_void_p, ctypes.c_int,
+                                                                                                  ctypes.c_void_p]),
     "pn_goal_map": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3 + [ctypes.c_int] +
                     [ctypes.c_void_p] * 3),
     "pn_semmap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
     "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "pn_semmap_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_conv_tuning_import": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p]),
+    "pn_conv_tuning_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "pn_conv_tuning_clear": (ctypes.c_int, []),
     "pn_conv_bench": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 14 + [ctypes.c_void_p, ctypes.c_void_p]),
     "pn_conv2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                   [ctypes.c_void_p] * 4 + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
@@ -74,8 +92,8 @@ class SemMapCfg(ctypes.Structure):
     """struct pn_semmap_cfg"""
     _fields_ = [("frame_height", ctypes.c_int), ("frame_width", ctypes.c_int), ("map_resolution", ctypes.c_int),
                 ("map_size_cm", ctypes.c_int), ("global_downscaling", ctypes.c_int), ("vision_range", ctypes.c_int),
-                ("du_scale", ctypes.c_int), ("num_sem_categories", ctypes.c_int), ("hfov", ctypes.c_float),
-                ("camera_height", ctypes.c_float), ("cat_pred_threshold", ctypes.c_float),
+                ("du_scale", ctypes.c_int), ("num_sem_categories", ctypes.c_int), ("hfov", ctypes.c_double),
+                ("camera_height", ctypes.c_double), ("cat_pred_threshold", ctypes.c_float),
                 ("exp_pred_threshold", ctypes.c_float), ("map_pred_threshold", ctypes.c_float)]
 
 
@@ -146,7 +164,50 @@ def load():
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = lib
+    _load_default_tuning(lib)
     return lib
+
+
+TUNING_DIR = os.path.join(_HERE, "tuning")
+
+
+def _load_default_tuning(lib):
+    """Import the committed launch-configuration tables (peanut_b200/tuning/*.txt) and $PN_CONV_TUNING_FILE, so that every
+    process - in particular every rank of one job - builds identical networks without timing anything for the shapes the
+    tables cover.  PN_CONV_TUNING_FILE=none skips the committed tables."""
+    override = os.environ.get("PN_CONV_TUNING_FILE", "")
+    paths = []
+    if override != "none" and os.path.isdir(TUNING_DIR):
+        paths += sorted(os.path.join(TUNING_DIR, f) for f in os.listdir(TUNING_DIR) if f.endswith(".txt"))
+    if override and override != "none":
+        if not os.path.exists(override):
+            raise RuntimeError(f"PN_CONV_TUNING_FILE={override} does not exist")
+        paths.append(override)
+    for p in paths:
+        with open(p, "rb") as f:
+            tuning_import(f.read(), lib)
+
+
+def tuning_import(text, lib=None):
+    """text: bytes / str in the format of tuning_export(); returns the number of entries read."""
+    lib = lib or load()
+    if isinstance(text, str):
+        text = text.encode()
+    n = ctypes.c_int(0)
+    st = lib.pn_conv_tuning_import(text, ctypes.byref(n))
+    if st != 0:
+        raise RuntimeError("peanut_b200: " + lib.pn_last_error().decode("utf-8", "replace"))
+    return n.value
+
+
+def tuning_export():
+    """The process-wide launch-configuration table as text (one "key bn splits pair opt" line per conv shape)."""
+    lib = load()
+    need = ctypes.c_int64(0)
+    check(lib.pn_conv_tuning_export(None, 0, ctypes.byref(need)))
+    buf = ctypes.create_string_buffer(need.value + 16)
+    check(lib.pn_conv_tuning_export(buf, len(buf), None))
+    return buf.value.decode()
 
 
 def check(status):

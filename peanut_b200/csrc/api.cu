@@ -116,7 +116,7 @@ using namespace pn;
 extern "C" {
 
 const char* pn_last_error(void) { return g_last_error.c_str(); }
-int pn_abi_version(void) { return 1; }
+int pn_abi_version(void) { return 2; }
 
 int pn_create(int device, pn_ctx** out) {
   PN_API_BEGIN
@@ -198,8 +198,10 @@ int pn_prednet_forward(pn_ctx* ctx, const float* map_dev, int apply_sigmoid, flo
   PN_REQUIRE(c->prednet, "pn_prednet_forward: call pn_prednet_build first");
   PN_REQUIRE(map_dev && out_dev, "pn_prednet_forward: null buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  c->prednet->net.begin_forward(s);
   launch_pdl(set_pred_slots_kernel, 1, 1, 0, s, c->prednet->slots, map_dev, out_dev, apply_sigmoid);
   c->prednet->net.run(s);
+  c->prednet->net.end_forward(s);
   PN_CUDA_CHECK(cudaGetLastError());
   PN_API_END
 }
@@ -216,9 +218,11 @@ int pn_prednet_forward_host(pn_ctx* ctx, const float* map_host, int apply_sigmoi
     n.stage_in = static_cast<float*>(n.net.arena.alloc(in_bytes, false));
     n.stage_out = static_cast<float*>(n.net.arena.alloc(out_bytes, false));
   }
+  n.net.begin_forward(c->stream);
   PN_CUDA_CHECK(cudaMemcpyAsync(n.stage_in, map_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
   launch_pdl(set_pred_slots_kernel, 1, 1, 0, c->stream, n.slots, n.stage_in, n.stage_out, apply_sigmoid);
   n.net.run(c->stream);
+  n.net.end_forward(c->stream);
   PN_CUDA_CHECK(cudaMemcpyAsync(out_host, n.stage_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   PN_API_END
@@ -271,7 +275,7 @@ int pn_semmap_build(pn_ctx* ctx, int num_envs, const pn_semmap_cfg* cfg) {
   const int res = cfg->map_resolution;
   const int max_h = static_cast<int>(360.0 / res), min_h = static_cast<int>(-40.0 / res);
   g.nz = max_h - min_h;
-  const double agent_height = static_cast<double>(cfg->camera_height) * 100.0;
+  const double agent_height = cfg->camera_height * 100.0;  // Python float arithmetic of mapping.py:33
   g.min_z = static_cast<int>(25.0 / res - min_h);
   g.max_z = static_cast<int>((agent_height + 1) / res - min_h);
   g.map_cells = (cfg->map_size_cm / cfg->global_downscaling) / res;
@@ -282,7 +286,8 @@ int pn_semmap_build(pn_ctx* ctx, int num_envs, const pn_semmap_cfg* cfg) {
   }
   g.xc = static_cast<float>((g.w - 1.0) / 2.0);
   g.zc = static_cast<float>((g.h - 1.0) / 2.0);
-  g.f = static_cast<float>((g.w / 2.0) / std::tan(static_cast<double>(cfg->hfov) / 2.0 * 3.14159265358979323846 / 180.0));
+  // (w / 2.) / np.tan(np.deg2rad(fov / 2.)), depth_utils.py get_camera_matrix; deg2rad(x) = x * (pi / 180)
+  g.f = static_cast<float>((g.w / 2.0) / std::tan((cfg->hfov / 2.0) * (3.14159265358979323846 / 180.0)));
   g.agent_height = static_cast<float>(agent_height);
   g.shift_x = static_cast<float>(g.vr * res / 2);
   g.res = static_cast<float>(res);
@@ -432,8 +437,10 @@ int pn_maskrcnn_forward(pn_ctx* ctx, const uint8_t* rgb_dev, const int* goal_cat
   PN_REQUIRE(c->maskrcnn, "pn_maskrcnn_forward: call pn_maskrcnn_build first");
   PN_REQUIRE(rgb_dev && sem_out_dev, "pn_maskrcnn_forward: null buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  c->maskrcnn->net.begin_forward(s);
   set_mrcnn_slots(*c->maskrcnn, rgb_dev, goal_cat_dev, score_thresh, sem_pred_prob_thr, goal_thr, sem_out_dev, s);
   c->maskrcnn->net.run(s);
+  c->maskrcnn->net.end_forward(s);
   PN_CUDA_CHECK(cudaGetLastError());
   PN_API_END
 }
@@ -452,6 +459,7 @@ int pn_maskrcnn_forward_host(pn_ctx* ctx, const uint8_t* rgb_host, const int* go
     m.stage_sem = static_cast<float*>(m.net.arena.alloc(out_bytes, false));
   }
   int* goal_dev = nullptr;
+  m.net.begin_forward(c->stream);
   PN_CUDA_CHECK(cudaMemcpyAsync(m.stage_rgb, rgb_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
   if (goal_cat_host) {
     goal_dev = reinterpret_cast<int*>(m.stage_rgb + ((in_bytes + 3) & ~size_t(3)));
@@ -459,6 +467,7 @@ int pn_maskrcnn_forward_host(pn_ctx* ctx, const uint8_t* rgb_host, const int* go
   }
   set_mrcnn_slots(m, m.stage_rgb, goal_dev, score_thresh, sem_pred_prob_thr, goal_thr, m.stage_sem, c->stream);
   m.net.run(c->stream);
+  m.net.end_forward(c->stream);
   PN_CUDA_CHECK(cudaMemcpyAsync(sem_out_host, m.stage_sem, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   PN_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   PN_API_END
@@ -609,6 +618,34 @@ int pn_map_update_full(pn_ctx* ctx, const pn_map_cfg* cfg, const pn_map_arrays* 
   return map_call(ctx, 3, cfg, arrays, E, stream);
 }
 
+int pn_map_stamp_local(pn_ctx* ctx, const float* local_map_dev, float* full_map_dev, const int* lmb_dev, int E, int num_channels,
+                       int local_w, int local_h, int full_w, int full_h, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(local_map_dev && full_map_dev && lmb_dev, "pn_map_stamp_local: null buffer");
+  PN_REQUIRE(E > 0 && num_channels > 0 && local_w > 0 && local_h > 0 && local_w <= full_w && local_h <= full_h,
+             "pn_map_stamp_local: bad geometry");
+  launch_map_stamp_local(local_map_dev, full_map_dev, lmb_dev, E, num_channels, local_w, local_h, full_w, full_h,
+                         static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
+int pn_map_crop_window(pn_ctx* ctx, const float* full_map_dev, int E, int num_channels, int full_w, int full_h, int x1, int y1,
+                       int win_w, int win_h, int copy_channels, float* window_out_dev, int out_channels, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(full_map_dev && window_out_dev, "pn_map_crop_window: null buffer");
+  PN_REQUIRE(E > 0 && copy_channels > 0 && copy_channels <= num_channels && copy_channels <= out_channels,
+             "pn_map_crop_window: bad channel counts");
+  PN_REQUIRE(x1 >= 0 && y1 >= 0 && win_w > 0 && win_h > 0 && x1 + win_w <= full_w && y1 + win_h <= full_h,
+             "pn_map_crop_window: window outside the full map");
+  launch_map_crop(full_map_dev, E, num_channels, full_w, full_h, x1, y1, win_w, win_h, copy_channels, window_out_dev, out_channels,
+                  static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
 int pn_goal_map(pn_ctx* ctx, const float* local_map_dev, int E, int num_channels, int local_w, int local_h,
                 const int* goal_cat_dev, const int* skip_morph_dev, const int* global_goal_dev, int goal_erode,
                 float* goal_map_out_dev, int* found_goal_out_dev, void* stream) {
@@ -620,6 +657,31 @@ int pn_goal_map(pn_ctx* ctx, const float* local_map_dev, int E, int num_channels
   PN_REQUIRE(E > 0 && num_channels >= 5 && local_w > 0 && local_h > 0, "pn_goal_map: bad geometry");
   launch_goal_map(local_map_dev, E, num_channels, local_w, local_h, goal_cat_dev, skip_morph_dev, global_goal_dev, goal_erode,
                   goal_map_out_dev, found_goal_out_dev, static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
+int pn_conv_tuning_import(const char* text, int* entries_out) {
+  PN_API_BEGIN
+  PN_REQUIRE(text != nullptr, "pn_conv_tuning_import: null text");
+  const int n = conv_tuning_import(text);
+  if (entries_out) *entries_out = n;
+  PN_API_END
+}
+
+int pn_conv_tuning_export(char* buf, int64_t buf_bytes, int64_t* needed_out) {
+  PN_API_BEGIN
+  const std::string t = conv_tuning_export();
+  if (needed_out) *needed_out = static_cast<int64_t>(t.size()) + 1;
+  if (buf && buf_bytes > 0) {
+    PN_REQUIRE(static_cast<size_t>(buf_bytes) > t.size(), "pn_conv_tuning_export: buffer too small");
+    std::memcpy(buf, t.c_str(), t.size() + 1);
+  }
+  PN_API_END
+}
+
+int pn_conv_tuning_clear(void) {
+  PN_API_BEGIN
+  conv_tuning_clear();
   PN_API_END
 }
 

@@ -8,6 +8,10 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <chrono>
+#include <mutex>
+#include <sstream>
+#include <thread>
 
 #include "conv_umma.cuh"
 #include "engine.h"
@@ -104,7 +108,7 @@ void launch_conv(const ConvMaps& tm, const ConvParams& p, int grid, size_t smem,
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kNumThreads), cfg.dynamicSmemBytes = smem, cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = debug_no_pdl() ? 0 : 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
   if (kSplit || kPair) {  // one thread-block cluster per output tile (split-K) / one SM pair per 256-row tile
     attr[1].id = cudaLaunchAttributeClusterDimension;
@@ -164,17 +168,33 @@ int tune_extra() {
   return v;
 }
 
-bool autotune_enabled() {
-  static const bool on = [] {
+// PN_CONV_AUTOTUNE: "0" = the tile model's choice only (no table, no timing); "table" = the imported table, else the model's
+// choice (never times anything: strictly reproducible); anything else / unset = the table, else time the shortlist.
+int autotune_mode() {
+  static const int mode = [] {
     const char* e = std::getenv("PN_CONV_AUTOTUNE");
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0') return 0;
+    if (e && std::strcmp(e, "table") == 0) return 1;
+    return 2;
   }();
-  return on;
+  return mode;
+}
+
+struct TuneEntry {
+  int bn = 0, splits = 1, pair = 0, opt = 0;
+};
+std::mutex g_tune_mu;
+std::map<std::string, TuneEntry>& tune_table() {
+  static std::map<std::string, TuneEntry> t;
+  return t;
 }
 
 // Average time of back-to-back launches (2 warm-up + 6 timed) on a private stream, in milliseconds.
+// Watchdog: a launch configuration that has not finished after kTuneWatchdogMs cannot be cancelled (a running kernel can
+// only be removed with its context), so the process reports WHICH configuration it was and exits instead of hanging the box.
+constexpr int kTuneWatchdogMs = 8000;
 template <typename F>
-float time_launches(F&& launch) {
+float time_launches(F&& launch, const char* what) {
   static cudaStream_t stream = nullptr;
   static cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (!stream) {
@@ -187,7 +207,19 @@ float time_launches(F&& launch) {
   PN_CUDA_CHECK(cudaEventRecord(e0, stream));
   for (int i = 0; i < 6; ++i) launch(stream);
   PN_CUDA_CHECK(cudaEventRecord(e1, stream));
-  PN_CUDA_CHECK(cudaStreamSynchronize(stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t q = cudaEventQuery(e1);
+    if (q == cudaSuccess) break;
+    if (q != cudaErrorNotReady) PN_CUDA_CHECK(q);
+    const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > kTuneWatchdogMs) {
+      std::fprintf(stderr, "peanut_b200: conv launch configuration did not finish within %d ms: %s\n", kTuneWatchdogMs, what);
+      std::fflush(stderr);
+      std::_Exit(97);
+    }
+    if (ms > 2) std::this_thread::sleep_for(std::chrono::microseconds(200));
+  }
   float ms = 0.f;
   PN_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   return ms / 6.f;
@@ -513,14 +545,24 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   // the model's choice; test hooks (force_*) bypass both.
   int opt = sp.force_opt;
   const bool forced = sp.force_opt || sp.force_bn || sp.force_splits || sp.force_pair || sp.force_direct_epilogue || sp.dbg;
-  if (!forced && autotune_enabled() && cands.size() > 1) {
-    char key[256];
-    std::snprintf(key, sizeof(key), "%d|%lld|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d", static_cast<int>(dt), M, Wo, cin_pad, sp.Cout, sp.R,
-                  sp.S, sp.stride, stride_w, sp.dil, residual ? 1 : 0, out.dt == dt ? 0 : 1, sp.relu ? 1 : 0,
-                  sp.no_split ? 1 : 0, std::min(round_up(sp.Cout, 8), out.C));
-    static std::map<std::string, Cand> cache;
-    auto it = cache.find(key);
-    if (it == cache.end()) {
+  if (!forced && autotune_mode() != 0 && cands.size() > 1) {
+    // The key holds everything the candidate set and the timings depend on (incl. padding, the dynamic-row-limit flag, the
+    // device's SM count and the opt-in modes), so an entry is only ever reused for an identical launch problem.
+    char key[320];
+    std::snprintf(key, sizeof(key), "%d|%lld|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d", static_cast<int>(dt), M, Wo,
+                  cin_pad, sp.Cout, sp.R, sp.S, sp.stride, stride_w, sp.dil, residual ? 1 : 0, out.dt == dt ? 0 : 1,
+                  sp.relu ? 1 : 0, sp.no_split ? 1 : 0, std::min(round_up(sp.Cout, 8), out.C), sp.pad, pad_w,
+                  sp.m_limit ? sp.m_limit_rows : 0, net.num_sms, tune_extra());
+    std::lock_guard<std::mutex> lock(g_tune_mu);  // one tuner at a time (it owns the device while it measures)
+    auto& table = tune_table();
+    auto it = table.find(key);
+    bool usable = false;
+    if (it != table.end()) {  // an imported entry must name one of this layer's valid configurations
+      const TuneEntry& e = it->second;
+      for (const Cand& c : cands) usable |= (c.bn == e.bn && c.splits == e.splits && c.pair == (e.pair != 0));
+      if (e.opt & 1) usable = usable && !e.pair && e.splits == 1 && e.bn <= 128;
+    }
+    if (!usable && autotune_mode() == 2) {
       std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.t < b.t; });
       std::vector<Cand> shortlist(cands.begin(), cands.begin() + std::min<size_t>(cands.size(), 6));
       bool has_model = false;
@@ -549,23 +591,31 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
         try {
           Variant v = make_variant(c.bn, c.splits, c.pair, c.opt);
           v.p.m_limit = nullptr;  // time the full-capacity launch
+          char what[320];
+          std::snprintf(what, sizeof(what), "%s M=%lld tile %d splits %d pair %d opt %d grid %d smem %zu stages %d", name.c_str(), M, c.bn,
+                        c.splits, c.pair ? 1 : 0, c.opt, v.grid, v.smem, v.p.stages);
           if (log) {
-            std::fprintf(stderr, "[tune] %s M=%lld: tile %d splits %d pair %d opt %d grid %d smem %zu stages %d ...", name.c_str(), M,
-                         c.bn, c.splits, c.pair ? 1 : 0, c.opt, v.grid, v.smem, v.p.stages);
+            std::fprintf(stderr, "[tune] %s ...", what);
             std::fflush(stderr);
           }
-          ms = time_launches([&](cudaStream_t s) { launch_variant(v, s); });
+          ms = time_launches([&](cudaStream_t s) { launch_variant(v, s); }, what);
           if (log) std::fprintf(stderr, " %.1f us\n", ms * 1e3f);
         } catch (const std::exception& e) {
           if (log) std::fprintf(stderr, " skipped (%s)\n", e.what());
-          cudaGetLastError();
+          cudaGetLastError();  // clears a launch-configuration error; anything sticky (a faulted kernel) is fatal
+          const cudaError_t st = cudaDeviceSynchronize();
+          PN_REQUIRE(st == cudaSuccess, name + ": CUDA error while timing a launch configuration: " + cudaGetErrorString(st));
           continue;
         }
         if (ms < best_c.t * (c.opt ? 0.97 : 1.0)) best_c = {ms, c.bn, c.splits, c.pair, c.opt};  // options must win clearly
       }
-      it = cache.emplace(key, best_c).first;
+      TuneEntry e;
+      e.bn = best_c.bn, e.splits = best_c.splits, e.pair = best_c.pair ? 1 : 0, e.opt = best_c.opt;
+      table[key] = e;
+      it = table.find(key);
+      usable = true;
     }
-    bn = it->second.bn, splits = it->second.splits, pair = it->second.pair, opt = it->second.opt;
+    if (usable) bn = it->second.bn, splits = it->second.splits, pair = it->second.pair != 0, opt = it->second.opt;
   }
   net.last_bn = bn + 1000 * splits + (pair ? 100000 : 0) + 1000000 * opt;
   const Variant chosen = make_variant(bn, splits, pair, opt);
@@ -573,6 +623,37 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   const double flops = 2.0 * static_cast<double>(M) * sp.Cout * sp.Cin * taps;
   net.add(name, [=](cudaStream_t s) { launch_variant(chosen, s); }, flops);
   net.launches_per_forward += 1;
+}
+
+std::string conv_tuning_export() {
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  std::ostringstream os;
+  for (const auto& kv : tune_table())
+    os << kv.first << ' ' << kv.second.bn << ' ' << kv.second.splits << ' ' << kv.second.pair << ' ' << kv.second.opt << '\n';
+  return os.str();
+}
+
+int conv_tuning_import(const std::string& text) {
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  std::istringstream is(text);
+  std::string line;
+  int n = 0;
+  while (std::getline(is, line)) {
+    if (line.empty() || line[0] == '#') continue;
+    std::istringstream ls(line);
+    std::string key;
+    TuneEntry e;
+    if (!(ls >> key >> e.bn >> e.splits >> e.pair >> e.opt)) throw std::runtime_error("peanut_b200: malformed tuning line: " + line);
+    PN_REQUIRE((e.bn == 32 || e.bn == 64 || e.bn == 128 || e.bn == 256) && e.splits >= 1 && e.splits <= 8, "bad tuning entry: " + line);
+    tune_table()[key] = e;
+    ++n;
+  }
+  return n;
+}
+
+void conv_tuning_clear() {
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  tune_table().clear();
 }
 
 }  // namespace pn

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <stdexcept>
@@ -42,13 +43,25 @@ __device__ __forceinline__ void pdl_grid_sync() {
 }
 #endif
 
+// Diagnosis switches (environment, read once): PN_DEBUG_NO_PDL=1 launches every kernel with plain stream serialization,
+// PN_DEBUG_NO_LANES=1 puts every op on the caller's stream, PN_DEBUG_NO_GRAPH=1 replays the launch list eagerly,
+// PN_DEBUG_SYNC_EACH=1 synchronises after every op of an eager pass with a watchdog that names the op that did not finish.
+inline bool debug_flag(const char* name) {
+  const char* e = std::getenv(name);
+  return e && e[0] && e[0] != '0';
+}
+inline bool debug_no_pdl() {
+  static const bool v = debug_flag("PN_DEBUG_NO_PDL");
+  return v;
+}
+
 template <typename... P, typename... A>
 inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = debug_no_pdl() ? 0 : 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
   PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...));
 }
@@ -176,6 +189,21 @@ struct Net {
     for (double f : op_flops) t += f;
     return t;
   }
+  // Cross-stream ordering of successive forwards: the launch list owns one set of activations / per-call slots, so a
+  // forward enqueued on stream B must not start (nor have its slots rewritten) while the previous one, enqueued on stream
+  // A, is still in flight.  begin_forward(s) makes s wait for the previous forward when it ran on another stream;
+  // end_forward(s) marks this one.  Same-stream callers pay nothing.
+  cudaEvent_t fwd_done = nullptr;
+  cudaStream_t fwd_stream = nullptr;
+  bool fwd_pending = false;
+  void begin_forward(cudaStream_t s) {
+    if (fwd_pending && fwd_stream != s) PN_CUDA_CHECK(cudaStreamWaitEvent(s, fwd_done, 0));
+  }
+  void end_forward(cudaStream_t s) {
+    if (!fwd_done) PN_CUDA_CHECK(cudaEventCreateWithFlags(&fwd_done, cudaEventDisableTiming));
+    PN_CUDA_CHECK(cudaEventRecord(fwd_done, s));
+    fwd_stream = s, fwd_pending = true;
+  }
   void run_eager(cudaStream_t s);
   void run_range(int first, int last, cudaStream_t s) {
     for (int i = first; i < last; ++i) ops[i](s);
@@ -217,6 +245,11 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
 // Folds BatchNorm running statistics into (scale, bias): y = x*scale + bias, eps as in nn.BatchNorm2d.
 void fold_bn(const WeightStore& w, const std::string& bn_prefix, int C, std::vector<float>& scale,
              std::vector<float>& bias, float eps = 1e-5f);
+// Launch-configuration table of add_conv (conv_host.cu): "key bn splits pair opt" lines.  Entries that are present are used
+// without timing, so every process that imports the same table builds bit-identical networks.
+std::string conv_tuning_export();
+int conv_tuning_import(const std::string& text);  // returns the number of entries read
+void conv_tuning_clear();
 inline int conv_out(int in, int k, int stride, int dil, int pad) {
   return (in + 2 * pad - dil * (k - 1) - 1) / stride + 1;
 }

@@ -302,7 +302,47 @@ void launch_window(const MapCfg& cfg, const MapArrays& a, int E, cudaStream_t s)
   else launch_pdl(k_map_window<kToFull, float>, grid, dim3(256), 0, s, cfg, a);
 }
 
+// Prediction window of update_prediction (:353-360): out[e, c, r, :] = full_map[e, c, x1 + r, y1 : y1 + win_h] for c < nc_copy.
+// grid (x, nc_copy, E); out has out_channels planes per environment (planes >= nc_copy are left alone).
+template <typename V>
+__global__ void __launch_bounds__(256) k_map_crop(const float* __restrict__ full, int nc, int full_w, int full_h, int x1, int y1,
+                                                  int win_w, int win_h, float* __restrict__ out, int out_channels) {
+  pdl_grid_sync();
+  constexpr int kVec = sizeof(V) / 4;
+  const int e = blockIdx.z, ch = blockIdx.y;
+  const int wv = win_h / kVec;
+  const size_t n = static_cast<size_t>(win_w) * wv;
+  const float* src = full + (static_cast<size_t>(e) * nc + ch) * full_w * full_h;
+  float* dst = out + (static_cast<size_t>(e) * out_channels + ch) * win_w * win_h;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / wv), c = static_cast<int>(i - static_cast<size_t>(r) * wv) * kVec;
+    *reinterpret_cast<V*>(dst + static_cast<size_t>(r) * win_h + c) =
+        *reinterpret_cast<const V*>(src + static_cast<size_t>(x1 + r) * full_h + y1 + c);
+  }
+}
+
 }  // namespace
+
+void launch_map_stamp_local(const float* local_map, float* full_map, const int* lmb, int E, int nc, int local_w, int local_h,
+                            int full_w, int full_h, cudaStream_t s) {
+  MapCfg cfg{};
+  cfg.nc = nc, cfg.full_w = full_w, cfg.full_h = full_h, cfg.local_w = local_w, cfg.local_h = local_h;
+  MapArrays a{};
+  a.full_map = full_map, a.local_map = const_cast<float*>(local_map), a.lmb = const_cast<int*>(lmb);
+  launch_window<true>(cfg, a, E, s);
+  PN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_map_crop(const float* full_map, int E, int nc, int full_w, int full_h, int x1, int y1, int win_w, int win_h,
+                     int nc_copy, float* out, int out_channels, cudaStream_t s) {
+  const bool vec = win_h % 4 == 0 && full_h % 4 == 0 && y1 % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(full_map) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+  const size_t n = static_cast<size_t>(win_w) * win_h / (vec ? 4 : 1);
+  const dim3 grid(static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 64)), nc_copy, E);
+  if (vec) launch_pdl(k_map_crop<float4>, grid, dim3(256), 0, s, full_map, nc, full_w, full_h, x1, y1, win_w, win_h, out, out_channels);
+  else launch_pdl(k_map_crop<float>, grid, dim3(256), 0, s, full_map, nc, full_w, full_h, x1, y1, win_w, win_h, out, out_channels);
+  PN_CUDA_CHECK(cudaGetLastError());
+}
 
 void map_bookkeeping(int op, const pn_map_cfg& c, const pn_map_arrays& arr, int E, cudaStream_t s) {
   MapCfg cfg{c.num_channels, c.full_w, c.full_h, c.local_w, c.local_h, c.map_resolution, c.map_size_cm, c.global_downscaling,

@@ -102,6 +102,10 @@ void launch_make_obs(const float* depth, const uint8_t* rgb, const float* sem, i
                      int nsem, float min_d, float max_d, float* obs, cudaStream_t s);
 
 // mapstate.cu: op 0 init_map_and_pose, 1 init_with_obs stamp, 2 update_local_map tail, 3 update_full_map
+void launch_map_stamp_local(const float* local_map, float* full_map, const int* lmb, int E, int nc, int local_w, int local_h,
+                            int full_w, int full_h, cudaStream_t s);
+void launch_map_crop(const float* full_map, int E, int nc, int full_w, int full_h, int x1, int y1, int win_w, int win_h,
+                     int nc_copy, float* out, int out_channels, cudaStream_t s);
 void map_bookkeeping(int op, const pn_map_cfg& cfg, const pn_map_arrays& arrays, int E, cudaStream_t s);
 void launch_goal_map(const float* local_map, int E, int nc, int w, int h, const int* goal_cat, const int* skip_morph,
                      const int* global_goal, int goal_erode, float* goal_map, int* found, cudaStream_t s);

@@ -1,6 +1,8 @@
 // HBM-bound helper kernels around the tensor-core convolutions: layout conversion, max pooling,
 // pyramid pooling (AdaptiveAvgPool2d), bilinear resize into a channel slice and the final
 // logits -> full-resolution NCHW (+ sigmoid) pass.  All operate on NHWC views with 16-byte vector access.
+#include <chrono>
+#include <cstdio>
 #include "engine.h"
 #include "vec.cuh"
 
@@ -293,6 +295,7 @@ void add_upsample_logits(Net& net, const Tensor& logits, int C, int Hout, int Wo
 Net::~Net() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (cap_stream) cudaStreamDestroy(cap_stream);
+  if (fwd_done) cudaEventDestroy(fwd_done);
   for (int l = 0; l < kMaxLanes; ++l) {
     if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
     if (lane_fork[l]) cudaEventDestroy(lane_fork[l]);
@@ -316,12 +319,31 @@ void Net::run_eager(cudaStream_t s) {
       lane_synced[l] = -1;
     }
   };
+  static const bool no_lanes = debug_flag("PN_DEBUG_NO_LANES");
+  static const bool sync_each = debug_flag("PN_DEBUG_SYNC_EACH");
   for (size_t i = 0; i < ops.size(); ++i) {
     if (op_join[i]) join_all();
-    const int lane = op_lane[i];
+    const int lane = no_lanes ? 0 : op_lane[i];
     if (lane == 0) {
       ops[i](s);
       ++main_ops;
+      if (sync_each) {  // diagnosis: which op does not finish (cannot be used while capturing)
+        cudaEvent_t ev;
+        PN_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        PN_CUDA_CHECK(cudaEventRecord(ev, s));
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+          const cudaError_t q = cudaEventQuery(ev);
+          if (q == cudaSuccess) break;
+          if (q != cudaErrorNotReady) PN_CUDA_CHECK(q);
+          if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(8)) {
+            std::fprintf(stderr, "peanut_b200: op %zu '%s' did not finish within 8 s\n", i, op_names[i].c_str());
+            std::fflush(stderr);
+            std::_Exit(98);
+          }
+        }
+        cudaEventDestroy(ev);
+      }
       continue;
     }
     PN_REQUIRE(lane > 0 && lane < kMaxLanes, "bad lane");
@@ -345,7 +367,8 @@ void Net::run_eager(cudaStream_t s) {
 // launch list into a CUDA graph that later calls replay - the per-layer launch overhead of
 // ~60-150 small kernels would otherwise dominate at batch 1.
 void Net::run(cudaStream_t s) {
-  if (!use_graph) {
+  static const bool no_graph = debug_flag("PN_DEBUG_NO_GRAPH") || debug_flag("PN_DEBUG_SYNC_EACH");
+  if (!use_graph || no_graph) {
     run_eager(s);
     return;
   }

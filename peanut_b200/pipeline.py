@@ -1,6 +1,15 @@
 """One perception step for E independent environments on one GPU: RGB-D frame + partial map -> (per-category masks,
 updated local map + pose, predicted semantic map).
 
+Two orderings of the same kernels:
+
+* ``mode="dependent"`` (default) is the reference's own chain - A (Mask-RCNN) -> glue -> B (mapper) -> the head of
+  ``Agent_State.update_prediction`` (agent_state.py:350-360: stamp the UPDATED local map into the full map, cut the
+  prediction window) -> C (map completion) - so the predicted map reflects the current frame.  The reference moves the
+  window device -> host -> device between B and C; here stamp and crop are two device kernels.
+* ``mode="overlapped"`` runs C on a side stream on the partial map the CALLER supplies (i.e. last step's map), next to A
+  and B: higher throughput, but the prediction is one frame stale.  Not the reference's ordering; kept as an option.
+
 This is the batched composition of the three reference call sites that ``PEANUT_Agent.act`` walks every step
 (SURVEY.md §3.1): ``SemanticPredMaskRCNN.get_prediction`` (nav/agent/agent_helper.py:220-225),
 ``Agent_Helper._preprocess_obs`` (agent_helper.py:175-195), ``Semantic_Mapping.forward``
@@ -32,7 +41,10 @@ def default_args(**kw):
 
 class PerceptionPipeline:
     def __init__(self, seg_weights, pred_weights, num_envs=1, device="cuda:0", precision="bf16", map_shape=(24, 240, 240),
-                 num_pred_classes=6, args=None):
+                 num_pred_classes=6, args=None, mode="dependent"):
+        if mode not in ("dependent", "overlapped"):
+            raise ValueError("mode must be 'dependent' (reference ordering) or 'overlapped' (stale-map throughput mode)")
+        self.mode = mode
         self.args = args or default_args()
         a = self.args
         dev = torch.device(device)
@@ -44,6 +56,7 @@ class PerceptionPipeline:
         self.seg = MaskRCNN(seg_weights, device=self.device, precision=precision, batch=self.E, height=a.env_frame_height,
                             width=a.env_frame_width)
         self.mapper = Semantic_Mapping(a, num_envs=self.E)
+        self._pred_weights, self._precision = pred_weights, precision
         self.pred = Segmentor(_default_cfg(map_shape[0], num_pred_classes), pred_weights, self.device, precision=precision)
         self.pred._ensure_built(self.E, *self.map_shape)
         nsem = a.num_sem_categories
@@ -52,9 +65,27 @@ class PerceptionPipeline:
         self.sem = torch.zeros((E, H, W, nsem), dtype=torch.float32, device=d)
         self.obs = torch.zeros((E, 4 + nsem, a.frame_height, a.frame_width), dtype=torch.float32, device=d)
         self.pred_out = torch.zeros((E, num_pred_classes) + self.map_shape[1:], dtype=torch.float32, device=d)
+        # dependent mode: the full map the updated local map is stamped into, the (fixed, centred) local-map bounds and the
+        # prediction window cut out of it (agent_state.py:186-204, 350-360)
+        self.nc = 4 + nsem
+        self.full_w = self.full_h = a.map_size_cm // a.map_resolution
+        self.local_w = self.local_h = self.full_w // a.global_downscaling
+        Cm, Hm, Wm = self.map_shape
+        if mode == "dependent":
+            if Hm > self.full_w or Wm > self.full_h:
+                raise ValueError("the prediction window does not fit the full map")
+            self.full_map = torch.zeros((E, self.nc, self.full_w, self.full_h), dtype=torch.float32, device=d)
+            r0, c0 = (self.full_w - self.local_w) // 2, (self.full_h - self.local_h) // 2
+            self.lmb = torch.tensor([[r0, r0 + self.local_w, c0, c0 + self.local_h]] * E, dtype=torch.int32, device=d)
+            self.win_x1, self.win_y1 = self.full_w // 2 - Hm // 2, self.full_h // 2 - Wm // 2   # agent_state.py:357-360
+            # channels of the net's input that exist in the map come from the window; a net with MORE input planes than
+            # the map has (BASELINE's synthetic 24 x 240 x 240 against the reference's 14 map channels) keeps the caller's
+            # planes there
+            self.win_channels = min(Cm, self.nc)
         self._side = torch.cuda.Stream(device=d)
         self._fork, self._join, self._join_d2h = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self._depth_ev, self._h2d_fence, self._depth_ready = torch.cuda.Event(), torch.cuda.Event(), None
+        self._pmap_ev, self._pmap_ready = torch.cuda.Event(), None
         # staging for the host entry point
         self._dev_in = None
         self._host_out = None
@@ -62,15 +93,53 @@ class PerceptionPipeline:
             raise ValueError("num_sem_categories must equal the segmentation classes + 1")
 
     def launches_per_step(self):
-        """Kernel launches one step enqueues (graph nodes of the two networks + mapper + glue)."""
+        """Kernel launches one step enqueues (graph nodes of the two networks + mapper + glue [+ stamp and crop])."""
         return self.seg.num_launches() + 1 + int(self.mapper.ctx.lib.pn_semmap_num_launches(self.mapper.ctx.handle)) + \
-            self.pred.num_launches()
+            self.pred.num_launches() + (2 if self.mode == "dependent" else 0)
+
+    def pred_single(self):
+        """A batch-1 engine of the same map-completion net (same weights, precision), built on first use: what the
+        single-environment reference call ``PEANUT_Prediction_Model.get_prediction`` runs."""
+        if getattr(self, "_pred1", None) is None:
+            self._pred1 = Segmentor(_default_cfg(self.map_shape[0], self.num_pred_classes), self._pred_weights, self.device,
+                                    precision=self._precision)
+        return self._pred1
+
+    def _step_dependent(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat):
+        """A -> glue -> B -> stamp -> crop -> C on the caller's stream (the reference's chain, agent_state.py:273-274 then
+        :350-361).  ``partial_map`` [E,C,Hm,Wm] is the net's input buffer: its first min(C, nc) planes are OVERWRITTEN with
+        the prediction window of the updated full map."""
+        a = self.args
+        main = torch.cuda.current_stream(self.device)
+        self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
+        if self._depth_ready is not None:
+            main.wait_event(self._depth_ready)
+        stream = ctypes.c_void_p(main.cuda_stream)
+        lib, h = self.seg.ctx.lib, self.seg.ctx.handle
+        _lib.check(lib.pn_make_obs(h, depth.data_ptr(), rgb.data_ptr(), self.sem.data_ptr(), self.E, a.env_frame_height,
+                                   a.env_frame_width, a.frame_height, a.frame_width, a.num_sem_categories, a.min_depth,
+                                   a.max_depth, self.obs.data_ptr(), stream))
+        fp, new_map, poses = self.mapper.forward_batch(self.obs, pose_delta, local_map, poses)
+        Cm, Hm, Wm = self.map_shape
+        _lib.check(lib.pn_map_stamp_local(h, new_map.data_ptr(), self.full_map.data_ptr(), self.lmb.data_ptr(), self.E, self.nc,
+                                          self.local_w, self.local_h, self.full_w, self.full_h, stream))
+        if self._pmap_ready is not None:  # step_host copies the caller's partial map beside Mask-RCNN
+            main.wait_event(self._pmap_ready)
+        _lib.check(lib.pn_map_crop_window(h, self.full_map.data_ptr(), self.E, self.nc, self.full_w, self.full_h, self.win_x1,
+                                          self.win_y1, Hm, Wm, self.win_channels, partial_map.data_ptr(), Cm, stream))
+        pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
+        return self.sem, fp, new_map, poses, pred
 
     def step_device(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat=None):
         """All CUDA tensors: rgb uint8 [E,H,W,3]; depth float32 [E,H,W] (simulator units, 0 = invalid);
         pose_delta [E,3]; local_map [E,4+S,n,n]; poses [E,3] (updated in place); partial_map [E,C,Hm,Wm].
         Returns (sem [E,H,W,S], fp_map [E,vr,vr], new_local_map [E,4+S,n,n], poses, pred_map [E,K,Hm,Wm]);
         no host synchronisation."""
+        if not (partial_map.is_cuda and partial_map.dtype == torch.float32 and partial_map.is_contiguous() and
+                tuple(partial_map.shape) == (self.E,) + self.map_shape):
+            raise TypeError(f"partial_map: expected a contiguous float32 CUDA tensor of shape {(self.E,) + self.map_shape}")
+        if self.mode == "dependent":
+            return self._step_dependent(rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat)
         a = self.args
         # The map-completion net only reads the caller's partial map: it runs on a side stream next to Mask-RCNN and the
         # mapper (at small E every layer is a single wave of CTAs that leaves room for a second resident CTA per SM).
@@ -119,18 +188,26 @@ class PerceptionPipeline:
             self._dev_in[2].copy_(pose_delta_h, non_blocking=True)
             self._depth_ev.record(self._side)
             self._dev_in[3].copy_(partial_map_h, non_blocking=True)
+            self._pmap_ev.record(self._side)
         rgb, depth, delta, pmap = self._dev_in
         self._depth_ready = self._depth_ev
+        self._pmap_ready = self._pmap_ev if self.mode == "dependent" else None
         try:
             _, fp, new_map, poses, pred = self.step_device(rgb, depth, delta, local_map, poses, pmap)
         finally:
             self._depth_ready = None
-        with torch.cuda.stream(self._side):  # the predicted map leaves on the side stream as soon as it exists
+            self._pmap_ready = None
+        if self.mode == "dependent":  # one chain on the caller's stream: the results leave in order behind stage C
+            self._host_out[1].copy_(poses, non_blocking=True)
+            self._host_out[2].copy_(fp, non_blocking=True)
             self._host_out[0].copy_(pred, non_blocking=True)
-            self._join_d2h.record(self._side)
-        self._host_out[1].copy_(poses, non_blocking=True)
-        self._host_out[2].copy_(fp, non_blocking=True)
-        main.wait_event(self._join_d2h)
+        else:
+            with torch.cuda.stream(self._side):  # the predicted map leaves on the side stream as soon as it exists
+                self._host_out[0].copy_(pred, non_blocking=True)
+                self._join_d2h.record(self._side)
+            self._host_out[1].copy_(poses, non_blocking=True)
+            self._host_out[2].copy_(fp, non_blocking=True)
+            main.wait_event(self._join_d2h)
         main.synchronize()
         return self._host_out[0], self._host_out[1], self._host_out[2], new_map
 

@@ -50,7 +50,7 @@ def _default_cfg(in_channels=14, num_classes=6):
 class Segmentor:
     """What ``init_segmentor`` returns: carries ``cfg`` / ``CLASSES`` like the mmseg model object."""
 
-    def __init__(self, cfg, state_dict, device, precision="bf16", classes=None):
+    def __init__(self, cfg, state_dict, device, precision="tf32", classes=None):
         m = cfg["model"]
         bb, head = m["backbone"], m["decode_head"]
         if bb.get("type", "ResNetV1c") != "ResNetV1c" or bb.get("depth", 50) != 50:
@@ -69,7 +69,7 @@ class Segmentor:
         if dev.type != "cuda":
             raise RuntimeError("peanut_b200 has no CPU path: device must be a CUDA device")
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
-        self.precision = {"bf16": _lib.PN_BF16, "tf32": _lib.PN_TF32, "fp32": _lib.PN_TF32}[precision]
+        self.precision = _lib.precision_code(precision)
         self.ctx = _lib.Context(self.device.index)
         self.ctx.set_weights({k: v for k, v in state_dict.items()
                               if not k.endswith("num_batches_tracked") and not k.startswith("auxiliary_head")})
@@ -139,7 +139,7 @@ class Segmentor:
         return out
 
 
-def init_segmentor(config, checkpoint=None, device="cuda:0", precision="bf16", state_dict=None):
+def init_segmentor(config, checkpoint=None, device="cuda:0", precision="tf32", state_dict=None):
     """prediction/mmseg/apis/inference.py:12-40.  ``checkpoint`` is an mmcv-format .pth
     ({'state_dict': ..., 'meta': {'CLASSES': ...}}); ``state_dict`` may be given directly instead."""
     if isinstance(config, str):
@@ -179,8 +179,11 @@ class PEANUT_Prediction_Model():
         self.args = args
         ckpt = getattr(args, "pred_model_wts", None)
         cfg_path = getattr(args, "pred_model_cfg", None)
-        cfg = Config.fromfile(cfg_path) if cfg_path and os.path.exists(cfg_path) else _default_cfg()
-        precision = precision or getattr(args, "pn_precision", "bf16")
+        # the reference opens args.pred_model_cfg unconditionally (prediction.py:146) and raises if it is missing; only a
+        # namespace WITHOUT the attribute (synthetic-weight callers) falls back to the reference's config values
+        cfg = Config.fromfile(cfg_path) if cfg_path else _default_cfg()
+        # fp32-parity path by default (tf32 operands, the tolerances of DESIGN section 3); "bf16" is the throughput opt-in
+        precision = precision or getattr(args, "pn_precision", "tf32")
         device = ("cuda:" + str(args.sem_gpu_id)) if args else "cuda:0"
         self.model = init_segmentor(cfg, checkpoint=ckpt if state_dict is None else None, device=device,
                                     precision=precision, state_dict=state_dict)

@@ -23,20 +23,24 @@ sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
 from agent.mapping import Semantic_Mapping  # noqa: E402  (the reference)
 from oracle import mapper as oracle  # noqa: E402
 
-CASES = [  # (name, seed, scene, sem_density)
-    ("room0", 0, "room", 0.1),
-    ("room1", 1, "room", 0.3),
-    ("stairs", 2, "stairs", 0.1),
-    ("wall", 3, "wall", 0.2),
-    ("empty", 4, "empty", 0.0),
+CASES = [  # (name, seed, scene, sem_density, argparse overrides)
+    ("room0", 0, "room", 0.1, {}),
+    ("room1", 1, "room", 0.3, {}),
+    ("stairs", 2, "stairs", 0.1, {}),
+    ("wall", 3, "wall", 0.2, {}),
+    ("empty", 4, "empty", 0.0, {}),
+    # (camera_height * 100 + 1) / 5 is an integer in Python double arithmetic only for some heights: 0.89 gives max_z = 26
+    # (a float32 round-trip of the height gives 25), so this case pins the obstacle height band's upper edge
+    ("room_cam089", 5, "room", 0.2, {"camera_height": 0.89}),
+    ("room_hfov90", 6, "room", 0.2, {"hfov": 90.0, "camera_height": 0.84}),
 ]
 
 
 def main():
     torch.set_num_threads(1)
-    args = oracle.default_args()
-    ref_module = Semantic_Mapping(args).eval()
-    for name, seed, scene, dens in CASES:
+    for name, seed, scene, dens, over in CASES:
+        args = oracle.default_args(**over)
+        ref_module = Semantic_Mapping(args).eval()
         obs = oracle.synth_obs(seed, args, scene, dens)
         delta, maps, poses = oracle.synth_state(seed, args)
         # reference (B = 1)
@@ -54,7 +58,7 @@ def main():
         assert torch.equal(pose_r, p_ref), name + ": pose_pred must alias the mutated poses_last"
         out = os.path.join(HERE, f"semmap_{name}.npz")
         # inputs are regenerated from the seed by the tests; only the reference outputs are stored
-        np.savez_compressed(out, seed=seed, scene=scene, sem_density=dens,
+        np.savez_compressed(out, seed=seed, scene=scene, sem_density=dens, overrides=repr(over),
                             fp_map_pred=fp_r[0].numpy().astype(np.float16),  # values are exactly 0 or 1
                             map_pred_q=np.round(map_r.numpy() * 65535.0).astype(np.uint16),  # 16-bit quantised copy
                             map_pred_sum=np.float64(map_r.double().sum().item()),

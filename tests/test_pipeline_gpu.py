@@ -1,6 +1,10 @@
 """PerceptionPipeline (peanut_b200/pipeline.py): the batched composition of the three reference call sites must equal the
 stages run one by one through their reference-facing shims, for device and host entry points alike (bit-exact: same
-kernels, same launch lists; the prediction net merely runs on a side stream)."""
+kernels, same launch lists).  Both orderings are covered: "dependent" (the reference's chain A -> glue -> B ->
+update_prediction's stamp + window -> C, agent_state.py:273-274, 350-361) and "overlapped" (C on the caller's stale map,
+on a side stream)."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -9,16 +13,17 @@ from oracle import mapper as OB
 from oracle import maskrcnn as OA
 from oracle import prednet as OC
 from oracle import preproc as OP
+from peanut_b200 import _lib, agent_prediction
 from peanut_b200.pipeline import PerceptionPipeline
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def setup():
+@pytest.fixture(scope="module", params=["dependent", "overlapped"])
+def setup(request):
     E, shape = 2, (14, 96, 96)
     wa, wc = OA.synth_weights(0), OC.synth_state_dict(shape[0], 6, seed=0)
-    pipe = PerceptionPipeline(wa, wc, num_envs=E, device="cuda:0", precision="bf16", map_shape=shape)
+    pipe = PerceptionPipeline(wa, wc, num_envs=E, device="cuda:0", precision="bf16", map_shape=shape, mode=request.param)
     pipe.args.sem_pred_prob_thr = 0.3   # random weights: keep some detections alive
     pipe.args.goal_thr = 0.3
     args = OB.default_args()
@@ -36,6 +41,9 @@ def test_step_equals_stages(setup):
     pipe, h = setup
     d = {k: v.cuda() for k, v in h.items()}
     poses = d["poses"].clone()
+    if pipe.mode == "dependent":
+        pipe.full_map.normal_()  # cells of the window outside the local map must come from the full map as it was
+        full_before = pipe.full_map.clone()
     sem, fp, new_map, poses_out, pred = pipe.step_device(d["rgb"], d["depth"], d["delta"], d["maps"], poses, d["pmap"])
     torch.cuda.synchronize()
     sem, fp, new_map, pred, poses_out = sem.clone(), fp.clone(), new_map.clone(), pred.clone(), poses_out.clone()
@@ -43,6 +51,28 @@ def test_step_equals_stages(setup):
     # stage by stage on the current stream
     sem1 = pipe.seg.forward_device(d["rgb"], None, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr).clone()
     assert torch.equal(sem1, sem) and float(sem.sum()) > 0
+    if pipe.mode == "dependent":
+        # the reference ordering: the net must have seen the window of the full map AFTER this step's local map was stamped
+        r0, r1, c0, c1 = (int(v) for v in pipe.lmb[0].tolist())
+        expect_full = full_before.clone()
+        expect_full[:, :, r0:r1, c0:c1] = new_map
+        assert torch.equal(pipe.full_map, expect_full)
+        x1, y1, win = pipe.win_x1, pipe.win_y1, pipe.map_shape[1]
+        assert torch.equal(d["pmap"], expect_full[:, :, x1:x1 + win, y1:y1 + win])
+        assert not torch.equal(d["pmap"], h["pmap"].cuda())
+        # ... and the step must agree with the device-side Agent_State.update_prediction shim (N1a), environment by environment
+        for e in range(pipe.E):
+            fm = full_before[e].clone()
+            tgt = agent_prediction.update_prediction(fm, new_map[e], (r0, r1, c0, c1), 2, pipe.pred_single(), win, as_numpy=False)
+            stream = torch.cuda.current_stream().cuda_stream
+            out = torch.empty_like(tgt)
+            explored = new_map[e, 1]
+            _lib.check(pipe.seg.ctx.lib.pn_target_pred(pipe.seg.ctx.handle, pred[e].contiguous().data_ptr(), pred.shape[1], win, x1, y1, 2,
+                                                       r0, c0, pipe.local_w, pipe.local_h, explored.data_ptr(),
+                                                       int(explored.stride(0)), out.data_ptr(), ctypes.c_void_p(stream)))
+            torch.cuda.synchronize()
+            assert torch.equal(fm, expect_full[e])
+            assert float((out - tgt).abs().max()) <= 2e-2  # batch-1 engine vs batch-E engine: different tile configs, bf16
     pred1 = pipe.pred.forward_device(d["pmap"], apply_sigmoid=True).clone()
     assert torch.equal(pred1, pred)
     assert float(pred.min()) >= 0.0 and float(pred.max()) <= 1.0
@@ -60,6 +90,8 @@ def test_step_equals_stages(setup):
 def test_step_host_equals_step_device(setup):
     pipe, h = setup
     d = {k: v.cuda() for k, v in h.items()}
+    if pipe.mode == "dependent":
+        pipe.full_map.zero_()
     _, fp, new_map, poses_d, pred = pipe.step_device(d["rgb"], d["depth"], d["delta"], d["maps"], d["poses"].clone(), d["pmap"])
     torch.cuda.synchronize()
     fp, new_map, pred, poses_d = fp.clone(), new_map.clone(), pred.clone(), poses_d.clone()

@@ -230,6 +230,25 @@ int pn_semmap_forward(pn_ctx* ctx, const float* obs_dev, const float* pose_delta
 int pn_semmap_read_ego(pn_ctx* ctx, float* ego_out_dev, int* stair_flags_out_dev, void* stream);
 int pn_semmap_num_launches(pn_ctx* ctx);
 
+/* ---- Result gather across the GPUs of one node (the path shards over independent environments,
+ * the only exchange is each rank's results travelling to the rank that hosts the planner).  No reference counterpart: the
+ * reference is one process, one environment (nav/collect.py:32-33).  One-sided push over NVLink peer memory: the root
+ * (pn_gather_create with rank == root) owns a slab [2 slots][world][bytes_per_rank]; pn_gather_export gives its 64-byte CUDA
+ * IPC handle, which the host program hands to every other rank (torch.distributed, MPI, a file ...) for pn_gather_connect.
+ * pn_gather_step enqueues on `stream`: the rank's push of local_dev (bytes_per_rank bytes) into its slice + a sequence flag;
+ * on the root additionally the wait for every rank's flag, so work enqueued on the root's stream after the step sees all
+ * results at pn_gather_result (slices are slice_stride bytes apart; valid until the root's next-but-one step).  Every rank
+ * must call pn_gather_step the same number of times.  Waits are bounded (4 s): pn_gather_status reports 0 = ok, 2 = a push
+ * timed out waiting for the root, 3 = the root timed out waiting for a rank. */
+typedef struct pn_gather pn_gather;
+int pn_gather_create(pn_ctx* ctx, int rank, int world, int root, int64_t bytes_per_rank, pn_gather** out);
+int pn_gather_export(pn_gather* g, void* handle64_out);
+int pn_gather_connect(pn_gather* g, const void* handle64);
+int pn_gather_step(pn_gather* g, const void* local_dev, void* stream);
+int pn_gather_result(pn_gather* g, void** slab_dev_out, int64_t* slice_stride_out);
+int pn_gather_status(pn_gather* g, int* status_out);
+int pn_gather_destroy(pn_gather* g);
+
 /* ---- Launch-configuration table of the tensor-core conv kernel.  At *_build time every conv layer picks its launch
  * configuration (N tile, split-K factor, CTA pair, CTAs per SM) from this process-wide table; a layer that is not in it
  * times a shortlist on its own buffers and adds the winner (PN_CONV_AUTOTUNE=table: never time, use the tile model's

@@ -100,7 +100,7 @@ def _frozen_bn(w, prefix):
 def _conv_bn(x, w, name, stride=1, padding=0, relu=False, emulate=False):
     s, b = _frozen_bn(w, name + ".norm")
     if emulate:  # the CUDA path stores bf16(weight * scale) and adds the shift in the epilogue
-        y = F.conv2d(x, _r(w[name + ".weight"] * s[:, None, None, None], True), None, stride, padding)
+        y = F.conv2d(x, _r(w[name + ".weight"] * s[:, None, None, None], emulate), None, stride, padding)
         y = y + b[None, :, None, None]
     else:
         y = F.conv2d(x, w[name + ".weight"], None, stride, padding)
@@ -109,11 +109,20 @@ def _conv_bn(x, w, name, stride=1, padding=0, relu=False, emulate=False):
 
 
 def _r(t, emulate):
-    return t.to(torch.bfloat16).to(torch.float32) if emulate else t
+    """Storage rounding of the CUDA path, applied wherever it materialises a tensor: True / "bf16" = bf16 (round to nearest
+    even); "tf32" = the 10-bit tf32 mantissa, round to nearest with ties away from zero (cvt.rna.tf32.f32), i.e. what the
+    fp32-storage path keeps so that the tensor core's operand truncation is exact; False = nothing (the fp32 reference)."""
+    if not emulate:
+        return t
+    if emulate == "tf32":
+        u = t.contiguous().view(torch.int32)
+        return ((u + 0x1000) & -0x2000).view(torch.float32)
+    return t.to(torch.bfloat16).to(torch.float32)
 
 
 def backbone(x, w, emulate_bf16=False):
-    """ResNet-101 bottom-up [ext]; returns {res2..res5}.  emulate_bf16 rounds every materialised tensor."""
+    """ResNet-101 bottom-up [ext]; returns {res2..res5}.  emulate_bf16 (True / "bf16" / "tf32", see _r) rounds every
+    materialised tensor the way the CUDA path stores it."""
     e = emulate_bf16
     p = "backbone.bottom_up."
     x = _r(x, e)

@@ -78,6 +78,14 @@ PROTOTYPES = {
     "pn_semmap_forward": (ctypes.c_int, [ctypes.c_void_p] * 9),
     "pn_semmap_read_ego": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "pn_semmap_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "pn_gather_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "pn_gather_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_gather_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_gather_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pn_gather_result": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
+    "pn_gather_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "pn_gather_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pn_conv_tuning_import": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p]),
     "pn_conv_tuning_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "pn_conv_tuning_clear": (ctypes.c_int, []),

@@ -91,6 +91,14 @@ void nchw_to_nhwc_direct(const float* in, const Tensor& t, int C, cudaStream_t s
     launch_pdl(nchw_to_nhwc_direct_kernel<float>, blocks, threads, 0, s, in, static_cast<float*>(t.ptr), t.ld, t.B, C, HW, 1);
 }
 
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+void ctx_device(const void* ctx, int* device, int* num_sms) {
+  const Ctx* c = static_cast<const Ctx*>(ctx);
+  PN_REQUIRE(c != nullptr, "null context");
+  if (device) *device = c->device;
+  if (num_sms) *num_sms = c->num_sms;
+}
+
 void check_device(Ctx* c) {
   PN_REQUIRE(c != nullptr, "null context");
   PN_CUDA_CHECK(cudaSetDevice(c->device));

@@ -617,6 +617,26 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     }
     if (usable) bn = it->second.bn, splits = it->second.splits, pair = it->second.pair != 0, opt = it->second.opt;
   }
+  // Diagnosis: PN_CONV_FORCE_OPT1=all|<substring of the layer name> runs every eligible layer (persistent multi-tile launch,
+  // single-CTA tile of at most 128 columns, TMA epilogue) with two CTAs per SM, whatever the table / tuner chose.
+  if (!forced) {
+    static const char* force1 = std::getenv("PN_CONV_FORCE_OPT1");
+    if (force1 && force1[0] && (std::strcmp(force1, "all") == 0 || name.find(force1) != std::string::npos)) {
+      int b1 = std::min(bn, 128);
+      while (b1 >= 32 && (b1 > cout32 || cout32 % b1 != 0)) b1 /= 2;
+      const long long tiles1 = static_cast<long long>(m_tiles) * (round_up(sp.Cout, std::max(b1, 32)) / std::max(b1, 32));
+      const int es1 = es;
+      const bool epi_ok = out.dt == dt && std::min(round_up(sp.Cout, 8), out.C) * es1 >= 64 && b1 * es1 >= 64;
+      if (b1 >= 32 && tiles1 > net.num_sms && epi_ok && sp.m_limit == nullptr) {
+        try {
+          (void)make_variant(b1, 1, false, 1);
+          bn = b1, splits = 1, pair = false, opt = 1;
+          if (std::getenv("PN_CONV_TUNE_LOG")) std::fprintf(stderr, "[force-opt1] %s M=%lld tile %d\n", name.c_str(), M, b1);
+        } catch (const std::exception&) {
+        }
+      }
+    }
+  }
   net.last_bn = bn + 1000 * splits + (pair ? 100000 : 0) + 1000000 * opt;
   const Variant chosen = make_variant(bn, splits, pair, opt);
 

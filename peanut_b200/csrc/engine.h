@@ -245,6 +245,11 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
 // Folds BatchNorm running statistics into (scale, bias): y = x*scale + bias, eps as in nn.BatchNorm2d.
 void fold_bn(const WeightStore& w, const std::string& bn_prefix, int C, std::vector<float>& scale,
              std::vector<float>& bias, float eps = 1e-5f);
+// api.cu: the thread-local message behind pn_last_error(), and the device / SM count of a pn_ctx (for sources that do not
+// see the context's definition)
+void set_last_error(const std::string& msg);
+void ctx_device(const void* ctx, int* device, int* num_sms);
+
 // Launch-configuration table of add_conv (conv_host.cu): "key bn splits pair opt" lines.  Entries that are present are used
 // without timing, so every process that imports the same table builds bit-identical networks.
 std::string conv_tuning_export();

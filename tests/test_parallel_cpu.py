@@ -60,3 +60,58 @@ def test_gather_world2_gloo(num_envs):
     got, slow = q.get()
     assert got == [[[float(e)] * 3] * 2 for e in range(num_envs)]
     assert slow == [2.0, 5.0]
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    from peanut_b200 import _lib
+    P.init_from_env("gloo")
+    _lib.load().pn_conv_tuning_clear()
+    order = []
+
+    def build():
+        # what a *_build call does to the process-wide table: rank 0 "tunes" (adds its choices); the others must find
+        # rank 0's entries already there when they build
+        order.append(_lib.tuning_export())
+        if rank == 0:
+            _lib.tuning_import("1|100|10|64|64|1|1|1|1|1|0|0|1|0|64|0|0|0|148|0 128 1 0 0\n")
+        return rank
+
+    assert P.build_synchronised(build) == rank
+    q.put((rank, order[0], _lib.tuning_export()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_build_synchronised_world2_gloo():
+    """Rank 0 builds first, its launch-configuration table reaches the other ranks before they build."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        r, before, after = q.get()
+        got[r] = (before, after)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    line = "1|100|10|64|64|1|1|1|1|1|0|0|1|0|64|0|0|0|148|0 128 1 0 0\n"
+    assert got[0] == ("", line)
+    assert got[1] == (line, line)
+
+
+def test_tuning_table_roundtrip_and_validation():
+    from peanut_b200 import _lib
+    lib = _lib.load()
+    lib.pn_conv_tuning_clear()
+    assert _lib.tuning_import("# comment\nk1 64 2 0 0\nk2 256 1 1 0\n") == 2
+    assert _lib.tuning_export() == "k1 64 2 0 0\nk2 256 1 1 0\n"
+    with pytest.raises(RuntimeError):
+        _lib.tuning_import("k3 100 1 0 0\n")   # not a tile width
+    with pytest.raises(RuntimeError):
+        _lib.tuning_import("k4 64\n")          # malformed
+    lib.pn_conv_tuning_clear()
+    assert _lib.tuning_export() == ""

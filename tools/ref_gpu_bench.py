@@ -20,9 +20,9 @@ from oracle import prednet as OC
 from oracle import preproc as OP
 
 
-def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    dev = torch.device("cuda:0")
+def run(steps=20, device="cuda:0", warmup=5):
+    """Returns the result dict (bench.py calls this for its `ref_gpu_eager` field)."""
+    dev = torch.device(device)
     torch.backends.cudnn.benchmark = True          # nav/pred_model_cfg.py:136 (C); detectron2 leaves it off for (A)
     wa = {k: v.to(dev) for k, v in OA.synth_weights(0).items()}
     wc = OC.synth_state_dict(24, 6, seed=0)
@@ -61,7 +61,7 @@ def main():
             t_stage["C"] += t3 - t2
         return pred
 
-    for _ in range(5):
+    for _ in range(warmup):
         step(False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -69,10 +69,11 @@ def main():
         step(True)
     torch.cuda.synchronize()
     ms = 1000.0 * (time.perf_counter() - t0) / steps
-    print(json.dumps({"what": "oracle in eager PyTorch on one B200 (reference GPU path, BASELINE.md section 3)", "frames_per_s": 1000.0 / ms,
-                      "ms_per_frame": ms, "ms_A_maskrcnn": 1000 * t_stage["A"] / steps, "ms_B_mapper": 1000 * t_stage["B"] / steps,
-                      "ms_C_prednet": 1000 * t_stage["C"] / steps, "steps": steps, "dtype": "fp32 (cudnn.allow_tf32 default)",
-                      "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}))
+    return {"what": "oracle in eager PyTorch on one B200 (reference GPU path, BASELINE.md section 3)", "frames_per_s": 1000.0 / ms,
+            "ms_per_frame": ms, "ms_A_maskrcnn": 1000 * t_stage["A"] / steps, "ms_B_mapper": 1000 * t_stage["B"] / steps,
+            "ms_C_prednet": 1000 * t_stage["C"] / steps, "steps": steps, "dtype": "fp32 (cudnn.allow_tf32 default)",
+            "torch": torch.__version__, "gpu": torch.cuda.get_device_name(dev)}
 
 
-main()
+if __name__ == "__main__":
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 20)))

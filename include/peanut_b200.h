@@ -190,6 +190,43 @@ int pn_goal_map(pn_ctx* ctx, const float* local_map_dev, int E, int num_channels
                 const int* goal_cat_dev, const int* skip_morph_dev, const int* global_goal_dev, int goal_erode,
                 float* goal_map_out_dev, int* found_goal_out_dev, void* stream);
 
+/* ---- Agent_State.update_global_goal (nav/agent/agent_state.py:376-416), for E environments with
+ * every field in device memory: obstacle dilation by disk(col_rad) -> traversible mask (collision cells blocked, visited
+ * cells free, the agent's cell always free), geodesic distance from the agent's cell (the eikonal discretisation of
+ * scikit-fmm's second-order distance marcher, solved by a block-parallel fixed-point iteration around an exact sequential
+ * replay of the marcher's first cells), exp(-dd / (dist_weight_temperature / map_resolution)) weighting inside the
+ * local-map window with the "stuck inside an obstacle: keep the last weights" rule, value = target_pred * weight (or the two
+ * special temperatures -1 / 0), first argmax, and the "avoid repeating the last goal" bookkeeping. */
+typedef struct pn_goal_cfg {
+  int num_channels;               /* channels of full_map (channel 0 = obstacles)                 */
+  int full_w, full_h;             /* 960 x 960                                                     */
+  int local_w, local_h;           /* 480 x 480                                                     */
+  int col_rad;                    /* 4     arguments.py:86 (disk radius of the obstacle dilation)  */
+  int map_resolution;             /* 5                                                             */
+  double dist_weight_temperature; /* 500   arguments.py:100 (-1: no weighting, 0: frontier mode)   */
+} pn_goal_cfg;
+
+typedef struct pn_goal_arrays {
+  const float* full_map;        /* [E, nc, full_w, full_h]                                                     */
+  const uint8_t* collision_map; /* [E, full_w, full_h] 1 = collision (helper.collision_map == 1), or NULL      */
+  const uint8_t* visited_vis;   /* [E, full_w, full_h] 1 = visited (helper.visited_vis == 1), or NULL          */
+  const int* lmb;               /* [E, 4]                                                                      */
+  const int* loc;               /* [E, 2] loc_r, loc_c (pn_map_update_local)                                   */
+  const float* target_pred;     /* [E, local_w, local_h] (pn_target_pred); may be NULL when only_distance      */
+  double* dd;                   /* [E, full_w, full_h] out: geodesic distance in cells, inf = blocked/unreached */
+  double* dd_wt;                /* [E, local_w, local_h] in/out (self.dd_wt)                                   */
+  int* dd_wt_valid;             /* [E] in/out: 0 = self.dd_wt is None                                          */
+  double* value;                /* [E, local_w, local_h] out (self.value) or NULL                              */
+  int* global_goal;             /* [E, 2] in/out (self.global_goals[0])                                        */
+  int* goal_kind;               /* [E] in/out: 1 = list of lists (init / presets), 2 = tuple written here      */
+  int* last_global_goal;        /* [E, 2] in/out (self.last_global_goal[0])                                    */
+  int* last_kind;               /* [E] in/out: 0 = None, else the kind of the stored goal; a list never equals the tuple
+                                   np.unravel_index yields, so only kind 2 can suppress a repeated goal (:413)  */
+} pn_goal_arrays;
+
+/* only_distance != 0 stops after dd (the geodesic field alone: what the planner's FMMPlanner.set_goal also computes). */
+int pn_global_goal(pn_ctx* ctx, const pn_goal_cfg* cfg, const pn_goal_arrays* arrays, int E, int only_distance, void* stream);
+
 /* ---- Glue between stages A and B: Agent_Helper._preprocess_obs / _preprocess_depth
  * (nav/agent/agent_helper.py:175-217).  depth [E,H,W] fp32 as the simulator emits it (0 = invalid, 1 = max range),
  * rgb [E,H,W,3] uint8 (may be NULL: channels 0-2 are unused by the mapper), sem [E,H,W,num_sem] fp32 (stage A output)

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "pn_map_stamp_local": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "pn_map_crop_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_void_p, ctypes.c_int,
                                                                                                   ctypes.c_void_p]),
+    "pn_global_goal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "pn_goal_map": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3 + [ctypes.c_int] +
                     [ctypes.c_void_p] * 3),
     "pn_semmap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
@@ -117,6 +118,19 @@ class MapArrays(ctypes.Structure):
     """struct pn_map_arrays (device pointers)"""
     _fields_ = [(n, ctypes.c_void_p) for n in ("full_map", "local_map", "full_pose", "local_pose", "origins", "lmb",
                                                "planner_pose_inputs", "loc", "dist_to_goal", "global_goal")]
+
+
+class GoalCfg(ctypes.Structure):
+    """struct pn_goal_cfg"""
+    _fields_ = [("num_channels", ctypes.c_int), ("full_w", ctypes.c_int), ("full_h", ctypes.c_int), ("local_w", ctypes.c_int),
+                ("local_h", ctypes.c_int), ("col_rad", ctypes.c_int), ("map_resolution", ctypes.c_int),
+                ("dist_weight_temperature", ctypes.c_double)]
+
+
+class GoalArrays(ctypes.Structure):
+    """struct pn_goal_arrays (device pointers)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("full_map", "collision_map", "visited_vis", "lmb", "loc", "target_pred", "dd", "dd_wt",
+                                               "dd_wt_valid", "value", "global_goal", "goal_kind", "last_global_goal", "last_kind")]
 
 
 class MaskRcnnCfg(ctypes.Structure):

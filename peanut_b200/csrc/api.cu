@@ -654,6 +654,22 @@ int pn_map_crop_window(pn_ctx* ctx, const float* full_map_dev, int E, int num_ch
   PN_API_END
 }
 
+int pn_global_goal(pn_ctx* ctx, const pn_goal_cfg* cfg, const pn_goal_arrays* a, int E, int only_distance, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(cfg && a && E > 0, "pn_global_goal: null configuration / arrays or no environments");
+  PN_REQUIRE(a->full_map && a->lmb && a->loc && a->dd, "pn_global_goal: null map / bounds / agent cell / distance buffer");
+  PN_REQUIRE(only_distance || (a->target_pred && a->dd_wt && a->dd_wt_valid && a->global_goal && a->goal_kind &&
+                               a->last_global_goal && a->last_kind),
+             "pn_global_goal: null goal state array");
+  PN_REQUIRE(cfg->num_channels >= 1 && cfg->local_w > 0 && cfg->local_h > 0 && cfg->local_w <= cfg->full_w &&
+                 cfg->local_h <= cfg->full_h && cfg->map_resolution > 0,
+             "pn_global_goal: bad geometry");
+  launch_global_goal(c->device, c->num_sms, *cfg, *a, E, only_distance, static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
 int pn_goal_map(pn_ctx* ctx, const float* local_map_dev, int E, int num_channels, int local_w, int local_h,
                 const int* goal_cat_dev, const int* skip_morph_dev, const int* global_goal_dev, int goal_erode,
                 float* goal_map_out_dev, int* found_goal_out_dev, void* stream) {

@@ -155,15 +155,16 @@ void launch_conv_bn(int bn, bool pair, const ConvMaps& tm, const ConvParams& p, 
   }
 }
 
-// Launch modes the autotuner may add to its shortlist beyond tile width / split-K / CTA pairs.  Bit 1: split-K over
-// clusters of CTA pairs, bit 2: two CTAs per SM.  Both are parity-tested (tests/test_conv_gpu.py) and win on individual
-// layers (profiles/r01_conv_mode_sweep_pairsplit_tf32_b1.txt, profiles/r01_conv_two_ctas_per_sm_bf16_b8.txt), but the
-// 8-environment bf16 pipeline did not finish building with both enabled on the last GPU run of round 1 (not yet
-// reproduced in isolation), so they stay opt-in: PN_CONV_TUNE_EXTRA=3 enables both.
+// Launch modes the autotuner adds to its shortlist beyond tile width / split-K / CTA pairs.  Bit 1: split-K over clusters
+// of CTA pairs, bit 2: two CTAs per SM.  Both are parity-tested (tests/test_conv_gpu.py) and win on individual layers
+// (profiles/r01_conv_mode_sweep_pairsplit_tf32_b1.txt, profiles/r01_conv_two_ctas_per_sm_bf16_b8.txt).  Round 1 kept them
+// opt-in because the 8-environment pipeline stalled with them; the stall was a tensor-memory hold-and-wait cycle between
+// early-resident CTAs of two streams, removed by allocating tensor memory after griddepcontrol.wait (conv_umma.cuh,
+// profiles/r02_stall_analysis.txt).  PN_CONV_TUNE_EXTRA overrides (0 = neither).
 int tune_extra() {
   static const int v = [] {
     const char* e = std::getenv("PN_CONV_TUNE_EXTRA");
-    return e ? std::atoi(e) : 0;
+    return e ? std::atoi(e) : 3;
   }();
   return v;
 }

@@ -375,23 +375,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     *reinterpret_cast<uint4*>(smem_ones + r * 32 + ((u ^ 1u) << 4)) = zero;
     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
   }
-  if (warp == kMmaWarp) {
-    if constexpr (kPair) {
-      tmem_alloc_pair(tmem_ptr, kTmemCols);
-      tmem_relinquish_pair();
-    } else {
-      tmem_alloc(tmem_ptr, kTmemCols);
-      tmem_relinquish();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barriers initialised (and the ones tile written) before anybody uses them
   if constexpr (kPair) {  // the peer's barriers must be initialised before anything signals them
     cluster_arrive_release();
     cluster_wait_acquire();
   }
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
   // Weights do not depend on the previous kernel: arm the first pipeline stages of this CTA's first work item and
   // fetch their weight tiles while the previous kernel drains (its tail would otherwise hide nothing but the prologue).
   int pre_armed = 0;
@@ -418,10 +406,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
   TileCoord first_tc{};
   if (warp == kProducerWarp) first_tc = tile_coord<kPair>(p, work_first, cta_rank, p.R * p.S * p.kb_per_tap);
-  // everything above (barrier init, TMEM allocation, descriptor prefetch, weight prefetch, first tile's index math)
+  // everything above (barrier init, descriptor prefetch, weight prefetch, first tile's index math)
   // overlapped the previous kernel's tail; from here on we read what it wrote
   griddep_wait();
   PN_LOG(1);
+  // Tensor memory is allocated only NOW.  A CTA that is resident early (programmatic dependent launch) and still waiting
+  // for its predecessor grid must not hold tensor-memory columns: with several conv CTAs per SM (two CTAs per SM, parallel
+  // lanes, a second stream) a running grid's CTA can then block in tcgen05.alloc behind columns held by a CTA that is
+  // itself waiting for a grid that needs THAT CTA to finish - a cross-stream cycle observed as a hang in 5 of 12 runs of
+  // the 8-environment pipeline, 0 of 12 with the allocation here (profiles/r02_stall_analysis.txt).  The TMA producer does
+  // not need the address and starts loading at once; the allocation overlaps its first-byte latency.
+  uint32_t tmem_base = 0;
+  if (warp == kMmaWarp) {
+    if constexpr (kPair) {
+      tmem_alloc_pair(tmem_ptr, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, kTmemCols);
+      tmem_relinquish();
+    }
+  }
+  if constexpr (kPair) {
+    // the leader's MMAs write the peer's tensor memory too: both allocations must exist before the first MMA
+    tc_fence_before();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    tc_fence_after();
+    tmem_base = *tmem_ptr;
+  } else if (warp < 4 || warp == kMmaWarp) {  // epilogue warps + the allocating MMA warp; the other warps never touch it
+    tc_fence_before();
+    named_bar_sync(1, 160);
+    tc_fence_after();
+    tmem_base = *tmem_ptr;
+  }
 
   int m_tiles_live = p.m_tiles;
   if (p.m_limit != nullptr) {

@@ -543,42 +543,39 @@ __global__ void __launch_bounds__(1024) k_rpn_merge(int post_topk, const float* 
 // ---------------------------------------------------------------------------------------------------
 // ROIAlignV2 (aligned=True, sampling_ratio=0) with detectron2's level assignment.  One CTA per ROI, one warp
 // per output bin (round robin), one lane per 8 channels (256 channels).
-// One sample of ROIAlign: the four bilinear taps (8 channels per lane) and their weights; ok = false when the
-// sample falls outside the feature map (contributes 0).
+// 8 channels of one cell as loaded (conversion deferred until the value is consumed, so that several loads stay in flight)
 template <typename T>
-struct RoiSample {
-  float w1, w2, w3, w4;
-  float v1[8], v2[8], v3[8], v4[8];
-  bool ok;
-  __device__ __forceinline__ void fetch(const T* feat, int H, int W, long long ld, int lane, float y, float x) {
-    ok = !(y < -1.0f || y > static_cast<float>(H) || x < -1.0f || x > static_cast<float>(W));
-    if (!ok) return;
-    if (y <= 0.f) y = 0.f;
-    if (x <= 0.f) x = 0.f;
-    int yl = static_cast<int>(y), xl = static_cast<int>(x), yh, xh;
-    if (yl >= H - 1) yh = yl = H - 1, y = static_cast<float>(yl);
-    else yh = yl + 1;
-    if (xl >= W - 1) xh = xl = W - 1, x = static_cast<float>(xl);
-    else xh = xl + 1;
-    const float ly = y - static_cast<float>(yl), lx = x - static_cast<float>(xl);
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-    load8(feat + (static_cast<size_t>(yl) * W + xl) * ld + lane * 8, v1);
-    load8(feat + (static_cast<size_t>(yl) * W + xh) * ld + lane * 8, v2);
-    load8(feat + (static_cast<size_t>(yh) * W + xl) * ld + lane * 8, v3);
-    load8(feat + (static_cast<size_t>(yh) * W + xh) * ld + lane * 8, v4);
-  }
-  __device__ __forceinline__ void accumulate(float (&acc)[8]) const {
-    if (!ok) return;
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (((w1 * v1[j] + w2 * v2[j]) + w3 * v3[j]) + w4 * v4[j]);
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
   }
 };
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  }
+};
+
 
 // grid = (S bin rows, ROIs); block = S warps: warp pw owns output bin (ph = blockIdx.x, pw); lane = 8 channels.
 // Samples are visited in torchvision's order (iy outer, ix inner) with the loads of two samples in flight.
 template <typename T>
-__global__ void __launch_bounds__(448) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
+__global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
                                                    int S, T* __restrict__ out, long long ldo) {
   pdl_grid_sync();
   const int r = blockIdx.y;
@@ -638,35 +635,65 @@ __global__ void __launch_bounds__(448) k_roi_align(Pyramid pyr, const float* __r
       if (clo + lane == xl) WX += hx;
       if (clo + lane == xh) WX += lx;
     }
+    // Cells of the footprint in row-major order, kFly independent 16 / 32-byte loads in flight per lane before the first
+    // one is consumed (the loop is latency-bound: ~16 dependent L2 round trips per bin otherwise).  Same products, same
+    // accumulation order as a plain row / column loop that skips zero weights.
+    constexpr int kFly = sizeof(T) == 2 ? 6 : 3;
     const int ncols = chi - clo + 1;
-    for (int rr = 0; rr <= rhi - rlo; ++rr) {
-      const float wy = __shfl_sync(0xffffffffu, WY, rr);
-      if (wy == 0.f) continue;
-      const T* rowp = feat + (static_cast<size_t>(rlo + rr) * lv.W + clo) * lv.ld + lane * 8;
-      for (int cc = 0; cc < ncols; cc += 2) {
-        const float wa = wy * __shfl_sync(0xffffffffu, WX, cc);
-        const float wb = (cc + 1 < ncols) ? wy * __shfl_sync(0xffffffffu, WX, (cc + 1) & 31) : 0.f;
-        float va[8], vb[8];
-        if (wa != 0.f) load8(rowp + static_cast<size_t>(cc) * lv.ld, va);
-        if (wb != 0.f) load8(rowp + static_cast<size_t>(cc + 1) * lv.ld, vb);
-        if (wa != 0.f) {
+    const int ncell = (rhi - rlo + 1) * ncols;
+    const T* base = feat + (static_cast<size_t>(rlo) * lv.W + clo) * lv.ld + lane * 8;
+    const size_t row_stride = static_cast<size_t>(lv.W) * lv.ld;
+    int rr = 0, cc = 0;
+    for (int c0 = 0; c0 < ncell; c0 += kFly) {
+      float w[kFly];
+      Raw8<T> v[kFly];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + wa * va[j];
-        }
-        if (wb != 0.f) {
+      for (int u = 0; u < kFly; ++u) {
+        const float wy = __shfl_sync(0xffffffffu, WY, rr & 31);
+        const float wx = __shfl_sync(0xffffffffu, WX, cc & 31);
+        w[u] = (c0 + u < ncell) ? wy * wx : 0.f;
+        if (w[u] != 0.f) v[u].load(base + static_cast<size_t>(rr) * row_stride + static_cast<size_t>(cc) * lv.ld);
+        if (++cc == ncols) cc = 0, ++rr;
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + wb * vb[j];
+      for (int u = 0; u < kFly; ++u) {
+        if (w[u] != 0.f) {
+          float val[8];
+          v[u].unpack(val);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + w[u] * val[j];
         }
       }
     }
   } else {
-    for (int s0 = 0; s0 < ns; s0 += 2) {
-      RoiSample<T> A, Bs;
-      A.fetch(feat, lv.H, lv.W, lv.ld, lane, sample_y(s0 / gw), sample_x(s0 % gw));
-      Bs.ok = false;
-      if (s0 + 1 < ns) Bs.fetch(feat, lv.H, lv.W, lv.ld, lane, sample_y((s0 + 1) / gw), sample_x((s0 + 1) % gw));
-      A.accumulate(acc);
-      Bs.accumulate(acc);
+    // bins wider than 32 feature cells (never with detectron2's level assignment): one sample at a time, torchvision's order
+    for (int s0 = 0; s0 < ns; ++s0) {
+      float y = sample_y(s0 / gw), x = sample_x(s0 % gw);
+      if (y < -1.0f || y > fh || x < -1.0f || x > fw) continue;
+      if (y <= 0.f) y = 0.f;
+      if (x <= 0.f) x = 0.f;
+      int yl = static_cast<int>(y), xl = static_cast<int>(x), yh, xh;
+      if (yl >= lv.H - 1) yh = yl = lv.H - 1, y = static_cast<float>(yl);
+      else yh = yl + 1;
+      if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
+      else xh = xl + 1;
+      const float ly = y - static_cast<float>(yl), lx = x - static_cast<float>(xl);
+      const float hy = 1.f - ly, hx = 1.f - lx;
+      const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+      // acc += ((w1 v1 + w2 v2) + w3 v3) + w4 v4, tap by tap (few live registers: this path is never the hot one)
+      float t[8], v[8];
+      load8(feat + (static_cast<size_t>(yl) * lv.W + xl) * lv.ld + lane * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = w1 * v[j];
+      load8(feat + (static_cast<size_t>(yl) * lv.W + xh) * lv.ld + lane * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = t[j] + w2 * v[j];
+      load8(feat + (static_cast<size_t>(yh) * lv.W + xl) * lv.ld + lane * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = t[j] + w3 * v[j];
+      load8(feat + (static_cast<size_t>(yh) * lv.W + xh) * lv.ld + lane * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (t[j] + w4 * v[j]);
     }
   }
 #pragma unroll

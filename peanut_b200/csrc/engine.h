@@ -62,6 +62,12 @@ inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = debug_no_pdl() ? 0 : 1;
+  static const bool only_in_graph = debug_flag("PN_DEBUG_PDL_ONLY_IN_GRAPH");  // diagnosis: plain launches outside stream capture
+  if (only_in_graph) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &st);
+    if (st != cudaStreamCaptureStatusActive) attr[0].val.programmaticStreamSerializationAllowed = 0;
+  }
   cfg.attrs = attr, cfg.numAttrs = 1;
   PN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...));
 }
@@ -200,6 +206,8 @@ struct Net {
     if (fwd_pending && fwd_stream != s) PN_CUDA_CHECK(cudaStreamWaitEvent(s, fwd_done, 0));
   }
   void end_forward(cudaStream_t s) {
+    static const bool off = debug_flag("PN_DEBUG_NO_FWD_ORDER");  // diagnosis only
+    if (off) return;
     if (!fwd_done) PN_CUDA_CHECK(cudaEventCreateWithFlags(&fwd_done, cudaEventDisableTiming));
     PN_CUDA_CHECK(cudaEventRecord(fwd_done, s));
     fwd_stream = s, fwd_pending = true;

@@ -106,6 +106,8 @@ void launch_map_stamp_local(const float* local_map, float* full_map, const int* 
                             int full_w, int full_h, cudaStream_t s);
 void launch_map_crop(const float* full_map, int E, int nc, int full_w, int full_h, int x1, int y1, int win_w, int win_h,
                      int nc_copy, float* out, int out_channels, cudaStream_t s);
+void launch_global_goal(int device, int num_sms, const pn_goal_cfg& cfg, const pn_goal_arrays& arrays, int E, int only_distance,
+                        cudaStream_t s);
 void map_bookkeeping(int op, const pn_map_cfg& cfg, const pn_map_arrays& arrays, int E, cudaStream_t s);
 void launch_goal_map(const float* local_map, int E, int nc, int w, int h, const int* goal_cat, const int* skip_morph,
                      const int* global_goal, int goal_erode, float* goal_map, int* found, cudaStream_t s);

@@ -8,6 +8,7 @@ and the planner: ``full_map`` / ``local_map``, ``full_pose`` / ``local_pose``, `
     stamp_initial()          agent_state.py:116-122   (the stamp of init_with_obs, after the first mapper call)
     update_local_map()       agent_state.py:276-303   (everything after the sem_map_module call)
     update_full_map()        agent_state.py:308-338
+    update_global_goal()     agent_state.py:376-416   (obstacle dilation, geodesic distance field, exp weighting, argmax goal)
     update_goal_map()        agent_state.py:423-452   (goal found on the map? erode / dilate / no-other-category mask)
 
 The reference computes every cell index on the host from ``pose.cpu().numpy()`` (three blocking device syncs per step and
@@ -116,6 +117,47 @@ class MapState:
                                             int(goal_erode), self.goal_map.data_ptr(), self.found_goal.data_ptr(),
                                             ctypes.c_void_p(stream)))
         return self.goal_map, self.found_goal
+
+    def update_global_goal(self, target_pred, dist_weight_temperature=500.0, collision_map=None, visited_vis=None,
+                           only_distance=False):
+        """``Agent_State.update_global_goal`` for all environments (N1b).  ``target_pred``: float32 CUDA tensor
+        [E, local_w, local_h] (``agent_prediction.update_prediction(..., as_numpy=False)`` per environment);
+        ``collision_map`` / ``visited_vis``: uint8 CUDA tensors [E, full_w, full_h] (1 = set) or None - the reference
+        keeps them on the host in the planner helper (agent_helper.py), here the caller uploads them when they change.
+        Updates ``self.global_goals`` (and ``goal_kind`` / ``last_global_goal`` / ``last_kind`` / ``dd_wt``) in place and sets
+        ``self.dd`` [E, full_w, full_h] float64 (inf = not traversible / unreachable) and ``self.value`` [E, local_w, local_h]
+        float64.  Uses ``self.loc`` as written by ``update_local_map``.  Returns ``self.global_goals``."""
+        dev = self.full_map.device
+        E = self.E
+        if not hasattr(self, "dd"):
+            self.dd = torch.empty((E, self.full_w, self.full_h), dtype=torch.float64, device=dev)
+            self.dd_wt = torch.zeros((E, self.local_w, self.local_h), dtype=torch.float64, device=dev)
+            self.dd_wt_valid = torch.zeros((E,), dtype=torch.int32, device=dev)          # agent_state.py:88 (None)
+            self.value = torch.zeros((E, self.local_w, self.local_h), dtype=torch.float64, device=dev)
+            self.goal_kind = torch.ones((E,), dtype=torch.int32, device=dev)             # :127-129 list of lists
+            self.last_global_goal = torch.zeros((E, 2), dtype=torch.int32, device=dev)
+            self.last_kind = torch.zeros((E,), dtype=torch.int32, device=dev)            # :89 (None)
+        if not only_distance:
+            if not (torch.is_tensor(target_pred) and target_pred.is_cuda and target_pred.dtype == torch.float32 and
+                    tuple(target_pred.shape) == (E, self.local_w, self.local_h) and target_pred.is_contiguous()):
+                raise TypeError("target_pred must be a contiguous float32 CUDA tensor [E, local_w, local_h]")
+        for name, t in (("collision_map", collision_map), ("visited_vis", visited_vis)):
+            if t is not None and not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and
+                                      tuple(t.shape) == (E, self.full_w, self.full_h)):
+                raise TypeError(f"{name} must be a contiguous uint8 CUDA tensor [E, full_w, full_h]")
+        self._arrays()
+        cfg = _lib.GoalCfg(self.nc, self.full_w, self.full_h, self.local_w, self.local_h, int(self.cfg.col_rad),
+                           int(self.cfg.map_resolution), float(dist_weight_temperature))
+        ptr = lambda t: None if t is None else t.data_ptr()
+        arrays = _lib.GoalArrays(self.full_map.data_ptr(), ptr(collision_map), ptr(visited_vis), self.lmb.data_ptr(),
+                                 self.loc.data_ptr(), None if only_distance else target_pred.data_ptr(), self.dd.data_ptr(),
+                                 self.dd_wt.data_ptr(), self.dd_wt_valid.data_ptr(), self.value.data_ptr(),
+                                 self.global_goals.data_ptr(), self.goal_kind.data_ptr(), self.last_global_goal.data_ptr(),
+                                 self.last_kind.data_ptr())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.ctx.lib.pn_global_goal(self.ctx.handle, ctypes.byref(cfg), ctypes.byref(arrays), E,
+                                               1 if only_distance else 0, ctypes.c_void_p(stream)))
+        return self.global_goals
 
     def planner_inputs(self):
         """One readback of the small per-environment state (the reference's host-side fields)."""

@@ -99,7 +99,9 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     builder = load_reference_modules()
-    cases = [("c14_96", 14, 96, 96, 0, 3), ("c14_120x88", 14, 120, 88, 1, 5), ("c24_64", 24, 64, 64, 2, 7)]
+    # the last case is BASELINE.json's headline map shape (24 x 240 x 240) with the weights bench.py uses (seed 0)
+    cases = [("c14_96", 14, 96, 96, 0, 3), ("c14_120x88", 14, 120, 88, 1, 5), ("c24_64", 24, 64, 64, 2, 7),
+             ("c24_240", 24, 240, 240, 0, 1234)]
     for name, C, H, W, wseed, xseed in cases:
         ref = builder.build_segmentor(reference_model_cfg(C))
         sd = O.synth_state_dict(C, 6, seed=wseed)

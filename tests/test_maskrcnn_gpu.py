@@ -241,10 +241,43 @@ def test_end_to_end_reference_frame_tf32(weights):
     n_ref = taps["det_boxes"].shape[0]
     assert n_ref > 0
     matched = _match(taps["det_boxes"], taps["det_classes"], bx, cl)
-    assert matched >= 0.8 * n_ref, f"only {matched} of {n_ref} oracle detections found"
+    # measured (tools/e2e_parity_probe.py, three frames): 90-94 of 100 detections matched, 99.64-99.73 % of the cells of the
+    # category map agree.  The rest are instances whose score / NMS decision sits within the tf32 storage noise (2^-11 per
+    # stored activation, amplified through 33 residual blocks to ~2e-3 of the feature range) of a threshold: random
+    # weights and SCORE_THRESH 0.3 put ~100 candidates per frame there.
+    assert matched >= 0.85 * n_ref, f"only {matched} of {n_ref} oracle detections found"
     ref_sem = O.accumulate(ref["masks"], ref["scores"], ref["classes"], 9, THR, THR, None, 480, 640)
     agree = ((sem.cpu()[0] > 0) == (ref_sem > 0)).float().mean().item()
-    assert agree >= 0.97, f"category-mask agreement {agree}"
+    assert agree >= 0.99, f"category-mask agreement {agree}"
+
+
+def test_end_to_end_reference_frame_bf16(weights):
+    """The throughput path end to end at the reference's geometry, against the oracle with the same bf16 storage rounding
+    emulated (oracle/maskrcnn.py `_r`): detections and the category stack.  bf16 storage noise (2^-8 per stored activation,
+    ~1.5e-2 of the feature range at res5) flips far more near-threshold decisions than tf32 does - measured on three frames:
+    54-63 of 100 detections matched at IoU >= 0.9, 98.3-98.5 % of the category-map cells agree (97.3-97.4 % bit-equal incl.
+    overlap counts) - which is why the drop-in shims default to tf32 and bf16 is an explicit throughput opt-in."""
+    frame = O.synth_rgb(11)
+    cfg = O.Cfg(score_thresh=THR)
+    taps = {}
+    ref = O.forward(frame, weights, cfg, emulate_bf16=True, taps=taps)
+    e = _engine(weights, "bf16", h=480, w=640, min_size=800, max_size=1333)
+    sem = e.forward_device(torch.from_numpy(frame)[None].cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR)
+    torch.cuda.synchronize()
+    nd = int(e.read_tap("det_count", (1,), torch.int32).item())
+    bx = e.read_tap("det_boxes", (100, 4)).cpu()[:nd]
+    cl = e.read_tap("det_classes", (100,), torch.int32).cpu()[:nd].long()
+    n_ref = taps["det_boxes"].shape[0]
+    assert n_ref > 0 and nd > 0
+    matched = _match(taps["det_boxes"], taps["det_classes"], bx, cl)
+    assert matched >= 0.40 * n_ref, f"only {matched} of {n_ref} oracle detections found"
+    loose = _match(taps["det_boxes"], taps["det_classes"], bx, cl, iou_thr=0.5)
+    assert loose >= 0.60 * n_ref, f"only {loose} of {n_ref} oracle detections found at IoU 0.5"
+    ref_sem = O.accumulate(ref["masks"], ref["scores"], ref["classes"], 9, THR, THR, None, 480, 640)
+    got = sem.cpu()[0]
+    agree = ((got > 0) == (ref_sem > 0)).float().mean().item()
+    assert agree >= 0.975, f"category-mask agreement {agree}"
+    assert (got == got.round()).all() and float(got[..., 9].abs().sum()) == 0
 
 
 def test_reference_api_and_goal_gate(weights):

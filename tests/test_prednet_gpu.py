@@ -133,6 +133,34 @@ def test_tf32_vs_reference_golden(path):
     assert np.array_equal(got.argmax(0)[decided], ref.argmax(0)[decided])
 
 
+@pytest.mark.parametrize("path", [p for p in _golden_cases() if "c24_" in p], ids=lambda p: p.rsplit("/", 1)[-1])
+def test_bf16_vs_reference_golden_24_channels(path):
+    """The throughput path (bf16 storage) at BASELINE.json's map shape (24 x 240 x 240, and 24 x 64 x 64) against the logits
+    of the reference's own model code: 5e-2 of the logit range; argmax category map equal wherever the reference's top-2
+    margin exceeds twice that; probabilities within 1.5e-2."""
+    g = np.load(path)
+    C, H, W, wseed, xseed, _ = (int(v) for v in g["meta"])
+    sd = oracle.synth_state_dict(C, 6, seed=wseed)
+    seg = prediction.init_segmentor(prediction._default_cfg(C, 6), device="cuda:0", precision="bf16", state_dict=sd)
+    x = oracle.synth_partial_map(C, H, W, seed=xseed)
+    got = prediction.run_inference(seg, x)[0]
+    ref = g["logits"]
+    rng = float(np.abs(ref).max())
+    tol = 5e-2 * rng
+    err = float(np.abs(got - ref).max())
+    assert got.shape == ref.shape and err <= tol, (err, tol)
+    top2 = np.sort(ref, axis=0)[-2:]
+    decided = (top2[1] - top2[0]) > 2 * tol
+    assert decided.mean() > 0.2
+    assert np.array_equal(got.argmax(0)[decided], ref.argmax(0)[decided])
+    # the fraction of ALL cells whose argmax agrees is reported by the assertion message if it ever drops
+    agree = float((got.argmax(0) == ref.argmax(0)).mean())
+    assert agree >= 0.97, agree
+    xd = torch.from_numpy(x)[None].cuda()
+    prob = seg.forward_device(xd, apply_sigmoid=True).cpu().numpy()[0]
+    assert float(np.abs(prob - 1.0 / (1.0 + np.exp(-ref.astype(np.float64)))).max()) <= 1.5e-2
+
+
 def test_tf32_reference_shape_720(weights, oracle_model):
     """The reference's own geometry (14 x 720 x 720, nav/arguments.py:40,74): tf32 path vs the fp32 oracle."""
     x = oracle.synth_partial_map(14, 720, 720, seed=21)

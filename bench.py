@@ -63,6 +63,7 @@ def parse():
     p.add_argument("--no-profile", action="store_true")
     p.add_argument("--no-latency", action="store_true", help="skip the nested batch-1 tf32 (configs[1]) block")
     p.add_argument("--no-ref-gpu", action="store_true", help="skip the eager-PyTorch-on-GPU comparator (ref_gpu_eager)")
+    p.add_argument("--no-scaling-base", action="store_true", help="skip the 1-GPU run of the multi-GPU workload (scaling_base)")
     p.add_argument("--verbose", action="store_true")
     return p.parse_args()
 
@@ -412,6 +413,13 @@ def run_ours(a):
     if world == 1 and name != "cfg1" and not a.no_latency:
         latency = measure(a, "cfg1", rank, local, world, dev, map_shape, max(steps, 30), False, "none")
 
+    # The multi-GPU default workload (cfg3: 8 envs per GPU) differs from the 1-GPU headline (cfg2: 32 frames), so the 1-GPU
+    # line also carries the 1-GPU number of cfg3: the base a weak-scaling efficiency of the N > 1 lines has to be taken
+    # against (value(N) / (N * scaling_base.value)).
+    scaling_base = None
+    if world == 1 and name != "cfg3" and a.workload == "auto" and not a.no_scaling_base:
+        scaling_base = measure(a, "cfg3", rank, local, world, dev, map_shape, steps, False, "none")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -439,6 +447,14 @@ def run_ours(a):
                            "ms_per_step": latency["dev_ms"], "e2e_frames_per_s": 1000.0 / latency["e2e_ms"],
                            "e2e_ms_per_step": latency["e2e_ms"], "steps": max(steps, 30),
                            "roofline": latency.get("roofline")}
+
+    if scaling_base is not None:
+        line["scaling_base"] = {"workload": scaling_base["desc"], "envs_per_gpu": scaling_base["E"], "n_gpus": 1,
+                                "value": scaling_base["E"] / (scaling_base["dev_ms"] / 1000.0), "unit": "frames/s",
+                                "ms_per_step": scaling_base["dev_ms"],
+                                "e2e_value": scaling_base["E"] / (scaling_base["e2e_ms"] / 1000.0),
+                                "note": "the N > 1 lines run THIS workload per GPU (plus the result gather inside the step): "
+                                        "weak-scaling efficiency = value(N) / (N * this value)"}
 
     # ---- the reference's GPU path (eager PyTorch restatement with the reference's host round trips), a reported comparator
     if world == 1 and not a.no_ref_gpu:

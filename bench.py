@@ -368,6 +368,10 @@ def measure(a, name, rank, local, world, dev, map_shape, steps, with_clocks, gat
             if fl > 0:
                 conv_ms += ms
                 conv_fl += fl * (live if opname.startswith("roi_heads.mask_head") else 1.0)
+        glue_ms = None
+        if a.mode == "dependent":   # glue + mapper + stamp + window: launches outside the two networks' launch lists
+            glue_ms = pipe.time_glue_mapper_window(d["rgb"], d["depth"], d["delta"], maps, poses, d["pmap"])
+            all_ms += glue_ms
         n_conv = sum(1 for _, _, fl in prof_a + prof_c if fl > 0)
         achieved = conv_fl / (conv_ms / 1000.0) / 1e12
         key = "bf16" if precision == "bf16" else "tf32"
@@ -385,6 +389,7 @@ def measure(a, name, rank, local, world, dev, map_shape, steps, with_clocks, gat
                            # serialised launch time; > 1 would mean overlap hid part of it
                            "share_of_step": conv_ms / dev_ms, "share_of_serialised_launches": conv_ms / all_ms,
                            "step_flops_over_step_time": conv_fl / (dev_ms / 1000.0) / 1e12,
+                           "glue_mapper_window_ms_per_step": glue_ms,
                            "detections_per_frame": ndet / float(E), "peak_source": src[key],
                            "how": "CUDA events around every launch (eager replay of the recorded launch list after the timed region)"}
     if gather is not None:

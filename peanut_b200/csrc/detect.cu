@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(256, 3) k_roi_align_staged(Pyramid pyr, const 
           float val[8];
           load8(reinterpret_cast<const T*>(rowp + static_cast<size_t>(cc) * 64), val);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + w * val[j];
+          for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w, val[j], acc[j]);   // one rounding per term (the file is compiled with -fmad=false)
         }
       }
 #pragma unroll
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* 
           float val[8];
           v[u].unpack(val);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = acc[j] + w[u] * val[j];
+          for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w[u], val[j], acc[j]);   // same fused form as the staged kernel: bit-identical
         }
       }
     }

@@ -250,7 +250,7 @@ __device__ __forceinline__ void upwind(double m1, double m2, double p1, double p
   // the marcher scans j = -1 first and replaces only on a strictly smaller value
   if (p1 < m1) v1 = p1, v2 = p2;
   else v1 = m1, v2 = m2;
-  if (!(v2 <= v1)) v2 = dinf();
+  if (!(v1 < dinf()) || !(v2 <= v1)) v2 = dinf();   // second order only behind a known first neighbour
 }
 __device__ __forceinline__ void add_terms(double v1, double v2, double& a, double& b, double& c) {
   if (v2 < dinf()) {

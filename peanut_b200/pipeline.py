@@ -105,15 +105,11 @@ class PerceptionPipeline:
                                     precision=self._precision)
         return self._pred1
 
-    def _step_dependent(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat):
-        """A -> glue -> B -> stamp -> crop -> C on the caller's stream (the reference's chain, agent_state.py:273-274 then
-        :350-361).  ``partial_map`` [E,C,Hm,Wm] is the net's input buffer: its first min(C, nc) planes are OVERWRITTEN with
-        the prediction window of the updated full map."""
+    def _glue_mapper_window(self, rgb, depth, pose_delta, local_map, poses, partial_map):
+        """Everything between stage A and stage C of the dependent chain, on the current stream: `_preprocess_obs` glue,
+        the mapper, and update_prediction's stamp + prediction window (agent_state.py:350-360)."""
         a = self.args
         main = torch.cuda.current_stream(self.device)
-        self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
-        if self._depth_ready is not None:
-            main.wait_event(self._depth_ready)
         stream = ctypes.c_void_p(main.cuda_stream)
         lib, h = self.seg.ctx.lib, self.seg.ctx.handle
         _lib.check(lib.pn_make_obs(h, depth.data_ptr(), rgb.data_ptr(), self.sem.data_ptr(), self.E, a.env_frame_height,
@@ -127,8 +123,35 @@ class PerceptionPipeline:
             main.wait_event(self._pmap_ready)
         _lib.check(lib.pn_map_crop_window(h, self.full_map.data_ptr(), self.E, self.nc, self.full_w, self.full_h, self.win_x1,
                                           self.win_y1, Hm, Wm, self.win_channels, partial_map.data_ptr(), Cm, stream))
+        return fp, new_map, poses
+
+    def _step_dependent(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat):
+        """A -> glue -> B -> stamp -> crop -> C on the caller's stream (the reference's chain, agent_state.py:273-274 then
+        :350-361).  ``partial_map`` [E,C,Hm,Wm] is the net's input buffer: its first min(C, nc) planes are OVERWRITTEN with
+        the prediction window of the updated full map."""
+        a = self.args
+        main = torch.cuda.current_stream(self.device)
+        self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
+        if self._depth_ready is not None:
+            main.wait_event(self._depth_ready)
+        fp, new_map, poses = self._glue_mapper_window(rgb, depth, pose_delta, local_map, poses, partial_map)
         pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
         return self.sem, fp, new_map, poses, pred
+
+    def time_glue_mapper_window(self, rgb, depth, pose_delta, local_map, poses, partial_map, iters=5):
+        """Device milliseconds of the kernels between stage A and stage C (CUDA events, after one warm-up): what the
+        per-launch profiles of the two networks do not cover.  Dependent mode only."""
+        if self.mode != "dependent":
+            raise RuntimeError("time_glue_mapper_window: dependent mode only")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p = poses.clone()
+        self._glue_mapper_window(rgb, depth, pose_delta, local_map, p, partial_map)
+        e0.record()
+        for _ in range(iters):
+            self._glue_mapper_window(rgb, depth, pose_delta, local_map, p, partial_map)
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        return e0.elapsed_time(e1) / iters
 
     def step_device(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat=None):
         """All CUDA tensors: rgb uint8 [E,H,W,3]; depth float32 [E,H,W] (simulator units, 0 = invalid);

@@ -58,6 +58,8 @@ def parse():
                    help="dependent = the reference's chain A -> B -> C (headline); overlapped = C on the stale map, side stream")
     p.add_argument("--envs", type=int, default=0, help="override environments per GPU")
     p.add_argument("--precision", default="", choices=["", "bf16", "tf32"])
+    p.add_argument("--micro-batches", type=int, default=0,
+                   help="dependent mode: pipeline the chain over this many groups of environments (0 = the workload's default)")
     p.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"], help="result gather inside the step (N > 1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-profile", action="store_true")
@@ -236,15 +238,23 @@ def measure(a, name, rank, local, world, dev, map_shape, steps, with_clocks, gat
     import torch
     import torch.distributed as dist
     from peanut_b200 import parallel
-    from peanut_b200.pipeline import PerceptionPipeline
+    from peanut_b200.pipeline import MicroBatchedPipeline, PerceptionPipeline
 
     wl = WORKLOADS[name]
     E = a.envs or wl["envs"]
     precision = a.precision or wl["precision"]
     wa, wc = synth_weights(map_shape[0])
     log(f"{name}: building E={E} {precision} mode={a.mode}")
-    pipe = parallel.build_synchronised(lambda: PerceptionPipeline(wa, wc, num_envs=E, device=dev, precision=precision,
-                                                                  map_shape=map_shape, mode=a.mode))
+    mb = a.micro_batches or wl.get("micro_batches", 1)
+    if a.mode != "dependent" or mb < 2 or E % mb != 0:
+        mb = 1
+    if mb > 1:
+        pipe = parallel.build_synchronised(lambda: MicroBatchedPipeline(wa, wc, num_envs=E, micro_batches=mb, device=dev,
+                                                                        precision=precision, map_shape=map_shape))
+    else:
+        pipe = parallel.build_synchronised(lambda: PerceptionPipeline(wa, wc, num_envs=E, device=dev, precision=precision,
+                                                                      map_shape=map_shape, mode=a.mode))
+    engines = pipe.subs if mb > 1 else [pipe]
     host = synth_inputs(E, map_shape, rank)
     pin = {k: v.pin_memory() for k, v in host.items()}
     d = {k: v.to(dev) for k, v in host.items()}
@@ -255,7 +265,7 @@ def measure(a, name, rank, local, world, dev, map_shape, steps, with_clocks, gat
     if world > 1 and gather_kind != "none":
         if gather_kind == "peer":
             try:  # raises on every rank together if any rank cannot map the root's slab (CUDA IPC not permitted ...)
-                gather, gather_impl = parallel.PeerGather(pipe.seg.ctx, pipe.pred_out), "peer (pn_gather_*: one-sided NVLink push + flags)"
+                gather, gather_impl = parallel.PeerGather(engines[0].seg.ctx, pipe.pred_out), "peer (pn_gather_*: one-sided NVLink push + flags)"
             except RuntimeError as e:
                 print(f"[bench] rank {rank}: {e}; falling back to the NCCL gather", file=sys.stderr, flush=True)
                 gather = None
@@ -350,17 +360,17 @@ def measure(a, name, rank, local, world, dev, map_shape, steps, with_clocks, gat
     if gather_status != 0:
         raise RuntimeError(f"result gather timed out (status {gather_status})")
 
-    out = dict(name=name, E=E, precision=precision, dev_ms=dev_ms, e2e_ms=e2e_ms, gather_ms=gather_ms, gather_impl=gather_impl,
+    out = dict(name=name, E=E, precision=precision, micro_batches=mb, dev_ms=dev_ms, e2e_ms=e2e_ms, gather_ms=gather_ms, gather_impl=gather_impl,
                wall_ms=1000.0 * t_wall / steps, clocks=clocks, launches=pipe.launches_per_step() + (2 if gather is not None else 0),
                h2d=pipe.h2d_bytes(pin["rgb"], pin["depth"], pin["delta"], pin["pmap"]), d2h=pipe.d2h_bytes(), desc=wl["desc"])
 
     # ---- roofline of the dominant kernel (conv_umma_kernel: every conv / FC of both networks), rank 0
     if rank == 0 and not a.no_profile:
         peaks, src = load_peaks()
-        prof_a = pipe.seg.profile(3)
-        prof_c = pipe.pred.profile(3)
+        prof_a = [x for e in engines for x in e.seg.profile(3)]
+        prof_c = [x for e in engines for x in e.pred.profile(3)]
         # mask-head ops are recorded at capacity (100 ROIs / frame) but run only on the live detections
-        ndet = int(pipe.seg.read_tap("det_count", (E,), torch.int32).sum().item())
+        ndet = sum(int(e.seg.read_tap("det_count", (e.E,), torch.int32).sum().item()) for e in engines)
         live = ndet / float(E * 100)
         conv_ms, conv_fl, all_ms = 0.0, 0.0, 0.0
         for opname, ms, fl in prof_a + prof_c:
@@ -370,7 +380,11 @@ def measure(a, name, rank, local, world, dev, map_shape, steps, with_clocks, gat
                 conv_fl += fl * (live if opname.startswith("roi_heads.mask_head") else 1.0)
         glue_ms = None
         if a.mode == "dependent":   # glue + mapper + stamp + window: launches outside the two networks' launch lists
-            glue_ms = pipe.time_glue_mapper_window(d["rgb"], d["depth"], d["delta"], maps, poses, d["pmap"])
+            glue_ms = 0.0
+            for i, e in enumerate(engines):
+                sl = slice(i * e.E, (i + 1) * e.E)
+                glue_ms += e.time_glue_mapper_window(d["rgb"][sl], d["depth"][sl], d["delta"][sl], d["maps"][sl], d["poses"][sl].clone(),
+                                                     d["pmap"][sl])
             all_ms += glue_ms
         n_conv = sum(1 for _, _, fl in prof_a + prof_c if fl > 0)
         achieved = conv_fl / (conv_ms / 1000.0) / 1e12
@@ -437,6 +451,7 @@ def run_ours(a):
             "config": {"workload": m["desc"], "envs_per_gpu": m["E"], "frame": [480, 640], "map_shape": list(map_shape),
                        "mode": a.mode + (" (reference order: Mask-RCNN -> mapper -> stamp + window -> map completion)"
                                          if a.mode == "dependent" else " (map completion on the caller's stale map, side stream)"),
+                       "micro_batches": m["micro_batches"],
                        "l2": "256 MiB flush write between timed iterations", "timing": "CUDA events per step, max over ranks",
                        "wall_ms_per_step_incl_flush": m["wall_ms"],
                        "gather": m["gather_impl"], "gather_in_step": world > 1 and a.gather != "none", "gather_ms": m["gather_ms"]},

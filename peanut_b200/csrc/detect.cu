@@ -572,174 +572,15 @@ struct Raw8<float> {
 };
 
 
-// Geometry of one ROI on its pyramid level (detectron2's level rule, ROIAlignV2 sampling), shared by both kernels.
-struct RoiGeom {
-  PyramidLevel lv;
-  float rsw, rsh, bin_w, bin_h;
-  int gh, gw;
-  float count;
-  __device__ __forceinline__ void init(const Pyramid& pyr, const float* boxes, int r, int S) {
-    const float x1 = boxes[r * 4], y1 = boxes[r * 4 + 1], x2 = boxes[r * 4 + 2], y2 = boxes[r * 4 + 3];
-    const float size = sqrtf((x2 - x1) * (y2 - y1));
-    float lvf = floorf(4.f + log2f(size / 224.f + 1e-8f));
-    lvf = fminf(fmaxf(lvf, 2.f), 5.f);
-    const int li = static_cast<int>(lvf) - 2;
-    // (a switch instead of pyr.lv[li]: dynamic indexing of a kernel parameter would copy it to local memory)
-    lv = li == 0 ? pyr.lv[0] : (li == 1 ? pyr.lv[1] : (li == 2 ? pyr.lv[2] : pyr.lv[3]));
-    rsw = x1 * lv.scale - 0.5f, rsh = y1 * lv.scale - 0.5f;
-    const float rew = x2 * lv.scale - 0.5f, reh = y2 * lv.scale - 0.5f;
-    const float rw = rew - rsw, rh = reh - rsh;
-    bin_h = rh / static_cast<float>(S), bin_w = rw / static_cast<float>(S);
-    gh = static_cast<int>(ceilf(rh / static_cast<float>(S)));
-    gw = static_cast<int>(ceilf(rw / static_cast<float>(S)));
-    count = static_cast<float>(max(gh * gw, 1));
-  }
-  __device__ __forceinline__ float sample_y(int ph, int iy) const {
-    return rsh + static_cast<float>(ph) * bin_h + (static_cast<float>(iy) + .5f) * bin_h / static_cast<float>(gh);
-  }
-  __device__ __forceinline__ float sample_x(int pw, int ix) const {
-    return rsw + static_cast<float>(pw) * bin_w + (static_cast<float>(ix) + .5f) * bin_w / static_cast<float>(gw);
-  }
-  // feature rows / columns touched by bins [p0, p1] along one axis (n = H or W)
-  __device__ __forceinline__ void span(bool rows, int p0, int p1, int& lo, int& hi) const {
-    const int n = rows ? lv.H : lv.W, g = rows ? gh : gw;
-    const float fn = static_cast<float>(n);
-    const float a = rows ? sample_y(p0, 0) : sample_x(p0, 0);
-    const float b = rows ? sample_y(p1, g - 1) : sample_x(p1, g - 1);
-    lo = min(static_cast<int>(fminf(fmaxf(a, 0.f), fn)), n - 1);
-    hi = min(static_cast<int>(fminf(fmaxf(b, 0.f), fn)) + 1, n - 1);
-  }
-};
-
-constexpr int kRoiStageCells = 1024;   // footprint cells the staged kernel holds (64 bytes each)
-constexpr int kRoiMaxSpan = 64;        // rows / columns of a staged footprint
-
-// Does the staged kernel take this ROI?  (Everything detectron2's level assignment produces except extreme aspect ratios.)
-__device__ __forceinline__ bool roi_is_staged(const RoiGeom& g, int S, int& r0, int& r1, int& c0, int& c1) {
-  if (g.gh * g.gw <= 0) return false;
-  g.span(true, 0, S - 1, r0, r1);
-  g.span(false, 0, S - 1, c0, c1);
-  const int nr = r1 - r0 + 1, ncol = c1 - c0 + 1;
-  return nr <= kRoiMaxSpan && ncol <= kRoiMaxSpan && nr * ncol <= kRoiStageCells;
-}
-
-// Staged ROIAlign: one CTA per ROI.  The ROI's whole footprint on its level is copied to shared memory once per slice of
-// 64 bytes of channels (32 bf16 / 16 fp32 channels; cp.async, every cell read from L2 exactly once instead of once per
-// overlapping bin), the separable bilinear weights WY[bin row][feature row] / WX[bin column][feature column] are computed
-// once per ROI, and thread (bin, 8 channels) accumulates its bin from shared memory - rows outer, columns inner, zero
-// weights skipped, the same products in the same order as k_roi_align below (bit-identical results).
-template <typename T>
-__global__ void __launch_bounds__(256, 3) k_roi_align_staged(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
-                                                              int S, T* __restrict__ out, long long ldo) {
-  pdl_grid_sync();
-  extern __shared__ __align__(16) uint8_t roi_smem[];   // [cells][64 B]
-  __shared__ float WY[14][kRoiMaxSpan], WX[14][kRoiMaxSpan];
-  __shared__ int ylo[14], yhi[14], xlo[14], xhi[14];
-  const int r = blockIdx.x;
-  const int b = img[r];
-  if (b < 0) return;
-  RoiGeom g;
-  g.init(pyr, boxes, r, S);
-  int r0, r1, c0, c1;
-  if (!roi_is_staged(g, S, r0, r1, c0, c1)) return;   // k_roi_align takes it
-  const int nr = r1 - r0 + 1, ncol = c1 - c0 + 1, ncell = nr * ncol;
-  const int tid = threadIdx.x;
-  const float fh = static_cast<float>(g.lv.H), fw = static_cast<float>(g.lv.W);
-  // ---- separable weights, accumulated over the bin's samples in sample order (as k_roi_align does per lane)
-  for (int i = tid; i < 2 * S * kRoiMaxSpan; i += blockDim.x) {
-    const bool rows = i < S * kRoiMaxSpan;
-    const int j = rows ? i : i - S * kRoiMaxSpan;
-    const int pb = j / kRoiMaxSpan, k = j % kRoiMaxSpan;   // bin index along the axis, footprint row / column
-    const int n = rows ? g.lv.H : g.lv.W, gs = rows ? g.gh : g.gw;
-    const int cell = (rows ? r0 : c0) + k;
-    const float fn = rows ? fh : fw;
-    float wsum = 0.f;
-    for (int is = 0; is < gs; ++is) {
-      float v = rows ? g.sample_y(pb, is) : g.sample_x(pb, is);
-      if (v < -1.0f || v > fn) continue;
-      if (v <= 0.f) v = 0.f;
-      int lo = static_cast<int>(v), hi;
-      if (lo >= n - 1) hi = lo = n - 1, v = static_cast<float>(lo);
-      else hi = lo + 1;
-      const float l = v - static_cast<float>(lo), h = 1.f - l;
-      if (cell == lo) wsum += h;
-      if (cell == hi) wsum += l;
-    }
-    (rows ? WY : WX)[pb][k] = wsum;
-  }
-  if (tid < 2 * S) {
-    const bool rows = tid < S;
-    const int pb = rows ? tid : tid - S;
-    int lo, hi;
-    g.span(rows, pb, pb, lo, hi);
-    if (rows) ylo[pb] = lo - r0, yhi[pb] = hi - r0;
-    else xlo[pb] = lo - c0, xhi[pb] = hi - c0;
-  }
-  constexpr int kChan = 64 / static_cast<int>(sizeof(T));   // channels per staged slice
-  constexpr int kGroups = kChan / 8;                         // 8-channel groups per slice
-  const T* feat = static_cast<const T*>(g.lv.ptr) + static_cast<size_t>(b) * g.lv.H * g.lv.W * g.lv.ld;
-  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(roi_smem));
-  const int nitems = S * S * kGroups;
-  for (int ch0 = 0; ch0 < 256; ch0 += kChan) {
-    __syncthreads();   // the previous slice is no longer read (first pass: the weights are written)
-    for (int pc = tid; pc < ncell * 4; pc += blockDim.x) {
-      const int cell = pc >> 2, part = pc & 3;
-      const int rr = cell / ncol, cc = cell - rr * ncol;
-      const T* src = feat + (static_cast<size_t>(r0 + rr) * g.lv.W + (c0 + cc)) * g.lv.ld + ch0 + part * (16 / static_cast<int>(sizeof(T)));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + static_cast<uint32_t>(pc) * 16u), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    for (int item = tid; item < nitems; item += blockDim.x) {
-      const int bin = item / kGroups, grp = item - bin * kGroups;
-      const int ph = bin / S, pw = bin - ph * S;
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      const int xa = xlo[pw], xb = xhi[pw];
-      for (int rr = ylo[ph]; rr <= yhi[ph]; ++rr) {
-        const float wy = WY[ph][rr];
-        if (wy == 0.f) continue;
-        const uint8_t* rowp = roi_smem + (static_cast<size_t>(rr) * ncol) * 64 + grp * (8 * sizeof(T));
-        for (int cc = xa; cc <= xb; ++cc) {
-          const float w = wy * WX[pw][cc];
-          if (w == 0.f) continue;
-          float val[8];
-          load8(reinterpret_cast<const T*>(rowp + static_cast<size_t>(cc) * 64), val);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w, val[j], acc[j]);   // one rounding per term (the file is compiled with -fmad=false)
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = acc[j] / g.count;
-        if (sizeof(T) == 4) {
-          uint32_t q;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(acc[j]));
-          acc[j] = __uint_as_float(q);
-        }
-      }
-      store8(out + (static_cast<size_t>(r) * S * S + bin) * ldo + ch0 + grp * 8, acc);
-    }
-  }
-}
-
 // grid = (S bin rows, ROIs); block = S warps: warp pw owns output bin (ph = blockIdx.x, pw); lane = 8 channels.
 // Samples are visited in torchvision's order (iy outer, ix inner) with the loads of two samples in flight.
 template <typename T>
 __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
-                                                   int S, T* __restrict__ out, long long ldo, int skip_staged) {
+                                                   int S, T* __restrict__ out, long long ldo) {
   pdl_grid_sync();
   const int r = blockIdx.y;
   const int b = img[r];
   if (b < 0) return;
-  if (skip_staged) {  // k_roi_align_staged has done this ROI
-    RoiGeom g;
-    g.init(pyr, boxes, r, S);
-    int a0, a1, b0, b1;
-    if (roi_is_staged(g, S, a0, a1, b0, b1)) return;
-  }
   const float x1 = boxes[r * 4], y1 = boxes[r * 4 + 1], x2 = boxes[r * 4 + 2], y2 = boxes[r * 4 + 3];
   const float size = sqrtf((x2 - x1) * (y2 - y1));
   float lvf = floorf(4.f + log2f(size / 224.f + 1e-8f));
@@ -794,33 +635,37 @@ __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* 
       if (clo + lane == xl) WX += hx;
       if (clo + lane == xh) WX += lx;
     }
-    // Cells of the footprint in row-major order, kFly independent 16 / 32-byte loads in flight per lane before the first
-    // one is consumed (the loop is latency-bound: ~16 dependent L2 round trips per bin otherwise).  Same products, same
+    // Rows outer, columns inner, up to kFly independent 16 / 32-byte loads in flight per lane before the first one is
+    // consumed.  ncu (profiles/r02_roi_align_per_bin_b8.txt): the kernel is ISSUE-bound (2.9 of 4 instructions per cycle
+    // and SM, L2 at 25 %), so the loop is written for few instructions per cell: the row weight and row pointer are
+    // computed once per row, one shuffle + one multiply + one compare per cell, FMA accumulate.  Same products, same
     // accumulation order as a plain row / column loop that skips zero weights.
     constexpr int kFly = sizeof(T) == 2 ? 6 : 3;
     const int ncols = chi - clo + 1;
-    const int ncell = (rhi - rlo + 1) * ncols;
-    const T* base = feat + (static_cast<size_t>(rlo) * lv.W + clo) * lv.ld + lane * 8;
+    const int nrows = rhi - rlo + 1;
+    const T* rowp = feat + (static_cast<size_t>(rlo) * lv.W + clo) * lv.ld + lane * 8;
     const size_t row_stride = static_cast<size_t>(lv.W) * lv.ld;
-    int rr = 0, cc = 0;
-    for (int c0 = 0; c0 < ncell; c0 += kFly) {
-      float w[kFly];
-      Raw8<T> v[kFly];
+    for (int rr = 0; rr < nrows; ++rr, rowp += row_stride) {
+      const float wy = __shfl_sync(0xffffffffu, WY, rr);
+      if (wy == 0.f) continue;
+      for (int c0 = 0; c0 < ncols; c0 += kFly) {
+        float w[kFly];
+        Raw8<T> v[kFly];
 #pragma unroll
-      for (int u = 0; u < kFly; ++u) {
-        const float wy = __shfl_sync(0xffffffffu, WY, rr & 31);
-        const float wx = __shfl_sync(0xffffffffu, WX, cc & 31);
-        w[u] = (c0 + u < ncell) ? wy * wx : 0.f;
-        if (w[u] != 0.f) v[u].load(base + static_cast<size_t>(rr) * row_stride + static_cast<size_t>(cc) * lv.ld);
-        if (++cc == ncols) cc = 0, ++rr;
-      }
+        for (int u = 0; u < kFly; ++u) {
+          const int cc = c0 + u;
+          const float wx = __shfl_sync(0xffffffffu, WX, cc & 31);
+          w[u] = (cc < ncols) ? wy * wx : 0.f;
+          if (w[u] != 0.f) v[u].load(rowp + static_cast<size_t>(cc) * lv.ld);
+        }
 #pragma unroll
-      for (int u = 0; u < kFly; ++u) {
-        if (w[u] != 0.f) {
-          float val[8];
-          v[u].unpack(val);
+        for (int u = 0; u < kFly; ++u) {
+          if (w[u] != 0.f) {
+            float val[8];
+            v[u].unpack(val);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w[u], val[j], acc[j]);   // same fused form as the staged kernel: bit-identical
+            for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w[u], val[j], acc[j]);   // one rounding per term (-fmad=false file)
+          }
         }
       }
     }
@@ -1177,28 +1022,13 @@ void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr, DType 
                    int nrois, int S, const Tensor& out) {
   PN_REQUIRE(out.C == 256 && out.dt == dt && S <= 14, "roi_align: 256-channel pyramid, at most 14 x 14 bins expected");
   Tensor o = out;
-  // staged kernel first (every ROI whose footprint fits 64 KB of shared memory: all but extreme aspect ratios), then the
-  // per-bin kernel for the rest (it returns at once for the ROIs already done)
-  const size_t stage_bytes = static_cast<size_t>(kRoiStageCells) * 64;
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_roi_align_staged<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_roi_align_staged<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
-  const char* pb = std::getenv("PN_DEBUG_ROI_PER_BIN");   // test / diagnosis: the per-bin kernel alone (read at build time)
-  const bool staged = !(pb && pb[0] && pb[0] != '0');
   net.add(name, [=](cudaStream_t s) {
-    if (!staged) {
-      if (dt == kBF16) launch_pdl(k_roi_align<__nv_bfloat16>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld, 0);
-      else launch_pdl(k_roi_align<float>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld, 0);
-      return;
-    }
-    if (dt == kBF16) {
-      launch_pdl(k_roi_align_staged<__nv_bfloat16>, dim3(nrois), 256, stage_bytes, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
-      launch_pdl(k_roi_align<__nv_bfloat16>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld, 1);
-    } else {
-      launch_pdl(k_roi_align_staged<float>, dim3(nrois), 256, stage_bytes, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
-      launch_pdl(k_roi_align<float>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld, 1);
-    }
+    if (dt == kBF16)
+      launch_pdl(k_roi_align<__nv_bfloat16>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
+    else
+      launch_pdl(k_roi_align<float>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
   });
-  net.launches_per_forward += 2;
+  net.launches_per_forward += 1;
 }
 
 void add_detections(Net& net, MaskRcnn& m) {

@@ -361,7 +361,7 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* keys, int n, uint
 }
 
 template <int kF>  // register budget for the per-voxel features: 12 (the reference's 10 categories + count) or kF
-__global__ void __launch_bounds__(128, kF <= 12 ? 8 : 4) k_columns(SemMapCfg c, int large, const float* __restrict__ obs,
+__global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, const float* __restrict__ obs,
                                                  const float* __restrict__ coords, const int* __restrict__ col_start,
                                                  const uint32_t* __restrict__ entries, const int* __restrict__ col_list,
                                                  const int* __restrict__ list_n, float* __restrict__ ego) {
@@ -705,7 +705,7 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
   launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
   // non-empty columns only, persistent CTAs: 8 KB of key storage each for the small ones, 128 KB for the rare
   // columns that collect more than kSmallCap entries (a wall seen edge-on)
-  const int g_small = std::min(ncols, num_sms * (c.nf <= 12 ? 16 : 8)), g_large = std::min(ncols, num_sms);
+  const int g_small = std::min(ncols, num_sms * 8), g_large = std::min(ncols, num_sms);
   if (c.nf <= 12) {
     launch_pdl(k_columns<12>, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
     launch_pdl(k_columns<12>, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);

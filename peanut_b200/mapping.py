@@ -41,10 +41,11 @@ class Semantic_Mapping(nn.Module):
             raise TypeError(f"{name}: expected float32 CUDA tensor of shape {tuple(shape)}, got "
                             f"{getattr(t, 'dtype', None)} {tuple(getattr(t, 'shape', ()))}")
 
-    def forward_batch(self, obs, pose_obs, maps_last, poses_last):
+    def forward_batch(self, obs, pose_obs, maps_last, poses_last, out=None, fp_out=None):
         """E environments at once: obs [E,C,h,w], pose_obs [E,3], maps_last [E,C,n,n] (any strides with unit
         x stride), poses_last [E,3] contiguous (updated in place).  Returns (fp_map_pred [E,vr,vr],
-        map_pred [E,C,n,n], poses_last)."""
+        map_pred [E,C,n,n], poses_last).  ``out`` / ``fp_out``: optional preallocated contiguous result tensors (no
+        allocation on the calling stream then); ``out`` must not alias ``maps_last``."""
         E = self.num_envs
         self._check(obs, (E, self.channels, self.h, self.w), "obs")
         self._check(pose_obs, (E, 3), "pose_obs")
@@ -57,8 +58,13 @@ class Semantic_Mapping(nn.Module):
         if maps_last.stride(3) != 1:
             maps_last = maps_last.contiguous()
         strides = (ctypes.c_int64 * 3)(maps_last.stride(0), maps_last.stride(1), maps_last.stride(2))
-        fp = torch.empty((E, self.vr, self.vr), dtype=torch.float32, device=obs.device)
-        out = torch.empty((E, self.channels, self.cells, self.cells), dtype=torch.float32, device=obs.device)
+        fp = fp_out if fp_out is not None else torch.empty((E, self.vr, self.vr), dtype=torch.float32, device=obs.device)
+        if out is None:
+            out = torch.empty((E, self.channels, self.cells, self.cells), dtype=torch.float32, device=obs.device)
+        self._check(fp, (E, self.vr, self.vr), "fp_out")
+        self._check(out, (E, self.channels, self.cells, self.cells), "out")
+        if not (fp.is_contiguous() and out.is_contiguous()):
+            raise ValueError("out / fp_out must be contiguous")
         stream = torch.cuda.current_stream(obs.device).cuda_stream
         _lib.check(self.ctx.lib.pn_semmap_forward(self.ctx.handle, obs.data_ptr(), pose_obs.data_ptr(),
                                                   maps_last.data_ptr(), strides, poses_last.data_ptr(), fp.data_ptr(),

@@ -105,17 +105,19 @@ class PerceptionPipeline:
                                     precision=self._precision)
         return self._pred1
 
-    def _glue_mapper_window(self, rgb, depth, pose_delta, local_map, poses, partial_map):
+    def _glue_mapper_window(self, rgb, depth, pose_delta, local_map, poses, partial_map, map_out=None, fp_out=None):
         """Everything between stage A and stage C of the dependent chain, on the current stream: `_preprocess_obs` glue,
         the mapper, and update_prediction's stamp + prediction window (agent_state.py:350-360)."""
         a = self.args
         main = torch.cuda.current_stream(self.device)
+        if self._depth_ready is not None:  # step_host copies depth / pose delta beside Mask-RCNN
+            main.wait_event(self._depth_ready)
         stream = ctypes.c_void_p(main.cuda_stream)
         lib, h = self.seg.ctx.lib, self.seg.ctx.handle
         _lib.check(lib.pn_make_obs(h, depth.data_ptr(), rgb.data_ptr(), self.sem.data_ptr(), self.E, a.env_frame_height,
                                    a.env_frame_width, a.frame_height, a.frame_width, a.num_sem_categories, a.min_depth,
                                    a.max_depth, self.obs.data_ptr(), stream))
-        fp, new_map, poses = self.mapper.forward_batch(self.obs, pose_delta, local_map, poses)
+        fp, new_map, poses = self.mapper.forward_batch(self.obs, pose_delta, local_map, poses, out=map_out, fp_out=fp_out)
         Cm, Hm, Wm = self.map_shape
         _lib.check(lib.pn_map_stamp_local(h, new_map.data_ptr(), self.full_map.data_ptr(), self.lmb.data_ptr(), self.E, self.nc,
                                           self.local_w, self.local_h, self.full_w, self.full_h, stream))
@@ -132,8 +134,6 @@ class PerceptionPipeline:
         a = self.args
         main = torch.cuda.current_stream(self.device)
         self.seg.forward_device(rgb, goal_cat, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=self.sem)
-        if self._depth_ready is not None:
-            main.wait_event(self._depth_ready)
         fp, new_map, poses = self._glue_mapper_window(rgb, depth, pose_delta, local_map, poses, partial_map)
         pred = self.pred.forward_device(partial_map, apply_sigmoid=True, out=self.pred_out)
         return self.sem, fp, new_map, poses, pred
@@ -231,6 +231,114 @@ class PerceptionPipeline:
             self._host_out[1].copy_(poses, non_blocking=True)
             self._host_out[2].copy_(fp, non_blocking=True)
             main.wait_event(self._join_d2h)
+        main.synchronize()
+        return self._host_out[0], self._host_out[1], self._host_out[2], new_map
+
+    def h2d_bytes(self, rgb_h, depth_h, pose_delta_h, partial_map_h):
+        return sum(t.numel() * t.element_size() for t in (rgb_h, depth_h, pose_delta_h, partial_map_h))
+
+    def d2h_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self._host_out) if self._host_out else 0
+
+
+class MicroBatchedPipeline:
+    """The dependent chain pipelined over micro-batches of environments on one GPU.
+
+    Each environment's chain stays the reference's (Mask-RCNN -> glue -> mapper -> stamp + window -> map completion), but the
+    E environments are split into ``micro_batches`` groups with their own engines: while the caller's stream runs Mask-RCNN of
+    group i + 1, a side stream runs everything after Mask-RCNN of group i.  Mask-RCNN's persistent tensor-core kernels leave
+    registers and warp slots idle that the latency-bound mapper kernels (low occupancy, little shared memory) can use, so
+    that work leaves the critical path.  Results are written into slices of shared [E, ...] tensors (no concatenation, no
+    allocation inside the step); the local map is double-buffered because the mapper's output must not alias its input.
+    Same public surface as ``PerceptionPipeline`` (``step_device`` / ``step_host`` / byte and launch counts)."""
+
+    def __init__(self, seg_weights, pred_weights, num_envs=2, micro_batches=2, device="cuda:0", precision="bf16",
+                 map_shape=(24, 240, 240), num_pred_classes=6, args=None):
+        if micro_batches < 2 or num_envs % micro_batches != 0:
+            raise ValueError("num_envs must be a multiple of micro_batches >= 2")
+        self.E, self.mb, self.Es = int(num_envs), int(micro_batches), int(num_envs) // int(micro_batches)
+        self.mode = "dependent"
+        self.subs = [PerceptionPipeline(seg_weights, pred_weights, self.Es, device, precision, map_shape, num_pred_classes,
+                                        args=None if args is None else types.SimpleNamespace(**vars(args)), mode="dependent")
+                     for _ in range(self.mb)]
+        p0 = self.subs[0]
+        self.device, self.args, self.map_shape = p0.device, p0.args, p0.map_shape
+        d = self.device
+        self.seg, self.pred = p0.seg, p0.pred       # (for callers that only need the shapes / one engine's profile)
+        self.pred_out = torch.zeros((self.E,) + tuple(p0.pred_out.shape[1:]), dtype=torch.float32, device=d)
+        self.fp_out = torch.zeros((self.E, p0.args.vision_range, p0.args.vision_range), dtype=torch.float32, device=d)
+        shape = (self.E, p0.nc, p0.local_w, p0.local_h)
+        self._maps = [torch.zeros(shape, dtype=torch.float32, device=d) for _ in range(2)]
+        for i, s in enumerate(self.subs):
+            s.pred_out = self.pred_out[i * self.Es:(i + 1) * self.Es]
+        self._side = [torch.cuda.Stream(device=d) for _ in range(self.mb - 1)]
+        self._a_done = [torch.cuda.Event() for _ in range(self.mb)]
+        self._rest_done = [torch.cuda.Event() for _ in range(self.mb - 1)]
+        self._copy = torch.cuda.Stream(device=d)
+        self._fence, self._depth_ev, self._pmap_ev = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self._dev_in = None
+        self._host_out = None
+
+    def launches_per_step(self):
+        return sum(s.launches_per_step() for s in self.subs)
+
+    def step_device(self, rgb, depth, pose_delta, local_map, poses, partial_map, goal_cat=None, _events=(None, None)):
+        """Same contract as PerceptionPipeline.step_device (dependent mode); ``sem`` is returned as a list of the groups'
+        [Es,H,W,S] tensors, everything else as [E, ...] tensors."""
+        a = self.args
+        main = torch.cuda.current_stream(self.device)
+        out_map = self._maps[0] if local_map.data_ptr() != self._maps[0].data_ptr() else self._maps[1]
+        sems = []
+        for i, sub in enumerate(self.subs):
+            sl = slice(i * self.Es, (i + 1) * self.Es)
+            g = None if goal_cat is None else goal_cat[sl]
+            sub.seg.forward_device(rgb[sl], g, a.sem_pred_prob_thr, a.sem_pred_prob_thr, a.goal_thr, out=sub.sem)
+            sems.append(sub.sem)
+            last = i == self.mb - 1
+            stream = main if last else self._side[i]
+            if not last:
+                self._a_done[i].record(main)
+                stream.wait_event(self._a_done[i])
+            with torch.cuda.stream(stream):
+                sub._depth_ready, sub._pmap_ready = _events
+                try:
+                    sub._glue_mapper_window(rgb[sl], depth[sl], pose_delta[sl], local_map[sl], poses[sl], partial_map[sl],
+                                            map_out=out_map[sl], fp_out=self.fp_out[sl])
+                finally:
+                    sub._depth_ready, sub._pmap_ready = None, None
+                sub.pred.forward_device(partial_map[sl], apply_sigmoid=True, out=sub.pred_out)
+                if not last:
+                    self._rest_done[i].record(stream)
+        for ev in self._rest_done:
+            main.wait_event(ev)
+        return sems, self.fp_out, out_map, poses, self.pred_out
+
+    def step_host(self, rgb_h, depth_h, pose_delta_h, partial_map_h, local_map, poses):
+        """End-to-end step with pinned HOST inputs / outputs, like PerceptionPipeline.step_host: only the frames gate
+        Mask-RCNN, the other inputs are copied on a copy stream beside it."""
+        d = self.device
+        if self._dev_in is None:
+            self._dev_in = (torch.empty_like(rgb_h, device=d), torch.empty_like(depth_h, device=d),
+                            torch.empty_like(pose_delta_h, device=d), torch.empty_like(partial_map_h, device=d))
+            self._host_out = (torch.empty(self.pred_out.shape, dtype=torch.float32).pin_memory(),
+                              torch.empty((self.E, 3), dtype=torch.float32).pin_memory(),
+                              torch.empty(self.fp_out.shape, dtype=torch.float32).pin_memory())
+        main = torch.cuda.current_stream(d)
+        self._dev_in[0].copy_(rgb_h, non_blocking=True)
+        self._fence.record(main)
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(self._fence)
+            self._dev_in[1].copy_(depth_h, non_blocking=True)
+            self._dev_in[2].copy_(pose_delta_h, non_blocking=True)
+            self._depth_ev.record(self._copy)
+            self._dev_in[3].copy_(partial_map_h, non_blocking=True)
+            self._pmap_ev.record(self._copy)
+        rgb, depth, delta, pmap = self._dev_in
+        _, fp, new_map, poses, pred = self.step_device(rgb, depth, delta, local_map, poses, pmap,
+                                                       _events=(self._depth_ev, self._pmap_ev))
+        self._host_out[1].copy_(poses, non_blocking=True)
+        self._host_out[2].copy_(fp, non_blocking=True)
+        self._host_out[0].copy_(pred, non_blocking=True)
         main.synchronize()
         return self._host_out[0], self._host_out[1], self._host_out[2], new_map
 

@@ -142,30 +142,6 @@ def test_roi_align_and_box_head(eng_tf32, otaps, weights):
     assert (out[:, 10:46] - dlt_ref).abs().max().item() <= 5e-3 * dlt_ref.abs().max().item()
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
-def test_staged_roi_align_equals_per_bin_kernel(weights, frame, precision, monkeypatch):
-    """The staged ROIAlign (whole footprint in shared memory, one CTA per ROI) forms the same products in the same order as
-    the per-bin kernel it replaced: box and mask pooling must be bit-identical between the two, ROIs the staged kernel hands
-    back to the per-bin kernel (footprints beyond its capacity) included."""
-    def pooled(per_bin):
-        if per_bin:
-            monkeypatch.setenv("PN_DEBUG_ROI_PER_BIN", "1")
-        else:
-            monkeypatch.delenv("PN_DEBUG_ROI_PER_BIN", raising=False)
-        e = _engine(weights, precision)
-        e.forward_device(torch.from_numpy(frame)[None].cuda(), score_thresh=THR, sem_pred_prob_thr=THR, goal_thr=THR)
-        torch.cuda.synchronize()
-        n = int(e.read_tap("prop_count", (1,), torch.int32).item())
-        nd = int(e.read_tap("det_count", (1,), torch.int32).item())
-        return (e.read_tap("box_pooled", (1000, 256, 7, 7)).cpu()[:n], e.read_tap("mask_pooled", (100, 256, 14, 14)).cpu()[:nd],
-                e.read_tap("prop_boxes", (1000, 4)).cpu()[:n])
-    box_a, mask_a, boxes = pooled(False)
-    box_b, mask_b, boxes_b = pooled(True)
-    assert box_a.shape[0] > 100 and mask_a.shape[0] > 0 and torch.equal(boxes, boxes_b)
-    assert torch.equal(box_a, box_b) and torch.equal(mask_a, mask_b)
-    assert float(box_a.abs().sum()) > 0
-
-
 def _inject_box_head(e, otaps):
     n = otaps["proposals"].shape[0]
     pb = torch.zeros((1000, 4))

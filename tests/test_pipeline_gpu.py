@@ -104,3 +104,60 @@ def test_step_host_equals_step_device(setup):
         pin[k].numel() * pin[k].element_size() for k in ("rgb", "depth", "delta", "pmap"))
     assert pipe.d2h_bytes() == pred_h.numel() * 4 + poses_h.numel() * 4 + fp_h.numel() * 4
     assert pipe.launches_per_step() > 100
+
+
+def test_micro_batched_pipeline_equals_per_group_pipelines():
+    """MicroBatchedPipeline (the dependent chain pipelined over groups of environments: Mask-RCNN of group i + 1 on the
+    caller's stream while a side stream finishes group i) must give, per group, exactly what a PerceptionPipeline of the
+    group's size gives: same engines, same launch lists - bit-identical - for the device and the host entry point, and over
+    two consecutive steps (double-buffered local maps, event reuse)."""
+    from peanut_b200.pipeline import MicroBatchedPipeline
+    E, shape = 4, (14, 96, 96)
+    wa, wc = OA.synth_weights(0), OC.synth_state_dict(shape[0], 6, seed=0)
+    args = OB.default_args()
+    rgb = torch.from_numpy(np.stack([OA.synth_rgb(20 + e) for e in range(E)]))
+    depth = torch.from_numpy(np.stack([OP.synth_depth(20 + e)[:, :, 0] for e in range(E)]))
+    st = [OB.synth_state(20 + e, args) for e in range(E)]
+    delta = torch.from_numpy(np.stack([s[0] for s in st]))
+    maps = torch.from_numpy(np.stack([s[1] for s in st]))
+    poses = torch.from_numpy(np.stack([s[2] for s in st]))
+    pmap = torch.from_numpy(np.stack([OC.synth_partial_map(*shape, seed=60 + e) for e in range(E)]))
+    mbp = MicroBatchedPipeline(wa, wc, num_envs=E, micro_batches=2, device="cuda:0", precision="bf16", map_shape=shape)
+    ref = PerceptionPipeline(wa, wc, num_envs=2, device="cuda:0", precision="bf16", map_shape=shape, mode="dependent")
+    for p in mbp.subs + [ref]:
+        p.args.sem_pred_prob_thr = 0.3
+        p.args.goal_thr = 0.3
+    mbp.args.sem_pred_prob_thr = 0.3
+    mbp.args.goal_thr = 0.3
+    d = dict(rgb=rgb.cuda(), depth=depth.cuda(), delta=delta.cuda(), maps=maps.cuda(), poses=poses.cuda(), pmap=pmap.cuda())
+    # --- two device steps through the micro-batched pipeline
+    pm = d["pmap"].clone()
+    po = d["poses"].clone()
+    _, fp1, map1, _, pred1 = mbp.step_device(d["rgb"], d["depth"], d["delta"], d["maps"], po, pm)
+    torch.cuda.synchronize()
+    fp1, map1c, pred1 = fp1.clone(), map1.clone(), pred1.clone()
+    _, fp2, map2, _, pred2 = mbp.step_device(d["rgb"], d["depth"], d["delta"], map1, po, pm)
+    torch.cuda.synchronize()
+    assert map2.data_ptr() != map1.data_ptr()
+    fp2, map2, pred2, po = fp2.clone(), map2.clone(), pred2.clone(), po.clone()
+    # --- the same, group by group, through a plain pipeline of the group's size
+    for gi in range(2):
+        sl = slice(2 * gi, 2 * gi + 2)
+        ref.full_map.zero_()
+        pmr = d["pmap"][sl].clone()
+        por = d["poses"][sl].clone()
+        _, rfp1, rmap1, _, rpred1 = ref.step_device(d["rgb"][sl], d["depth"][sl], d["delta"][sl], d["maps"][sl], por, pmr)
+        torch.cuda.synchronize()
+        assert torch.equal(rfp1, fp1[sl]) and torch.equal(rmap1, map1c[sl]) and torch.equal(rpred1, pred1[sl])
+        _, rfp2, rmap2, _, rpred2 = ref.step_device(d["rgb"][sl], d["depth"][sl], d["delta"][sl], rmap1, por, pmr)
+        torch.cuda.synchronize()
+        assert torch.equal(rfp2, fp2[sl]) and torch.equal(rmap2, map2[sl]) and torch.equal(rpred2, pred2[sl])
+        assert torch.equal(por, po[sl])
+    assert float(pred1.min()) >= 0.0 and float(pred1.max()) <= 1.0 and float(map1c.sum()) > 0
+    # --- host entry point
+    for p in mbp.subs:
+        p.full_map.zero_()
+    pin = {k: v.pin_memory() for k, v in dict(rgb=rgb, depth=depth, delta=delta, pmap=pmap).items()}
+    pred_h, poses_h, fp_h, map_h = mbp.step_host(pin["rgb"], pin["depth"], pin["delta"], pin["pmap"], d["maps"], d["poses"].clone())
+    assert torch.equal(pred_h, pred1.cpu()) and torch.equal(fp_h, fp1.cpu()) and torch.equal(map_h, map1c)
+    assert mbp.launches_per_step() == 2 * ref.launches_per_step()

@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(1024) k_rpn_merge(int post_topk, const float* 
 
 // ---------------------------------------------------------------------------------------------------
 // ROIAlignV2 (aligned=True, sampling_ratio=0) with detectron2's level assignment.  One CTA per ROI, one warp
-// per output bin (round robin), one lane per 8 channels (256 channels).
+// per output bin COLUMN (it walks the column's S bins), one lane per 8 channels (256 channels).
 // 8 channels of one cell as loaded (conversion deferred until the value is consumed, so that several loads stay in flight)
 template <typename T>
 struct Raw8;
@@ -572,134 +572,83 @@ struct Raw8<float> {
 };
 
 
-// grid = (S bin rows, ROIs); block = S warps: warp pw owns output bin (ph = blockIdx.x, pw); lane = 8 channels.
-// Samples are visited in torchvision's order (iy outer, ix inner) with the loads of two samples in flight.
-template <typename T>
-__global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
-                                                   int S, T* __restrict__ out, long long ldo) {
-  pdl_grid_sync();
-  const int r = blockIdx.y;
-  const int b = img[r];
-  if (b < 0) return;
+// Geometry of one ROI on its pyramid level (torchvision roi_align.cpp with aligned=True, sampling_ratio=0; level rule of
+// detectron2 assign_boxes_to_levels).
+struct RoiGeom {
+  PyramidLevel lv;
+  float rsw, rsh, bin_h, bin_w, count;
+  int gh, gw;
+  __device__ __forceinline__ float sample_y(int ph, int iy) const {
+    return rsh + static_cast<float>(ph) * bin_h + (static_cast<float>(iy) + .5f) * bin_h / static_cast<float>(gh);
+  }
+  __device__ __forceinline__ float sample_x(int pw, int ix) const {
+    return rsw + static_cast<float>(pw) * bin_w + (static_cast<float>(ix) + .5f) * bin_w / static_cast<float>(gw);
+  }
+};
+__device__ __forceinline__ RoiGeom roi_geom(const Pyramid& pyr, const float* __restrict__ boxes, int r, int S) {
+  RoiGeom g;
   const float x1 = boxes[r * 4], y1 = boxes[r * 4 + 1], x2 = boxes[r * 4 + 2], y2 = boxes[r * 4 + 3];
   const float size = sqrtf((x2 - x1) * (y2 - y1));
   float lvf = floorf(4.f + log2f(size / 224.f + 1e-8f));
   lvf = fminf(fmaxf(lvf, 2.f), 5.f);
-  const PyramidLevel lv = pyr.lv[static_cast<int>(lvf) - 2];
+  const int li = static_cast<int>(lvf) - 2;   // selects instead of a dynamic index: the parameter struct stays in the constant bank
+  g.lv = pyr.lv[0];
+  if (li == 1) g.lv = pyr.lv[1];
+  if (li == 2) g.lv = pyr.lv[2];
+  if (li == 3) g.lv = pyr.lv[3];
+  g.rsw = x1 * g.lv.scale - 0.5f, g.rsh = y1 * g.lv.scale - 0.5f;
+  const float rew = x2 * g.lv.scale - 0.5f, reh = y2 * g.lv.scale - 0.5f;
+  const float rw = rew - g.rsw, rh = reh - g.rsh;
+  g.bin_h = rh / static_cast<float>(S), g.bin_w = rw / static_cast<float>(S);
+  g.gh = static_cast<int>(ceilf(rh / static_cast<float>(S)));
+  g.gw = static_cast<int>(ceilf(rw / static_cast<float>(S)));
+  g.count = static_cast<float>(max(g.gh * g.gw, 1));
+  return g;
+}
+
+// One bin, one sample at a time in torchvision's order: for bins wider than 32 feature cells, which detectron2's level
+// assignment never produces (recomputes the geometry so that the hot loop does not carry its registers).
+template <typename T>
+__device__ __forceinline__ void roi_bin_per_sample(const Pyramid& pyr, const float* __restrict__ boxes, int r, int b, int S, int ph, int pw,
+                                                int lane, float (&acc)[8]) {
+  const RoiGeom g = roi_geom(pyr, boxes, r, S);
+  const PyramidLevel& lv = g.lv;
   const T* feat = static_cast<const T*>(lv.ptr) + static_cast<size_t>(b) * lv.H * lv.W * lv.ld;
-  const float rsw = x1 * lv.scale - 0.5f, rsh = y1 * lv.scale - 0.5f;
-  const float rew = x2 * lv.scale - 0.5f, reh = y2 * lv.scale - 0.5f;
-  const float rw = rew - rsw, rh = reh - rsh;
-  const float bin_h = rh / static_cast<float>(S), bin_w = rw / static_cast<float>(S);
-  const int gh = static_cast<int>(ceilf(rh / static_cast<float>(S)));
-  const int gw = static_cast<int>(ceilf(rw / static_cast<float>(S)));
-  const float count = static_cast<float>(max(gh * gw, 1));
-  const int ph = blockIdx.x, pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const int ns = gh * gw;
-  auto sample_y = [&](int iy) { return rsh + static_cast<float>(ph) * bin_h + (static_cast<float>(iy) + .5f) * bin_h / static_cast<float>(gh); };
-  auto sample_x = [&](int ix) { return rsw + static_cast<float>(pw) * bin_w + (static_cast<float>(ix) + .5f) * bin_w / static_cast<float>(gw); };
-  // Bilinear sampling is separable and the bin is a sum over a regular sample grid, so
-  //   bin = sum_rows sum_cols WY[row] * WX[col] * feat[row][col],  WY[row] = sum over the bin's sample rows of their
-  // weight on that feature row (same for WX): every feature cell under the bin is read ONCE instead of once per
-  // (sample, tap).  Lane l accumulates the weight of row rlo + l / column clo + l; bins spanning more than 32 rows or
-  // columns (never with detectron2's level assignment) take the per-sample path.
   const float fh = static_cast<float>(lv.H), fw = static_cast<float>(lv.W);
-  const float yf = fminf(fmaxf(sample_y(0), 0.f), fh), yl_ = fminf(fmaxf(sample_y(gh - 1), 0.f), fh);
-  const float xf = fminf(fmaxf(sample_x(0), 0.f), fw), xl_ = fminf(fmaxf(sample_x(gw - 1), 0.f), fw);
-  const int rlo = min(static_cast<int>(yf), lv.H - 1), rhi = min(static_cast<int>(yl_) + 1, lv.H - 1);
-  const int clo = min(static_cast<int>(xf), lv.W - 1), chi = min(static_cast<int>(xl_) + 1, lv.W - 1);
-  if (ns > 0 && rhi - rlo < 32 && chi - clo < 32) {
-    float WY = 0.f, WX = 0.f;
-    for (int iy = 0; iy < gh; ++iy) {
-      float y = sample_y(iy);
-      if (y < -1.0f || y > fh) continue;
-      if (y <= 0.f) y = 0.f;
-      int yl = static_cast<int>(y), yh;
-      if (yl >= lv.H - 1) yh = yl = lv.H - 1, y = static_cast<float>(yl);
-      else yh = yl + 1;
-      const float ly = y - static_cast<float>(yl), hy = 1.f - ly;
-      if (rlo + lane == yl) WY += hy;
-      if (rlo + lane == yh) WY += ly;
-    }
-    for (int ix = 0; ix < gw; ++ix) {
-      float x = sample_x(ix);
-      if (x < -1.0f || x > fw) continue;
-      if (x <= 0.f) x = 0.f;
-      int xl = static_cast<int>(x), xh;
-      if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
-      else xh = xl + 1;
-      const float lx = x - static_cast<float>(xl), hx = 1.f - lx;
-      if (clo + lane == xl) WX += hx;
-      if (clo + lane == xh) WX += lx;
-    }
-    // Rows outer, columns inner, up to kFly independent 16 / 32-byte loads in flight per lane before the first one is
-    // consumed.  ncu (profiles/r02_roi_align_per_bin_b8.txt): the kernel is ISSUE-bound (2.9 of 4 instructions per cycle
-    // and SM, L2 at 25 %), so the loop is written for few instructions per cell: the row weight and row pointer are
-    // computed once per row, one shuffle + one multiply + one compare per cell, FMA accumulate.  Same products, same
-    // accumulation order as a plain row / column loop that skips zero weights.
-    constexpr int kFly = sizeof(T) == 2 ? 6 : 3;
-    const int ncols = chi - clo + 1;
-    const int nrows = rhi - rlo + 1;
-    const T* rowp = feat + (static_cast<size_t>(rlo) * lv.W + clo) * lv.ld + lane * 8;
-    const size_t row_stride = static_cast<size_t>(lv.W) * lv.ld;
-    for (int rr = 0; rr < nrows; ++rr, rowp += row_stride) {
-      const float wy = __shfl_sync(0xffffffffu, WY, rr);
-      if (wy == 0.f) continue;
-      for (int c0 = 0; c0 < ncols; c0 += kFly) {
-        float w[kFly];
-        Raw8<T> v[kFly];
+  const int ns = g.gh * g.gw;
+  for (int s0 = 0; s0 < ns; ++s0) {
+    float y = g.sample_y(ph, s0 / g.gw), x = g.sample_x(pw, s0 % g.gw);
+    if (y < -1.0f || y > fh || x < -1.0f || x > fw) continue;
+    if (y <= 0.f) y = 0.f;
+    if (x <= 0.f) x = 0.f;
+    int yl = static_cast<int>(y), xl = static_cast<int>(x), yh, xh;
+    if (yl >= lv.H - 1) yh = yl = lv.H - 1, y = static_cast<float>(yl);
+    else yh = yl + 1;
+    if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
+    else xh = xl + 1;
+    const float ly = y - static_cast<float>(yl), lx = x - static_cast<float>(xl);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+    // acc += ((w1 v1 + w2 v2) + w3 v3) + w4 v4, tap by tap
+    float t[8], v[8];
+    load8(feat + (static_cast<size_t>(yl) * lv.W + xl) * lv.ld + lane * 8, v);
 #pragma unroll
-        for (int u = 0; u < kFly; ++u) {
-          const int cc = c0 + u;
-          const float wx = __shfl_sync(0xffffffffu, WX, cc & 31);
-          w[u] = (cc < ncols) ? wy * wx : 0.f;
-          if (w[u] != 0.f) v[u].load(rowp + static_cast<size_t>(cc) * lv.ld);
-        }
+    for (int j = 0; j < 8; ++j) t[j] = w1 * v[j];
+    load8(feat + (static_cast<size_t>(yl) * lv.W + xh) * lv.ld + lane * 8, v);
 #pragma unroll
-        for (int u = 0; u < kFly; ++u) {
-          if (w[u] != 0.f) {
-            float val[8];
-            v[u].unpack(val);
+    for (int j = 0; j < 8; ++j) t[j] = t[j] + w2 * v[j];
+    load8(feat + (static_cast<size_t>(yh) * lv.W + xl) * lv.ld + lane * 8, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w[u], val[j], acc[j]);   // one rounding per term (-fmad=false file)
-          }
-        }
-      }
-    }
-  } else {
-    // bins wider than 32 feature cells (never with detectron2's level assignment): one sample at a time, torchvision's order
-    for (int s0 = 0; s0 < ns; ++s0) {
-      float y = sample_y(s0 / gw), x = sample_x(s0 % gw);
-      if (y < -1.0f || y > fh || x < -1.0f || x > fw) continue;
-      if (y <= 0.f) y = 0.f;
-      if (x <= 0.f) x = 0.f;
-      int yl = static_cast<int>(y), xl = static_cast<int>(x), yh, xh;
-      if (yl >= lv.H - 1) yh = yl = lv.H - 1, y = static_cast<float>(yl);
-      else yh = yl + 1;
-      if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
-      else xh = xl + 1;
-      const float ly = y - static_cast<float>(yl), lx = x - static_cast<float>(xl);
-      const float hy = 1.f - ly, hx = 1.f - lx;
-      const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-      // acc += ((w1 v1 + w2 v2) + w3 v3) + w4 v4, tap by tap (few live registers: this path is never the hot one)
-      float t[8], v[8];
-      load8(feat + (static_cast<size_t>(yl) * lv.W + xl) * lv.ld + lane * 8, v);
+    for (int j = 0; j < 8; ++j) t[j] = t[j] + w3 * v[j];
+    load8(feat + (static_cast<size_t>(yh) * lv.W + xh) * lv.ld + lane * 8, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = w1 * v[j];
-      load8(feat + (static_cast<size_t>(yl) * lv.W + xh) * lv.ld + lane * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = t[j] + w2 * v[j];
-      load8(feat + (static_cast<size_t>(yh) * lv.W + xl) * lv.ld + lane * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = t[j] + w3 * v[j];
-      load8(feat + (static_cast<size_t>(yh) * lv.W + xh) * lv.ld + lane * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (t[j] + w4 * v[j]);
-    }
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] + (t[j] + w4 * v[j]);
   }
+}
+
+// acc / count -> (tf32 rounding for fp32 storage) -> store, 8 channels.
+template <typename T>
+__device__ __forceinline__ void roi_bin_store(float (&acc)[8], float count, T* dst) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     acc[j] = acc[j] / count;
@@ -709,7 +658,202 @@ __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* 
       acc[j] = __uint_as_float(q);
     }
   }
-  store8(out + (static_cast<size_t>(r) * S * S + ph * S + pw) * ldo + lane * 8, acc);
+  store8(dst, acc);
+}
+
+// The S bins of one bin column whose footprint is kNC feature columns wide (kNC known at compile time: the column weights
+// sit in registers, the loads of a row - of two rows for narrow bf16 footprints - are issued back to back without
+// predicates, and a cell costs one load, one multiply, the unpack and eight FMAs).  ncu on the predicated six-slot loop
+// it replaces (profiles/r02_roi_align_per_roi_b8.txt): 230 instructions per row for 3.5 live cells, the kernel issue-bound
+// at 2.9 of 4 instructions per cycle.  Zero weights are not skipped: fma(0, v, acc) == acc, so the sums are the same.
+template <typename T, int kNC>
+__device__ __forceinline__ void roi_bins_fixed(const float (*s_wy)[32], const int* s_rlo, const int* s_nrows, float WX, const T* colp,
+                                               size_t row_stride, size_t ld, int S, float count, T* outp, long long ldo) {
+  constexpr int kRows = (sizeof(T) == 2 && kNC <= 4) ? 2 : 1;
+  float wx[kNC];
+#pragma unroll
+  for (int u = 0; u < kNC; ++u) wx[u] = __shfl_sync(0xffffffffu, WX, u);
+  for (int ph = 0; ph < S; ++ph) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int nrows = s_nrows[ph];
+    const T* rowp = colp + static_cast<size_t>(s_rlo[ph]) * row_stride;
+    const float* wyp = s_wy[ph];
+    int rr = 0;
+    for (; rr + kRows <= nrows; rr += kRows, rowp += kRows * row_stride) {
+      Raw8<T> v[kRows][kNC];
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+#pragma unroll
+        for (int u = 0; u < kNC; ++u) v[q][u].load(rowp + q * row_stride + u * ld);
+      }
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+        const float wy = wyp[rr + q];
+#pragma unroll
+        for (int u = 0; u < kNC; ++u) {
+          const float w = wy * wx[u];
+          float val[8];
+          v[q][u].unpack(val);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w, val[j], acc[j]);   // one rounding per term (-fmad=false file)
+        }
+      }
+    }
+    if (kRows == 2 && rr < nrows) {   // odd row count: the last row alone
+      Raw8<T> v[kNC];
+#pragma unroll
+      for (int u = 0; u < kNC; ++u) v[u].load(rowp + u * ld);
+      const float wy = wyp[rr];
+#pragma unroll
+      for (int u = 0; u < kNC; ++u) {
+        const float w = wy * wx[u];
+        float val[8];
+        v[u].unpack(val);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w, val[j], acc[j]);
+      }
+    }
+    roi_bin_store<T>(acc, count, outp + static_cast<size_t>(ph) * S * ldo);
+  }
+}
+
+// grid = ROIs; block = S warps.  Warp w first builds the ROW table of bin row w (which feature rows the bin row's samples
+// touch and with what summed weight - shared by the S bins of that row) in shared memory and the COLUMN table of bin column
+// w in its registers, then walks the S bins of column w.  The coordinate arithmetic (level choice, divisions, the sample
+// loops) is therefore done once per bin row / column and ROI instead of once per bin.
+//
+// Bilinear sampling is separable and the bin is a sum over a regular sample grid, so
+//   bin = sum_rows sum_cols WY[row] * WX[col] * feat[row][col],  WY[row] = sum over the bin's sample rows of their
+// weight on that feature row (same for WX): every feature cell under the bin is read ONCE instead of once per
+// (sample, tap).  Lane l accumulates the weight of row rlo + l / column clo + l; bins spanning more than 32 rows or
+// columns take the per-sample path.  Accumulation order: rows outer, columns inner, one FMA per term.
+template <typename T>
+__global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* __restrict__ boxes, const int* __restrict__ img,
+                                                   int S, T* __restrict__ out, long long ldo) {
+  pdl_grid_sync();
+  const int r = blockIdx.x;
+  const int b = img[r];
+  if (b < 0) return;
+  __shared__ float s_wy[14][32];   // [bin row][feature row - rlo]
+  __shared__ int s_rlo[14], s_nrows[14];
+  __shared__ int s_rows_bad;       // some bin row spans more than 32 feature rows (or the ROI has no samples)
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_rows_bad = 0;
+  __syncthreads();
+  int ncols;
+  bool cols_ok;
+  float WX = 0.f, count;
+  size_t row_stride, ld;
+  const T* colp;
+  {
+    const RoiGeom g = roi_geom(pyr, boxes, r, S);
+    const PyramidLevel& lv = g.lv;
+    const int ns = g.gh * g.gw;
+    const float fh = static_cast<float>(lv.H), fw = static_cast<float>(lv.W);
+    {  // row table of bin row `wid`
+      const int ph = wid;
+      const float yf = fminf(fmaxf(g.sample_y(ph, 0), 0.f), fh), yl_ = fminf(fmaxf(g.sample_y(ph, g.gh - 1), 0.f), fh);
+      const int rlo = min(static_cast<int>(yf), lv.H - 1), rhi = min(static_cast<int>(yl_) + 1, lv.H - 1);
+      const bool rows_ok = ns > 0 && rhi - rlo < 32;
+      float WY = 0.f;
+      if (rows_ok) {
+        for (int iy = 0; iy < g.gh; ++iy) {
+          float y = g.sample_y(ph, iy);
+          if (y < -1.0f || y > fh) continue;
+          if (y <= 0.f) y = 0.f;
+          int yl = static_cast<int>(y), yh;
+          if (yl >= lv.H - 1) yh = yl = lv.H - 1, y = static_cast<float>(yl);
+          else yh = yl + 1;
+          const float ly = y - static_cast<float>(yl), hy = 1.f - ly;
+          if (rlo + lane == yl) WY += hy;
+          if (rlo + lane == yh) WY += ly;
+        }
+      }
+      s_wy[ph][lane] = WY;
+      if (lane == 0) {
+        s_rlo[ph] = rlo, s_nrows[ph] = rows_ok ? rhi - rlo + 1 : -1;
+        if (!rows_ok) s_rows_bad = 1;
+      }
+    }
+    // column table of bin column `wid`
+    const int pw = wid;
+    const float xf = fminf(fmaxf(g.sample_x(pw, 0), 0.f), fw), xl_ = fminf(fmaxf(g.sample_x(pw, g.gw - 1), 0.f), fw);
+    const int clo = min(static_cast<int>(xf), lv.W - 1), chi = min(static_cast<int>(xl_) + 1, lv.W - 1);
+    cols_ok = ns > 0 && chi - clo < 32;
+    if (cols_ok) {
+      for (int ix = 0; ix < g.gw; ++ix) {
+        float x = g.sample_x(pw, ix);
+        if (x < -1.0f || x > fw) continue;
+        if (x <= 0.f) x = 0.f;
+        int xl = static_cast<int>(x), xh;
+        if (xl >= lv.W - 1) xh = xl = lv.W - 1, x = static_cast<float>(xl);
+        else xh = xl + 1;
+        const float lx = x - static_cast<float>(xl), hx = 1.f - lx;
+        if (clo + lane == xl) WX += hx;
+        if (clo + lane == xh) WX += lx;
+      }
+    }
+    ncols = chi - clo + 1;
+    ld = static_cast<size_t>(lv.ld);
+    row_stride = static_cast<size_t>(lv.W) * ld;
+    colp = static_cast<const T*>(lv.ptr) + static_cast<size_t>(b) * lv.H * row_stride + static_cast<size_t>(clo) * ld + lane * 8;
+    count = g.count;
+  }
+  __syncthreads();
+  const int pw = wid;
+  T* outp = out + (static_cast<size_t>(r) * S * S + pw) * ldo + lane * 8;
+  if (cols_ok && s_rows_bad == 0 && ncols <= 8) {
+    switch (ncols) {
+      case 1: roi_bins_fixed<T, 1>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 2: roi_bins_fixed<T, 2>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 3: roi_bins_fixed<T, 3>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 4: roi_bins_fixed<T, 4>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 5: roi_bins_fixed<T, 5>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 6: roi_bins_fixed<T, 6>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 7: roi_bins_fixed<T, 7>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      default: roi_bins_fixed<T, 8>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+    }
+    return;
+  }
+  for (int ph = 0; ph < S; ++ph) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int nrows = s_nrows[ph];
+    if (nrows > 0 && cols_ok) {
+      // wide footprints (more than 8 feature columns per bin): predicated batches of kFly cells
+      constexpr int kFly = sizeof(T) == 2 ? 6 : 3;
+      const T* rowp = colp + static_cast<size_t>(s_rlo[ph]) * row_stride;
+      for (int rr = 0; rr < nrows; ++rr, rowp += row_stride) {
+        const float wy = s_wy[ph][rr];
+        for (int c0 = 0; c0 < ncols; c0 += kFly) {
+          float w[kFly];
+          Raw8<T> v[kFly];
+#pragma unroll
+          for (int u = 0; u < kFly; ++u) {
+            const int cc = c0 + u;
+            const float wx = __shfl_sync(0xffffffffu, WX, cc & 31);
+            w[u] = (cc < ncols) ? wy * wx : 0.f;
+            if (cc < ncols) v[u].load(rowp + static_cast<size_t>(cc) * ld);
+          }
+#pragma unroll
+          for (int u = 0; u < kFly; ++u) {
+            if (c0 + u < ncols) {
+              float val[8];
+              v[u].unpack(val);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w[u], val[j], acc[j]);
+            }
+          }
+        }
+      }
+    } else {
+      roi_bin_per_sample<T>(pyr, boxes, r, b, S, ph, pw, lane, acc);
+    }
+    roi_bin_store<T>(acc, count, outp + static_cast<size_t>(ph) * S * ldo);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1024,9 +1168,9 @@ void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr, DType 
   Tensor o = out;
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
-      launch_pdl(k_roi_align<__nv_bfloat16>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
+      launch_pdl(k_roi_align<__nv_bfloat16>, dim3(nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);
     else
-      launch_pdl(k_roi_align<float>, dim3(S, nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
+      launch_pdl(k_roi_align<float>, dim3(nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<float*>(o.ptr), o.ld);
   });
   net.launches_per_forward += 1;
 }

@@ -69,7 +69,7 @@ __device__ __forceinline__ void corner(float coord, float G, int ix, int& p, flo
 
 // --------------------------------------------------------------------------------------------------
 // k_coords: one thread per depth pixel - splat coordinates + the two counts the stair-mask test needs
-// (qcount[e] = {#valid heights, #heights in the stair band}).  grid = (ceil(N / 256), E).
+// (qcount[e] = {#valid heights, #heights in the stair band, #heights <= 0.2, -}).  grid = (ceil(N / 256), E).
 __global__ void __launch_bounds__(256) k_coords(SemMapCfg c, const float* __restrict__ obs, float* __restrict__ coords,
                                                 uint32_t* __restrict__ qcount) {
   pdl_grid_sync();
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_coords(SemMapCfg c, const float* __rest
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float* depth = obs + (static_cast<size_t>(e) * c.channels + 3) * N;
   float* cx = coords + static_cast<size_t>(e) * 3 * N;
-  uint32_t valid = 0, mid = 0;
+  uint32_t valid = 0, mid = 0, low = 0;
   if (i < N) {
     float X, Y, Z;
     point_coords(c, i / c.w, i % c.w, depth[i], X, Y, Z);
@@ -87,12 +87,15 @@ __global__ void __launch_bounds__(256) k_coords(SemMapCfg c, const float* __rest
       const float mz = Z * 2.f + 1.6f;
       valid = 1;
       mid = (mz > 0.2f && mz < 0.7f) ? 1u : 0u;
+      low = (mz <= 0.2f) ? 1u : 0u;
     }
   }
   const uint32_t nv = __popc(__ballot_sync(0xffffffffu, valid != 0)), nm = __popc(__ballot_sync(0xffffffffu, mid != 0));
+  const uint32_t nl = __popc(__ballot_sync(0xffffffffu, low != 0));
   if ((threadIdx.x & 31) == 0 && nv) {
-    atomicAdd(&qcount[e * 2], nv);
-    if (nm) atomicAdd(&qcount[e * 2 + 1], nm);
+    atomicAdd(&qcount[e * 4], nv);
+    if (nm) atomicAdd(&qcount[e * 4 + 1], nm);
+    if (nl) atomicAdd(&qcount[e * 4 + 2], nl);
   }
 }
 
@@ -108,8 +111,9 @@ __global__ void __launch_bounds__(1024) k_quantile(SemMapCfg c, const float* __r
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_k, s_cnt_le, s_next;
   const int tid = threadIdx.x;
-  const uint32_t n = qcount[e * 2];
-  const uint32_t s_mid = qcount[e * 2 + 1];
+  const uint32_t n = qcount[e * 4];
+  const uint32_t s_mid = qcount[e * 4 + 1];
+  const uint32_t n_low = qcount[e * 4 + 2];
 
   // torch.quantile(my_zs, 0.03), linear interpolation: ranks = q*(n-1) in fp32 (mapping.py:94)
   bool flag = false;
@@ -119,6 +123,14 @@ __global__ void __launch_bounds__(1024) k_quantile(SemMapCfg c, const float* __r
     const uint32_t k_lo = static_cast<uint32_t>(rb);
     const uint32_t k_hi = static_cast<uint32_t>(ceilf(rank));
     const float wgt = rank - rb;
+    // Only `quantile > 0.2` is used, and the interpolated quantile lies between the two order statistics k_lo, k_hi (the
+    // lerp's roundings are monotone): with n_low = #heights <= 0.2 it is decided without selecting anything unless the
+    // two statistics straddle 0.2 (n_low == k_lo + 1 == k_hi), and it is irrelevant when the stair-band test fails.
+    const bool band = static_cast<float>(s_mid) > static_cast<float>(0.2 * static_cast<double>(n));
+    if (!band || n_low >= k_hi + 1u || n_low <= k_lo) {
+      if (tid == 0) stair_flag[e] = (band && n_low <= k_lo) ? 1 : 0;
+      return;
+    }
     // radix select of the k_lo-th smallest (0-based) over order-preserving keys, 8 bits per pass
     if (tid == 0) s_prefix = 0, s_k = k_lo;
     __syncthreads();
@@ -243,63 +255,106 @@ __global__ void __launch_bounds__(256) k_hist(SemMapCfg c, const float* __restri
 }
 
 // --------------------------------------------------------------------------------------------------
-// k_scan: exclusive prefix sum of the column counters; also resets the fill cursors.  grid = E, block = 1024.
-// It also compacts the non-empty columns into a work list for k_columns: columns with at most `small_cap` entries
-// from the front of col_list, larger ones from the back (list_n = {#small, #large}); the order inside the list is
-// irrelevant, every column is processed independently.
-__global__ void __launch_bounds__(1024) k_scan(int ncols, int small_cap, const int* __restrict__ col_count,
-                                               int* __restrict__ col_start, int* __restrict__ col_fill,
-                                               int* __restrict__ col_list, int* __restrict__ list_n) {
+// k_scan: exclusive prefix sum of the column counters; also resets the fill cursors.  grid = E, block = 1024: thread t owns a
+// run of consecutive columns (serial sum), one block scan over the 1024 run totals.
+// It also compacts the non-empty columns into four work lists (col_list is [E][2][ncols], list_n is [E][4]):
+//   tiny (at most kTinyCap entries; plane 0 from the front)  -> k_columns_warp, one warp per column;
+//   mid  (at most kMidCap entries; plane 1 from the front)   -> k_columns_cta, one CTA per column, entries staged in shared memory;
+//   large (at most kLargeCap entries; plane 1 from the back) -> k_columns_cta with a 2048-entry stage, one CTA per SM;
+//   big  (everything else; plane 0 from the back)            -> k_columns_big, keys only in shared memory.
+// The order inside a list is irrelevant, every column is processed independently.
+constexpr int kTinyCap = 32, kMidCap = 512, kLargeCap = 2048;
+constexpr int kScanPer = 16;  // columns per thread of k_scan (1024 threads): vision_range up to 128
+__global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict__ col_count, int* __restrict__ col_start,
+                                               int* __restrict__ col_fill, int* __restrict__ col_list, int* __restrict__ list_n) {
   pdl_grid_sync();
   const int e = blockIdx.x;
-  int* list = col_list + static_cast<size_t>(e) * ncols;
-  __shared__ int n_small, n_large;
-  if (threadIdx.x == 0) n_small = 0, n_large = 0;
+  int* list = col_list + static_cast<size_t>(e) * 2 * ncols;
+  __shared__ int warp_sums[32];
+  __shared__ uint32_t cls_sums[2][32];
   const int* cnt = col_count + static_cast<size_t>(e) * ncols;
   int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
   int* fill = col_fill + static_cast<size_t>(e) * ncols;
-  __shared__ int warp_sums[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < ncols; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int v = i < ncols ? cnt[i] : 0;
-    int x = v;
+  const int per = (ncols + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
+  const int c0 = min(static_cast<int>(threadIdx.x) * per, ncols), c1 = min(c0 + per, ncols);
+  int v[kScanPer];   // this thread's counters, all loads in flight together
+#pragma unroll
+  for (int j = 0; j < kScanPer; ++j) v[j] = (c0 + j < c1) ? cnt[c0 + j] : 0;
+  int run = 0;
+#pragma unroll
+  for (int j = 0; j < kScanPer; ++j) run += v[j];
+  int x = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int sw = warp_sums[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      const int y = __shfl_up_sync(0xffffffffu, sw, o);
+      if (lane >= o) sw += y;
     }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      int s = warp_sums[lane];
+    warp_sums[lane] = sw;
+  }
+  __syncthreads();
+  int excl = (wid ? warp_sums[wid - 1] : 0) + x - run;
+  // list positions by two more block scans over packed per-thread class counts (16 bits each: at most 16 384 columns);
+  // thousands of shared-memory atomics on four counters would serialise (15 us per map in round 2's first version)
+  uint32_t ca = 0, cb = 0;   // ca = tiny | mid << 16, cb = large | big << 16
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += y;
-      }
-      warp_sums[lane] = s;
+  for (int j = 0; j < kScanPer; ++j) {
+    if (v[j] > 0) {
+      if (v[j] <= kTinyCap) ca += 1u;
+      else if (v[j] <= kMidCap) ca += 1u << 16;
+      else if (v[j] <= kLargeCap) cb += 1u;
+      else cb += 1u << 16;
     }
-    __syncthreads();
-    const int excl = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
-    if (i < ncols) {
+  }
+  uint32_t xa = ca, xb = cb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+    if (lane >= o) xa += ya, xb += yb;
+  }
+  __syncthreads();   // warp_sums of the first scan have been read
+  if (lane == 31) cls_sums[0][wid] = xa, cls_sums[1][wid] = xb;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t sa = cls_sums[0][lane], sb = cls_sums[1][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ya = __shfl_up_sync(0xffffffffu, sa, o), yb = __shfl_up_sync(0xffffffffu, sb, o);
+      if (lane >= o) sa += ya, sb += yb;
+    }
+    cls_sums[0][lane] = sa, cls_sums[1][lane] = sb;
+  }
+  __syncthreads();
+  const uint32_t ea = (wid ? cls_sums[0][wid - 1] : 0u) + xa - ca, eb = (wid ? cls_sums[1][wid - 1] : 0u) + xb - cb;
+  int p_tiny = static_cast<int>(ea & 0xffffu), p_mid = static_cast<int>(ea >> 16);
+  int p_large = static_cast<int>(eb & 0xffffu), p_big = static_cast<int>(eb >> 16);
+#pragma unroll
+  for (int j = 0; j < kScanPer; ++j) {
+    const int i = c0 + j;
+    if (i < c1) {
       start[i] = excl;
       fill[i] = 0;
-      if (v > 0) {
-        if (v <= small_cap) list[atomicAdd(&n_small, 1)] = i;
-        else list[ncols - 1 - atomicAdd(&n_large, 1)] = i;
+      excl += v[j];
+      if (v[j] > 0) {
+        if (v[j] <= kTinyCap) list[p_tiny++] = i;
+        else if (v[j] <= kMidCap) list[ncols + p_mid++] = i;
+        else if (v[j] <= kLargeCap) list[2 * ncols - 1 - p_large++] = i;
+        else list[ncols - 1 - p_big++] = i;
       }
     }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    start[ncols] = carry;
-    list_n[e * 2] = n_small, list_n[e * 2 + 1] = n_large;
+  if (threadIdx.x == blockDim.x - 1) {
+    start[ncols] = excl;
+    list_n[e * 4] = p_tiny, list_n[e * 4 + 1] = p_big, list_n[e * 4 + 2] = p_mid, list_n[e * 4 + 3] = p_large;
   }
 }
 
@@ -348,8 +403,13 @@ __global__ void k_fill(SemMapCfg c, const float* __restrict__ coords, const int*
 }
 
 // --------------------------------------------------------------------------------------------------
-// k_columns: one CTA (128 threads) per (x,y) column.  `cap` = keys that fit the dynamic smem of this launch;
-// columns with more entries are left to the large-capacity launch (and vice versa).
+// Voxel columns.  Column (px, py) owns the keys that k_fill put into its bucket; voxel (px, py, z) receives, in the
+// reference's order, eight groups of additions - lateral corner ixy = 0..3 (itertools.product order), inside it the z corner
+// iz = 0, 1 - each group's entries in point-index order, fp32 product then fp32 add per entry, and a round-half-even of
+// the running value after every group (depth_utils.py:241-250).  Sorting the keys (ixy, lower z cell + 1, point) makes
+// every group of every voxel a contiguous key range: group (ixy, iz) of voxel z = keys with z-field z - iz + 1.
+// The chain of additions of one (voxel, feature) pair is inherently serial, different pairs are independent: a lane owns
+// one (voxel, feature) pair, kL lanes (16: at most 12 features, 32: at most 24) form a voxel slot.
 __device__ __forceinline__ int lower_bound_key(const uint32_t* keys, int n, uint32_t k) {
   int lo = 0, hi = n;
   while (lo < hi) {
@@ -360,29 +420,317 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* keys, int n, uint
   return lo;
 }
 
-template <int kF>  // register budget for the per-voxel features: 12 (the reference's 10 categories + count) or kF
-__global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, const float* __restrict__ obs,
+// Shared-memory working set of one column whose entries are staged (sorted keys, both weights and the feature vector of
+// every entry, feature 0 = the constant 1 of the count channel).
+template <int kCap, int kFs>
+struct ColumnStage {
+  uint32_t keys[kCap];
+  float w0[kCap], w1[kCap];
+  float feat[kCap * kFs];
+  uint32_t zbits[4];        // z-fields (0 .. nz) that occur in the column's keys
+  int nv;
+  int vcnt[4];              // touched voxels per 32-voxel chunk
+  uint8_t vox[128];         // touched voxels, any order (the height projections are sums of integers: exact, order-free)
+  float red_all[32], red_agent[32];
+};
+
+// Every thread of a warp stages up to kB entries (sorted positions pos[u], keys k[u], inactive slots masked): all
+// coordinate and feature loads of the batch are issued before the first value is used (a loop of dependent L2 round trips
+// otherwise), and the z-fields are merged inside the warp before one lane touches the shared mask (hundreds of
+// shared-memory atomics on the same word would serialise).  Must be called by all 32 lanes.
+template <int kB, bool kOwnWarp, int kCap, int kFs>
+__device__ __forceinline__ void stage_batch(const SemMapCfg& c, ColumnStage<kCap, kFs>& st, const int (&pos)[kB],
+                                            const uint32_t (&k)[kB], const bool (&act)[kB], const float* __restrict__ cxp,
+                                            const float* __restrict__ featp, int N) {
+  float X[kB], Y[kB], Z[kB], fv[kB][kFs];
+#pragma unroll
+  for (int u = 0; u < kB; ++u) {
+    const int i = static_cast<int>(k[u] & 0x7fffu);   // inactive: key 0 -> point 0, a valid address
+    X[u] = cxp[i], Y[u] = cxp[N + i], Z[u] = cxp[2 * N + i];
+#pragma unroll
+    for (int f = 1; f < kFs; ++f) fv[u][f] = (f < c.nf) ? featp[static_cast<size_t>(f - 1) * N + i] : 0.f;
+  }
+  uint32_t zw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int u = 0; u < kB; ++u) {
+    if (act[u]) {
+      // weights of the entry on its two voxels, the reference's products in the reference's order: ((1 * wx) * wy) * wz
+      const int ixy = static_cast<int>(k[u] >> 22);
+      int pp;
+      float wx, wy, wz0, wz1;
+      bool ss;
+      corner(X[u], c.vr_f, ixy >> 1, pp, wx, ss);
+      corner(Y[u], c.vr_f, ixy & 1, pp, wy, ss);
+      corner(Z[u], c.nz_f, 0, pp, wz0, ss);
+      corner(Z[u], c.nz_f, 1, pp, wz1, ss);
+      const float wxy = (1.f * wx) * wy;
+      st.w0[pos[u]] = wxy * wz0, st.w1[pos[u]] = wxy * wz1;
+      float* fr = st.feat + pos[u] * kFs;
+      fr[0] = 1.f;
+#pragma unroll
+      for (int f = 1; f < kFs; ++f) fr[f] = fv[u][f];
+      const uint32_t word = (k[u] >> 20) & 3u, bit = 1u << ((k[u] >> 15) & 31u);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) zw[w] |= (word == static_cast<uint32_t>(w)) ? bit : 0u;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint32_t m = __reduce_or_sync(0xffffffffu, zw[w]);
+    if ((threadIdx.x & 31) == 0) {
+      if constexpr (kOwnWarp) st.zbits[w] = m;          // the warp owns the column: plain store, nothing to clear
+      else if (m != 0u) atomicOr(&st.zbits[w], m);
+    }
+  }
+}
+
+// The replay of one staged column by kWarps warps (tid = thread index inside the group, `sync` = barrier of the group).
+// Leaves the column's twelve (or more) ego-map values in global memory.
+template <int kL, int kWarps, int kCap, int kFs, typename Sync>
+__device__ __forceinline__ void replay_column(const SemMapCfg& c, ColumnStage<kCap, kFs>& st, int n, int tid, Sync sync,
+                                              float* __restrict__ ego_e, int cell, int ncols) {
+  constexpr int kSlotsPerWarp = 32 / kL;
+  const int lane = tid & 31, wid = tid >> 5;
+  // voxel z is touched by keys with z-field z + 1 (iz = 0) or z (iz = 1); voxel 0 is never written (corner(): pf > 0)
+  // (compacted with ballots: chunk w = voxels [32 w, 32 w + 32), nz <= 126)
+  auto touched_at = [&](int z) {
+    return z > 0 && z < c.nz && (((st.zbits[(z + 1) >> 5] >> ((z + 1) & 31)) | (st.zbits[z >> 5] >> (z & 31))) & 1u) != 0u;
+  };
+  if constexpr (kWarps == 1) {
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int z = w * 32 + lane;
+      const bool t = touched_at(z);
+      const uint32_t m = __ballot_sync(0xffffffffu, t);
+      if (t) st.vox[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint8_t>(z);
+      base += __popc(m);
+    }
+    if (lane == 0) st.nv = base;
+  } else {
+    bool t = false;
+    uint32_t m = 0u;
+    if (wid < 4) {
+      t = touched_at(tid);
+      m = __ballot_sync(0xffffffffu, t);
+      if (lane == 0) st.vcnt[wid] = __popc(m);
+    }
+    sync();
+    if (wid < 4) {
+      int base = 0;
+      for (int w = 0; w < wid; ++w) base += st.vcnt[w];
+      if (t) st.vox[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint8_t>(tid);
+      if (tid == 0) st.nv = st.vcnt[0] + st.vcnt[1] + st.vcnt[2] + st.vcnt[3];
+    }
+  }
+  sync();
+  const int nv = st.nv;
+  const int sl = lane / kL, f = lane % kL;
+  const bool feat_lane = f < c.nf;
+  float all_h = 0.f, agent_h = 0.f;
+  for (int base = wid * kSlotsPerWarp; base < nv; base += kWarps * kSlotsPerWarp) {   // warp-uniform trip count
+    const int v = base + sl;
+    const bool valid = v < nv;
+    const int z = valid ? static_cast<int>(st.vox[v]) : 0;
+    // the 16 range boundaries of this voxel's eight groups, one per lane of the slot
+    int bound = 0;
+    if (valid && f < 16) {
+      const int g = f >> 1, ixy = g >> 1, iz = g & 1;
+      const uint32_t kbase = (static_cast<uint32_t>(ixy) << 22) | (static_cast<uint32_t>(z - iz + 1) << 15);
+      bound = lower_bound_key(st.keys, n, kbase + (static_cast<uint32_t>(f & 1) << 15));
+    }
+    int lo[8], hi[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      lo[g] = __shfl_sync(0xffffffffu, bound, sl * kL + 2 * g);
+      hi[g] = __shfl_sync(0xffffffffu, bound, sl * kL + 2 * g + 1);
+    }
+    if (valid && feat_lane) {
+      float acc = 0.f;
+      const float* fcol = st.feat + f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float* wz = (g & 1) ? st.w1 : st.w0;
+        for (int t = lo[g]; t < hi[g]; ++t) acc = acc + fcol[t * kFs] * wz[t];
+        acc = rintf(acc);   // grid_flat = torch.round(grid_flat) after every corner (depth_utils.py:250): half-to-even
+      }
+      // height projections (mapping.py:102-113)
+      all_h += acc;
+      if (z >= c.min_z && z < c.max_z) agent_h += acc;
+    }
+  }
+  if constexpr (kSlotsPerWarp == 2) {
+    all_h += __shfl_xor_sync(0xffffffffu, all_h, 16);
+    agent_h += __shfl_xor_sync(0xffffffffu, agent_h, 16);
+  }
+  if constexpr (kWarps == 1) {
+    if (lane < kL) st.red_all[lane] = all_h, st.red_agent[lane] = agent_h;
+  } else {
+    if (lane < kL && feat_lane && all_h != 0.f) {
+      atomicAdd(&st.red_all[lane], all_h);
+      if (agent_h != 0.f) atomicAdd(&st.red_agent[lane], agent_h);
+    }
+  }
+  sync();
+  if (tid < c.ego_channels) {
+    // ego channel 0 = obstacle, 1 = explored, 2.. = categories (local-map channels 4..)
+    const int ch = tid;
+    const int ff = ch < 2 ? 0 : ch - 1;
+    const float ah = st.red_all[ff], gh = st.red_agent[ff];
+    float v;
+    if (ch == 0) v = gh / c.map_thr;
+    else if (ch == 1) v = ah / c.exp_thr;
+    else {
+      const bool use_all = (ff == c.special_f[0] || ff == c.special_f[1] || ff == c.special_f[2]);
+      v = (use_all ? ah : gh) / c.cat_thr;
+    }
+    ego_e[static_cast<size_t>(ch) * ncols + cell] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
+// k_columns_warp: columns with at most kTinyCap (= 32) entries - nine in ten - one WARP per column, four independent warps
+// per CTA, persistent over the tiny list; no CTA barrier anywhere.  Lane l owns entry l: rank sort (the keys are unique,
+// they embed the point index: the number of smaller keys is the sorted position), weights and features staged once.
+template <int kL, int kFs>
+__global__ void __launch_bounds__(128) k_columns_warp(SemMapCfg c, const float* __restrict__ obs, const float* __restrict__ coords,
+                                                      const int* __restrict__ col_start, const uint32_t* __restrict__ entries,
+                                                      const int* __restrict__ col_list, const int* __restrict__ list_n,
+                                                      float* __restrict__ ego) {
+  pdl_grid_sync();
+  __shared__ ColumnStage<kTinyCap, kFs> stage[4];
+  __shared__ uint32_t raw_all[4][kTinyCap];
+  const int e = blockIdx.y;
+  const int ncols = c.vr * c.vr;
+  const int N = c.h * c.w;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  ColumnStage<kTinyCap, kFs>& st = stage[wid];
+  uint32_t* raw = raw_all[wid];
+  const int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
+  const int* list = col_list + static_cast<size_t>(e) * 2 * ncols;
+  const int n_list = list_n[e * 4];
+  float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
+  const float* cxp = coords + static_cast<size_t>(e) * 3 * N;
+  const float* featp = obs + (static_cast<size_t>(e) * c.channels + 4) * N;
+  auto sync = [] { __syncwarp(); };
+  for (int li = blockIdx.x * 4 + wid; li < n_list; li += gridDim.x * 4) {
+    const int col = list[li];
+    const int s0 = start[col];
+    const int n = start[col + 1] - s0;
+    const int px = col / c.vr, py = col - px * c.vr;
+    const int cell = py * c.vr + px;  // voxels.transpose(2,3): row = y index, column = x index
+    __syncwarp();  // the previous column's stage is no longer read
+    uint32_t k = 0;
+    if (lane < n) k = entries[static_cast<size_t>(e) * 4 * N + s0 + lane], raw[lane] = k;
+    __syncwarp();
+    int rank = 0;
+    if (lane < n) {
+      for (int j = 0; j < n; ++j) rank += raw[j] < k ? 1 : 0;
+      st.keys[rank] = k;
+    }
+    {
+      const int pos[1] = {rank};
+      const uint32_t kk[1] = {k};
+      const bool act[1] = {lane < n};
+      stage_batch<1, true>(c, st, pos, kk, act, cxp, featp, N);
+    }
+    __syncwarp();
+    replay_column<kL, 1>(c, st, n, lane, sync, ego_e, cell, ncols);
+  }
+}
+
+// k_columns_cta: columns with more entries (walls and far floor: 7 % of the columns, two thirds of the entries), one CTA of
+// four warps = eight voxel slots per column, persistent over the mid list (kTinyCap < n <= kMidCap = 512, several CTAs per SM)
+// or the large list (kMidCap < n <= kLargeCap = 2048, one CTA per SM).  Bitonic sort of the keys in shared memory, then every
+// thread stages the entries at its sorted positions: a far floor cell collects hundreds of points in ONE voxel, whose
+// serial chain of additions then runs out of shared memory (a few cycles per entry) instead of global memory.
+template <int kL, int kFs, int kCap, int kList, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) k_columns_cta(SemMapCfg c, const float* __restrict__ obs, const float* __restrict__ coords,
+                                                     const int* __restrict__ col_start, const uint32_t* __restrict__ entries,
+                                                     const int* __restrict__ col_list, const int* __restrict__ list_n,
+                                                     float* __restrict__ ego) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t stage_raw[];
+  ColumnStage<kCap, kFs>& st = *reinterpret_cast<ColumnStage<kCap, kFs>*>(stage_raw);
+  constexpr int kThreads = kWarps * 32;
+  const int e = blockIdx.y;
+  const int ncols = c.vr * c.vr;
+  const int N = c.h * c.w;
+  const int tid = threadIdx.x;
+  const int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
+  // kList 2: the mid list (plane 1 from the front); 3: the large list (plane 1 from the back)
+  const int* list = col_list + static_cast<size_t>(e) * 2 * ncols + ncols;
+  const int n_list = list_n[e * 4 + kList];
+  float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
+  const float* cxp = coords + static_cast<size_t>(e) * 3 * N;
+  const float* featp = obs + (static_cast<size_t>(e) * c.channels + 4) * N;
+  auto sync = [] { __syncthreads(); };
+  for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+    const int col = kList == 2 ? list[li] : list[ncols - 1 - li];
+    const int s0 = start[col];
+    const int n = start[col + 1] - s0;
+    const int px = col / c.vr, py = col - px * c.vr;
+    const int cell = py * c.vr + px;
+    __syncthreads();  // the previous column's stage is no longer read
+    if (tid < 4) st.zbits[tid] = 0u;
+    if (tid < 32) st.red_all[tid] = 0.f, st.red_agent[tid] = 0.f;
+    int npow = 64;
+    while (npow < n) npow <<= 1;
+    const uint32_t* ent = entries + static_cast<size_t>(e) * 4 * N + s0;
+    for (int i = tid; i < npow; i += kThreads) st.keys[i] = i < n ? ent[i] : 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < npow; i += kThreads) {
+          const int l = i ^ j;
+          if (l > i) {
+            const uint32_t a = st.keys[i], b = st.keys[l];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) st.keys[i] = b, st.keys[l] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    constexpr int kB = 4;   // entries per thread and batch
+    for (int p0 = 0; p0 < n; p0 += kThreads * kB) {   // warp-uniform trip count
+      int pos[kB];
+      uint32_t kk[kB];
+      bool act[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        pos[u] = p0 + u * kThreads + tid;
+        act[u] = pos[u] < n;
+        kk[u] = act[u] ? st.keys[pos[u]] : 0u;
+      }
+      stage_batch<kB, false>(c, st, pos, kk, act, cxp, featp, N);
+    }
+    __syncthreads();
+    replay_column<kL, kWarps>(c, st, n, tid, sync, ego_e, cell, ncols);
+  }
+}
+
+// k_columns_big: the rare columns with more than kMidCap entries (a wall seen edge-on), one CTA per column: only the keys
+// fit shared memory (up to 32 768), thread z replays voxel z with its entries' coordinates and features read from global
+// memory, two entries in flight.
+template <int kF>  // register budget for the per-voxel features
+__global__ void __launch_bounds__(128, 4) k_columns_big(SemMapCfg c, const float* __restrict__ obs,
                                                  const float* __restrict__ coords, const int* __restrict__ col_start,
                                                  const uint32_t* __restrict__ entries, const int* __restrict__ col_list,
                                                  const int* __restrict__ list_n, float* __restrict__ ego) {
   pdl_grid_sync();
   extern __shared__ uint32_t keys[];
   __shared__ float red_all[kF], red_agent[kF];
-  __shared__ uint32_t raw[128];
-  // small columns: per-entry lateral weight, both z weights and the feature vector, staged by one thread per entry
-  __shared__ float e_wxy[128], e_wz0[128], e_wz1[128], e_feat[128][kF];
   __shared__ uint32_t zbits[4];  // z cells (0 .. nz, biased) that occur in the column's keys
   const int e = blockIdx.y;
   const int ncols = c.vr * c.vr;
   const int N = c.h * c.w;
   const int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
-  const int* list = col_list + static_cast<size_t>(e) * ncols;
-  const int n_list = list_n[e * 2 + large];
+  const int* list = col_list + static_cast<size_t>(e) * 2 * ncols;
+  const int n_list = list_n[e * 4 + 1];
   const int tid = threadIdx.x;
   float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
-  // persistent over this launch's share of the non-empty columns (empty ones keep the zeros of the memset)
   for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
-  const int col = large ? list[ncols - 1 - li] : list[li];
+  const int col = list[ncols - 1 - li];
   const int s0 = start[col];
   const int n = start[col + 1] - s0;
   const int px = col / c.vr, py = col - px * c.vr;
@@ -391,41 +739,11 @@ __global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, cons
   if (tid < 4) zbits[tid] = 0u;
   if (tid < kF) red_all[tid] = 0.f, red_agent[tid] = 0.f;
   const uint32_t* ent = entries + static_cast<size_t>(e) * 4 * N + s0;
-  if (n <= 128) {
-    // small column (the common case): rank sort - keys are unique (they embed the point index), so the number of
-    // smaller keys is the sorted position; two barriers instead of the ~log^2 n of the bitonic network
-    if (tid < n) raw[tid] = ent[tid];
-    __syncthreads();
-    if (tid < n) {
-      const uint32_t k = raw[tid];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) rank += raw[j] < k ? 1 : 0;
-      keys[rank] = k;
-      atomicOr(&zbits[(k >> 20) & 3u], 1u << ((k >> 15) & 31u));  // z cell (7 bits at 15..21) seen in this column
-      // this entry's weights and features, once, in parallel over the column's entries (the voxel threads below would
-      // otherwise each walk a chain of dependent global loads per entry)
-      const float* cxp = coords + static_cast<size_t>(e) * 3 * N;
-      const float* featp = obs + (static_cast<size_t>(e) * c.channels + 4) * N;
-      const int i = static_cast<int>(k & 0x7fffu);
-      const int ixy = static_cast<int>(k >> 22);
-      int pp;
-      float wx, wy, wz0, wz1;
-      bool ss;
-      corner(cxp[i], c.vr_f, ixy >> 1, pp, wx, ss);
-      corner(cxp[N + i], c.vr_f, ixy & 1, pp, wy, ss);
-      const float zc = cxp[2 * N + i];
-      corner(zc, c.nz_f, 0, pp, wz0, ss);
-      corner(zc, c.nz_f, 1, pp, wz1, ss);
-      e_wxy[rank] = (1.f * wx) * wy;
-      e_wz0[rank] = wz0, e_wz1[rank] = wz1;
-#pragma unroll
-      for (int f = 1; f < kF; ++f) e_feat[rank][f] = (f < c.nf) ? featp[static_cast<size_t>(f - 1) * N + i] : 0.f;
-    }
-    __syncthreads();
-  } else {
+  {
     // load + bitonic sort (ascending) of the column's keys
     int npow = 1;
     while (npow < n) npow <<= 1;
+    __syncthreads();
     for (int i = tid; i < npow; i += blockDim.x) {
       const uint32_t k = i < n ? ent[i] : 0xffffffffu;
       keys[i] = k;
@@ -466,16 +784,6 @@ __global__ void __launch_bounds__(128, 4) k_columns(SemMapCfg c, int large, cons
         const uint32_t kbase = (static_cast<uint32_t>(ixy) << 22) | (static_cast<uint32_t>(z - iz + 1) << 15);
         const int lo = lower_bound_key(keys, n, kbase);
         const int hi = lower_bound_key(keys, n, kbase + (1u << 15));
-        if (n <= 128) {  // staged column: everything is in shared memory
-          for (int t = lo; t < hi; ++t) {
-            const float w = e_wxy[t] * (iz ? e_wz1[t] : e_wz0[t]);
-            acc[0] = acc[0] + 1.f * w;
-#pragma unroll
-            for (int f = 1; f < kF; ++f) {
-              if (f < nf) acc[f] = acc[f] + e_feat[t][f] * w;
-            }
-          }
-        } else
         // two entries in flight (their coordinate and feature loads are independent of the running sums); the adds
         // stay in entry order, as the reference's index_add does
         for (int t0 = lo; t0 < hi; t0 += 2) {
@@ -609,6 +917,13 @@ __global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restri
   int tap_idx[16];
   float tap_w[16];
   int ntaps = 0;
+  // Only cells whose sampling position lies within fuse_r of the map centre can reach the ego window (the first sampler
+  // rotates about the centre, SemMap::init derives the radius with a two-cell margin): everything else - four cells in
+  // five - is a plain max(maps_last, 0) and skips the sixteen-tap arithmetic.
+  const float ctr = 0.5f * static_cast<float>(n - 1);
+  const float ddx = fx2 - ctr, ddy = fy2 - ctr;
+  const bool near = ddx * ddx + ddy * ddy <= c.fuse_r2;
+  if (near) {
 #pragma unroll
   for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
@@ -639,6 +954,7 @@ __global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restri
       }
     }
   }
+  }
   const size_t plane = static_cast<size_t>(n) * n;
   const size_t pix = static_cast<size_t>(y) * n + x;
   const float* ml = maps_last + static_cast<size_t>(e) * ml_env + static_cast<size_t>(y) * ml_row + x;
@@ -668,26 +984,45 @@ __global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restri
 void SemMap::init(const SemMapCfg& cfg, int envs) {
   c = cfg;
   E = envs;
+  {
+    // k_fuse's reach test: farthest ego-window cell from the map centre (pixel units), through the first sampler (a rotation
+    // about the centre, base coordinates scaled by (n - 1) / n) and the two bilinear footprints (sqrt(2) each), plus 2 cells
+    const double n = c.map_cells, ctr = 0.5 * (n - 1);
+    const double wx1 = c.map_cells / 2 - c.vr / 2, wy1 = c.map_cells / 2;
+    const double hx = std::max(std::fabs(wx1 - ctr), std::fabs(wx1 + c.vr - 1 - ctr));
+    const double hy = std::max(std::fabs(wy1 - ctr), std::fabs(wy1 + c.vr - 1 - ctr));
+    const double r = (std::sqrt(hx * hx + hy * hy) + std::sqrt(2.0)) * n / (n - 1) + std::sqrt(2.0) + 2.0;
+    c.fuse_r2 = static_cast<float>(r * r);
+  }
   PN_REQUIRE(c.nf <= kMaxFeat, "semmap: too many semantic categories");
   PN_REQUIRE(c.nz <= 126 && c.h * c.w <= 32767, "semmap: geometry out of range");
   const size_t N = static_cast<size_t>(c.h) * c.w;
   const size_t ncols = static_cast<size_t>(c.vr) * c.vr;
   coords = static_cast<float*>(arena.alloc(E * 3 * N * sizeof(float)));
-  col_count = static_cast<int*>(arena.alloc((E * ncols + 2 * E) * sizeof(int)));  // [E][vr*vr] + qcount[E][2]
+  col_count = static_cast<int*>(arena.alloc((E * ncols + 4 * E) * sizeof(int)));  // [E][vr*vr] + qcount[E][4]
   qcount = reinterpret_cast<uint32_t*>(col_count + E * ncols);
   col_start = static_cast<int*>(arena.alloc(E * (ncols + 1) * sizeof(int)));
   col_fill = static_cast<int*>(arena.alloc(E * ncols * sizeof(int)));
   entries = static_cast<uint32_t*>(arena.alloc(E * 4 * N * sizeof(uint32_t)));
   ego = static_cast<float*>(arena.alloc(E * c.ego_channels * ncols * sizeof(float)));
-  col_list = static_cast<int*>(arena.alloc(E * ncols * sizeof(int)));
-  list_n = static_cast<int*>(arena.alloc(E * 2 * sizeof(int)));
+  col_list = static_cast<int*>(arena.alloc(E * 2 * ncols * sizeof(int)));
+  list_n = static_cast<int*>(arena.alloc(E * 4 * sizeof(int)));
   int dev = 0;
   PN_CUDA_CHECK(cudaGetDevice(&dev));
   PN_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   xf = static_cast<float*>(arena.alloc(E * 4 * sizeof(float)));
   stair_flag = static_cast<int*>(arena.alloc(E * sizeof(int)));
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns<kMaxFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_big<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_big<kMaxFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<16, 12, kMidCap, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(sizeof(ColumnStage<kMidCap, 12>))));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<32, kMaxFeat, kMidCap, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(sizeof(ColumnStage<kMidCap, kMaxFeat>))));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<16, 12, kLargeCap, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(sizeof(ColumnStage<kLargeCap, 12>))));
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<32, kMaxFeat, kLargeCap, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(sizeof(ColumnStage<kLargeCap, kMaxFeat>))));
+  PN_REQUIRE(ncols <= 1024 * static_cast<size_t>(kScanPer), "semmap: vision_range too large for k_scan");
 }
 
 void SemMap::forward(const float* obs, const float* pose_delta, const float* maps_last, long long ml_env,
@@ -695,23 +1030,30 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
                      cudaStream_t s) {
   const int N = c.h * c.w;
   const int ncols = c.vr * c.vr;
-  PN_CUDA_CHECK(cudaMemsetAsync(col_count, 0, (static_cast<size_t>(E) * ncols + 2 * E) * sizeof(int), s));  // + qcount
+  PN_CUDA_CHECK(cudaMemsetAsync(col_count, 0, (static_cast<size_t>(E) * ncols + 4 * E) * sizeof(int), s));  // + qcount
   PN_CUDA_CHECK(cudaMemsetAsync(ego, 0, static_cast<size_t>(E) * c.ego_channels * ncols * sizeof(float), s));
   launch_pdl(k_coords, dim3((N + 255) / 256, E), 256, 0, s, c, obs, coords, qcount);
   launch_pdl(k_quantile, E, 1024, 0, s, c, coords, qcount, stair_flag);
   launch_pdl(k_hist, dim3((N + 255) / 256, E), 256, 0, s, c, obs, coords, stair_flag, col_count);
-  constexpr int kSmallCap = 2048;
-  launch_pdl(k_scan, E, 1024, 0, s, ncols, kSmallCap, col_count, col_start, col_fill, col_list, list_n);
+  launch_pdl(k_scan, E, 1024, 0, s, ncols, col_count, col_start, col_fill, col_list, list_n);
   launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
-  // non-empty columns only, persistent CTAs: 8 KB of key storage each for the small ones, 128 KB for the rare
-  // columns that collect more than kSmallCap entries (a wall seen edge-on)
-  const int g_small = std::min(ncols, num_sms * 8), g_large = std::min(ncols, num_sms);
+  // non-empty columns only, persistent over four work lists (see k_scan): a warp per tiny column, a CTA per mid / large
+  // column with its entries staged in shared memory, a CTA with 128 KB of key storage per big column
+  const int g_warp = std::min((ncols + 3) / 4, num_sms * 16), g_cta = std::min(ncols, num_sms * 6), g_big = std::min(ncols, num_sms);
   if (c.nf <= 12) {
-    launch_pdl(k_columns<12>, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
-    launch_pdl(k_columns<12>, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_warp<16, 12>, dim3(g_warp, E), 128, 0, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_cta<16, 12, kMidCap, 2, 4>, dim3(g_cta, E), 128, sizeof(ColumnStage<kMidCap, 12>), s, c, obs, coords, col_start,
+               entries, col_list, list_n, ego);
+    launch_pdl(k_columns_cta<16, 12, kLargeCap, 3, 16>, dim3(g_big, E), 512, sizeof(ColumnStage<kLargeCap, 12>), s, c, obs, coords,
+               col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_big<12>, dim3(g_big, E), 128, 32768 * 4, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
   } else {
-    launch_pdl(k_columns<kMaxFeat>, dim3(g_small, E), 128, kSmallCap * 4, s, c, 0, obs, coords, col_start, entries, col_list, list_n, ego);
-    launch_pdl(k_columns<kMaxFeat>, dim3(g_large, E), 128, 32768 * 4, s, c, 1, obs, coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_warp<32, kMaxFeat>, dim3(g_warp, E), 128, 0, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_cta<32, kMaxFeat, kMidCap, 2, 4>, dim3(g_cta, E), 128, sizeof(ColumnStage<kMidCap, kMaxFeat>), s, c, obs, coords,
+               col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_cta<32, kMaxFeat, kLargeCap, 3, 16>, dim3(g_big, E), 512, sizeof(ColumnStage<kLargeCap, kMaxFeat>), s, c, obs,
+               coords, col_start, entries, col_list, list_n, ego);
+    launch_pdl(k_columns_big<kMaxFeat>, dim3(g_big, E), 128, 32768 * 4, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
   }
   launch_pdl(k_pose, (E + 63) / 64, 64, 0, s, c, E, pose_delta, poses_inout, xf);
   launch_pdl(k_fuse, dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);

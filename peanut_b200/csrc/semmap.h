@@ -18,6 +18,7 @@ struct SemMapCfg {
   float xc, zc, f;     // camera matrix (depth_utils.py:27-34)
   float agent_height, shift_x, res, half_vr, vr_f, z_mid, nz_f;
   float map_thr, exp_thr, cat_thr;
+  float fuse_r2 = 0.f;  // set by SemMap::init: squared reach of the ego window in k_fuse's sampling space
 };
 
 struct SemMap {
@@ -26,17 +27,17 @@ struct SemMap {
   Arena arena;
   float* coords = nullptr;     // [E][3][N] normalised splat coordinates
   int* col_count = nullptr;    // [E][vr*vr]
-  uint32_t* qcount = nullptr;  // [E][2] valid heights / heights in the stair band (same allocation as col_count)
+  uint32_t* qcount = nullptr;  // [E][4] valid heights / heights in the stair band / heights <= 0.2 (same allocation as col_count)
   int* col_start = nullptr;    // [E][vr*vr + 1]
   int* col_fill = nullptr;     // [E][vr*vr]
   uint32_t* entries = nullptr; // [E][4*N] bucketed (corner, z, point) keys
   float* ego = nullptr;        // [E][ego_channels][vr][vr]
-  int* col_list = nullptr;     // [E][vr*vr] non-empty columns: small ones from the front, large ones from the back
-  int* list_n = nullptr;       // [E][2] = {#small, #large}
+  int* col_list = nullptr;     // [E][2][vr*vr] non-empty columns: plane 0 = tiny from the front, big from the back; plane 1 = mid / large
+  int* list_n = nullptr;       // [E][4] = {#tiny, #big, #mid, #large}
   int num_sms = 148;
   float* xf = nullptr;         // [E][4] cos, sin, tx, ty of the sampling grids
   int* stair_flag = nullptr;   // [E]
-  static constexpr int kLaunches = 9;  // kernels per forward (plus two memsets)
+  static constexpr int kLaunches = 11;  // kernels per forward (plus two memsets)
 
   void init(const SemMapCfg& cfg, int envs);
   // maps_last may be a strided view (element strides between envs, channel planes and rows; unit x stride)

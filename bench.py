@@ -9,11 +9,14 @@ checkpoints exist offline).
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload auto|cfg1|cfg2|cfg3] [--impl reference]
 
 Workloads (BASELINE.json `configs`):
-  cfg2 = 32 frames, bf16 (configs[2]): the default at 1 GPU - the configuration the north star's roofline target is quoted
-         on; the batch-1 fp32-storage / tf32 result (configs[1], `cfg1`) rides along as the nested `latency` block;
-  cfg3 = 8 envs per GPU, bf16 (configs[3] per-GPU slice): the default under torchrun (N > 1), with the result gather to
-         rank 0 (one-sided push over NVLink peer memory, pn_gather_*) INSIDE every timed step.
-Every rank runs the same per-GPU workload on its own environments (weak scaling, no data-path collective).
+  cfg2 = 32 frames per GPU, bf16 (configs[2]): the headline at every N - the configuration the north star's roofline target
+         is quoted on.  Per-GPU work is FIXED as N grows (weak scaling: value(N) / (N * value(1)) is the efficiency the
+         driver computes from the lines); under torchrun (N > 1) every timed step also contains the result gather to rank
+         0 (one-sided push over NVLink peer memory, pn_gather_*);
+  cfg1 = batch 1, fp32 storage / tf32 MMA (configs[1]): rides along at N = 1 as the nested `latency` block;
+  cfg3 = 8 envs per GPU, bf16 (configs[3]: 64 envs on 8 GPUs): measured in the same run at every N as the nested `cfg3`
+         block (same step, same gather), so that its own weak-scaling series is in the driver's records too.
+Every rank runs the same per-GPU workload on its own environments (no data-path collective).
 
 `--impl reference` times the reference's CPU implementation of the same step on the host cores: the reference's own
 code where it is importable offline (Semantic_Mapping is restated op by op and pinned bit-exact to it), the
@@ -34,7 +37,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     "cfg1": dict(envs=1, precision="tf32", desc="configs[1]: batch=1 full pipeline (Mask-RCNN + mapper + map-prediction net), fp32 storage / tf32 MMA"),
     "cfg3": dict(envs=8, precision="bf16", desc="configs[3] per-GPU slice: 8 envs per GPU, bf16 tensor-core path"),
-    "cfg2": dict(envs=32, precision="bf16", desc="configs[2]: batch=32 frames, bf16 tensor-core path"),
+    "cfg2": dict(envs=32, precision="bf16", desc="configs[2]: batch=32 frames per GPU, bf16 tensor-core path"),
 }
 MAP_SHAPES = {"base": (24, 240, 240), "ref": (14, 720, 720)}
 METRIC = "frames/sec (RGB-D -> predicted semantic map)"
@@ -65,7 +68,7 @@ def parse():
     p.add_argument("--no-profile", action="store_true")
     p.add_argument("--no-latency", action="store_true", help="skip the nested batch-1 tf32 (configs[1]) block")
     p.add_argument("--no-ref-gpu", action="store_true", help="skip the eager-PyTorch-on-GPU comparator (ref_gpu_eager)")
-    p.add_argument("--no-scaling-base", action="store_true", help="skip the 1-GPU run of the multi-GPU workload (scaling_base)")
+    p.add_argument("--no-scaling-base", action="store_true", help="skip the nested configs[3] block (cfg3)")
     p.add_argument("--verbose", action="store_true")
     return p.parse_args()
 
@@ -183,7 +186,7 @@ def time_cpu(step, warmup, steps, budget_s):
 
 
 def resolve_workload(a, world):
-    return a.workload if a.workload != "auto" else ("cfg2" if world == 1 else "cfg3")
+    return a.workload if a.workload != "auto" else "cfg2"
 
 
 def run_reference(a):
@@ -432,12 +435,12 @@ def run_ours(a):
     if world == 1 and name != "cfg1" and not a.no_latency:
         latency = measure(a, "cfg1", rank, local, world, dev, map_shape, max(steps, 30), False, "none")
 
-    # The multi-GPU default workload (cfg3: 8 envs per GPU) differs from the 1-GPU headline (cfg2: 32 frames), so the 1-GPU
-    # line also carries the 1-GPU number of cfg3: the base a weak-scaling efficiency of the N > 1 lines has to be taken
-    # against (value(N) / (N * scaling_base.value)).
-    scaling_base = None
-    if world == 1 and name != "cfg3" and a.workload == "auto" and not a.no_scaling_base:
-        scaling_base = measure(a, "cfg3", rank, local, world, dev, map_shape, steps, False, "none")
+    # configs[3] (8 envs per GPU) in the same run at every N: its weak-scaling series = cfg3.value(N) / (N * cfg3.value(1))
+    cfg3 = None
+    if name != "cfg3" and a.workload == "auto" and not a.no_scaling_base:
+        a3 = argparse.Namespace(**vars(a))
+        a3.no_profile = True   # the roofline block belongs to the headline workload
+        cfg3 = measure(a3, "cfg3", rank, local, world, dev, map_shape, steps, False, a.gather)
 
     if rank != 0:
         if world > 1:
@@ -468,13 +471,13 @@ def run_ours(a):
                            "e2e_ms_per_step": latency["e2e_ms"], "steps": max(steps, 30),
                            "roofline": latency.get("roofline")}
 
-    if scaling_base is not None:
-        line["scaling_base"] = {"workload": scaling_base["desc"], "envs_per_gpu": scaling_base["E"], "n_gpus": 1,
-                                "value": scaling_base["E"] / (scaling_base["dev_ms"] / 1000.0), "unit": "frames/s",
-                                "ms_per_step": scaling_base["dev_ms"],
-                                "e2e_value": scaling_base["E"] / (scaling_base["e2e_ms"] / 1000.0),
-                                "note": "the N > 1 lines run THIS workload per GPU (plus the result gather inside the step): "
-                                        "weak-scaling efficiency = value(N) / (N * this value)"}
+    if cfg3 is not None:
+        line["cfg3"] = {"workload": cfg3["desc"], "envs_per_gpu": cfg3["E"], "n_gpus": world,
+                        "value": cfg3["E"] * world / (cfg3["dev_ms"] / 1000.0), "unit": "frames/s",
+                        "ms_per_step": cfg3["dev_ms"], "e2e_value": cfg3["E"] * world / (cfg3["e2e_ms"] / 1000.0),
+                        "gather_in_step": world > 1 and a.gather != "none", "gather_ms": cfg3["gather_ms"],
+                        "note": "BASELINE configs[3] measured like the headline (whole-job frames/s, max over ranks); "
+                                "weak-scaling efficiency = cfg3.value(N) / (N * cfg3.value(1))"}
 
     # ---- the reference's GPU path (eager PyTorch restatement with the reference's host round trips), a reported comparator
     if world == 1 and not a.no_ref_gpu:

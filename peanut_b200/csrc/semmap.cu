@@ -268,6 +268,8 @@ constexpr int kScanPer = 16;  // columns per thread of k_scan (1024 threads): vi
 __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict__ col_count, int* __restrict__ col_start,
                                                int* __restrict__ col_fill, int* __restrict__ col_list, int* __restrict__ list_n) {
   pdl_grid_sync();
+  extern __shared__ int s_cnt[];   // [ncols]: the counters, then the prefix sums (global traffic stays coalesced: a single SM
+                                   // retires about one 32-byte sector per cycle, 16 us for this kernel with strided accesses)
   const int e = blockIdx.x;
   int* list = col_list + static_cast<size_t>(e) * 2 * ncols;
   __shared__ int warp_sums[32];
@@ -276,35 +278,18 @@ __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict_
   int* start = col_start + static_cast<size_t>(e) * (ncols + 1);
   int* fill = col_fill + static_cast<size_t>(e) * ncols;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) s_cnt[i] = cnt[i], fill[i] = 0;
+  __syncthreads();
   const int per = (ncols + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
   const int c0 = min(static_cast<int>(threadIdx.x) * per, ncols), c1 = min(c0 + per, ncols);
-  int v[kScanPer];   // this thread's counters, all loads in flight together
+  int v[kScanPer];   // this thread's run of consecutive counters
 #pragma unroll
-  for (int j = 0; j < kScanPer; ++j) v[j] = (c0 + j < c1) ? cnt[c0 + j] : 0;
+  for (int j = 0; j < kScanPer; ++j) v[j] = (c0 + j < c1) ? s_cnt[c0 + j] : 0;
   int run = 0;
 #pragma unroll
   for (int j = 0; j < kScanPer; ++j) run += v[j];
-  int x = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) warp_sums[wid] = x;
-  __syncthreads();
-  if (wid == 0) {
-    int sw = warp_sums[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, sw, o);
-      if (lane >= o) sw += y;
-    }
-    warp_sums[lane] = sw;
-  }
-  __syncthreads();
-  int excl = (wid ? warp_sums[wid - 1] : 0) + x - run;
-  // list positions by two more block scans over packed per-thread class counts (16 bits each: at most 16 384 columns);
-  // thousands of shared-memory atomics on four counters would serialise (15 us per map in round 2's first version)
+  // one block scan of the run totals and of the packed per-thread class counts (16 bits each: at most 16 384 columns);
+  // shared-memory atomics on four list counters would serialise
   uint32_t ca = 0, cb = 0;   // ca = tiny | mid << 16, cb = large | big << 16
 #pragma unroll
   for (int j = 0; j < kScanPer; ++j) {
@@ -315,25 +300,29 @@ __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict_
       else cb += 1u << 16;
     }
   }
+  int x = run;
   uint32_t xa = ca, xb = cb;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
     const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
-    if (lane >= o) xa += ya, xb += yb;
+    if (lane >= o) x += y, xa += ya, xb += yb;
   }
-  __syncthreads();   // warp_sums of the first scan have been read
-  if (lane == 31) cls_sums[0][wid] = xa, cls_sums[1][wid] = xb;
+  if (lane == 31) warp_sums[wid] = x, cls_sums[0][wid] = xa, cls_sums[1][wid] = xb;
   __syncthreads();
   if (wid == 0) {
+    int sw = warp_sums[lane];
     uint32_t sa = cls_sums[0][lane], sb = cls_sums[1][lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, sw, o);
       const uint32_t ya = __shfl_up_sync(0xffffffffu, sa, o), yb = __shfl_up_sync(0xffffffffu, sb, o);
-      if (lane >= o) sa += ya, sb += yb;
+      if (lane >= o) sw += y, sa += ya, sb += yb;
     }
-    cls_sums[0][lane] = sa, cls_sums[1][lane] = sb;
+    warp_sums[lane] = sw, cls_sums[0][lane] = sa, cls_sums[1][lane] = sb;
   }
   __syncthreads();
+  int excl = (wid ? warp_sums[wid - 1] : 0) + x - run;
   const uint32_t ea = (wid ? cls_sums[0][wid - 1] : 0u) + xa - ca, eb = (wid ? cls_sums[1][wid - 1] : 0u) + xb - cb;
   int p_tiny = static_cast<int>(ea & 0xffffu), p_mid = static_cast<int>(ea >> 16);
   int p_large = static_cast<int>(eb & 0xffffu), p_big = static_cast<int>(eb >> 16);
@@ -341,8 +330,7 @@ __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict_
   for (int j = 0; j < kScanPer; ++j) {
     const int i = c0 + j;
     if (i < c1) {
-      start[i] = excl;
-      fill[i] = 0;
+      s_cnt[i] = excl;
       excl += v[j];
       if (v[j] > 0) {
         if (v[j] <= kTinyCap) list[p_tiny++] = i;
@@ -356,6 +344,8 @@ __global__ void __launch_bounds__(1024) k_scan(int ncols, const int* __restrict_
     start[ncols] = excl;
     list_n[e * 4] = p_tiny, list_n[e * 4 + 1] = p_big, list_n[e * 4 + 2] = p_mid, list_n[e * 4 + 3] = p_large;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) start[i] = s_cnt[i];
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -691,7 +681,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_columns_cta(SemMapCfg c, const 
         __syncthreads();
       }
     }
-    constexpr int kB = 4;   // entries per thread and batch
+    constexpr int kB = 2;   // entries per thread and batch (four would cost 128 registers and a third of the resident CTAs)
     for (int p0 = 0; p0 < n; p0 += kThreads * kB) {   // warp-uniform trip count
       int pos[kB];
       uint32_t kk[kB];
@@ -888,7 +878,7 @@ __device__ __forceinline__ float base_coord(int i, int n) {
 // --------------------------------------------------------------------------------------------------
 // k_fuse: translated = grid_sample(grid_sample(agent_view, rot), trans); map = max(maps_last, translated).
 // One thread per local-map cell; the 100 x 100 ego window is the only non-zero part of agent_view.
-__global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restrict__ xf, const float* __restrict__ ego,
+__global__ void __launch_bounds__(256, 3) k_fuse(SemMapCfg c, const float* __restrict__ xf, const float* __restrict__ ego,
                                               const float* __restrict__ maps_last, long long ml_env, long long ml_plane,
                                               long long ml_row, float* __restrict__ map_out,
                                               float* __restrict__ fp_out) {
@@ -923,7 +913,27 @@ __global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restri
   const float ctr = 0.5f * static_cast<float>(n - 1);
   const float ddx = fx2 - ctr, ddy = fy2 - ctr;
   const bool near = ddx * ddx + ddy * ddy <= c.fuse_r2;
-  if (near) {
+  if (!near) {
+    // plain max(maps_last, 0): all channel loads in flight, then the stores; pointers advance by the plane strides
+    const float* ml = maps_last + static_cast<size_t>(e) * ml_env + static_cast<size_t>(y) * ml_row + x;
+    float* mo = map_out + (static_cast<size_t>(e) * c.channels * n + y) * n + x;
+    const size_t plane = static_cast<size_t>(n) * n;
+    constexpr int kU = 16;
+    for (int ch0 = 0; ch0 < c.channels; ch0 += kU) {
+      float last[kU];
+      const float* p = ml;
+#pragma unroll
+      for (int u = 0; u < kU; ++u, p += ml_plane) last[u] = (ch0 + u < c.channels) ? __ldg(p) : 0.f;
+      float* q = mo;
+#pragma unroll
+      for (int u = 0; u < kU; ++u, q += plane) {
+        if (ch0 + u < c.channels) *q = fmaxf(last[u], 0.f);
+      }
+      ml += kU * ml_plane, mo += kU * plane;
+    }
+    return;
+  }
+  {
 #pragma unroll
   for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
@@ -1023,6 +1033,7 @@ void SemMap::init(const SemMapCfg& cfg, int envs) {
   PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<32, kMaxFeat, kLargeCap, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(ColumnStage<kLargeCap, kMaxFeat>))));
   PN_REQUIRE(ncols <= 1024 * static_cast<size_t>(kScanPer), "semmap: vision_range too large for k_scan");
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * kScanPer * static_cast<int>(sizeof(int))));
 }
 
 void SemMap::forward(const float* obs, const float* pose_delta, const float* maps_last, long long ml_env,
@@ -1035,7 +1046,7 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
   launch_pdl(k_coords, dim3((N + 255) / 256, E), 256, 0, s, c, obs, coords, qcount);
   launch_pdl(k_quantile, E, 1024, 0, s, c, coords, qcount, stair_flag);
   launch_pdl(k_hist, dim3((N + 255) / 256, E), 256, 0, s, c, obs, coords, stair_flag, col_count);
-  launch_pdl(k_scan, E, 1024, 0, s, ncols, col_count, col_start, col_fill, col_list, list_n);
+  launch_pdl(k_scan, E, 1024, static_cast<size_t>(ncols) * sizeof(int), s, ncols, col_count, col_start, col_fill, col_list, list_n);
   launch_pdl(k_fill, dim3((N + 255) / 256, E), 256, 0, s, c, coords, col_start, col_fill, entries);
   // non-empty columns only, persistent over four work lists (see k_scan): a warp per tiny column, a CTA per mid / large
   // column with its entries staged in shared memory, a CTA with 128 KB of key storage per big column

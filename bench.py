@@ -195,6 +195,9 @@ def run_reference(a):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host thread (set before torch loads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["MKL_NUM_THREADS"] = str(threads)
     map_shape = MAP_SHAPES[a.map]
     step = cpu_step_factory(map_shape, threads)
     times = time_cpu(step, min(a.warmup, 1), a.steps, budget_s=150.0)

@@ -877,143 +877,99 @@ __device__ __forceinline__ float base_coord(int i, int n) {
 
 // --------------------------------------------------------------------------------------------------
 // k_fuse: translated = grid_sample(grid_sample(agent_view, rot), trans); map = max(maps_last, translated).
-// The 100 x 100 ego window is the only non-zero part of agent_view, and only cells whose sampling position lies within
-// fuse_r of the map centre can reach it (the first sampler rotates about the centre; SemMap::init derives the radius with a
-// two-cell margin): everything else - four cells in five - is a plain max(maps_last, 0).
-//
-// Position of output cell (y, x) in the second sampler's source image, and its squared distance from the centre.
-struct FusePos {
-  float fx2, fy2, d2;
-};
-__device__ __forceinline__ FusePos fuse_pos(int x, int y, int n, float tx, float ty) {
-  FusePos p;
+// One thread per local-map cell.  The 100 x 100 ego window is the only non-zero part of agent_view, and only cells whose
+// sampling position lies within fuse_r of the map centre can reach it (the first sampler rotates about the centre;
+// SemMap::init derives the radius with a two-cell margin): everything else - four cells in five - is a plain
+// max(maps_last, 0).  For the others the sixteen taps of the two chained samplers are walked once, tap outer / channel
+// inner, with the kE ego channels' sums in registers (same products, same order per channel as a tap list would give;
+// round 2's first version kept the taps in local-memory arrays and re-read them per channel: 1 500 instructions per cell).
+template <int kE>
+__global__ void __launch_bounds__(256) k_fuse(SemMapCfg c, const float* __restrict__ xf, const float* __restrict__ ego,
+                                              const float* __restrict__ maps_last, long long ml_env, long long ml_plane,
+                                              long long ml_row, float* __restrict__ map_out, float* __restrict__ fp_out) {
+  pdl_grid_sync();
+  const int e = blockIdx.z;
+  const int n = c.map_cells;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= n) return;
+  const int ncols = c.vr * c.vr;
+  const float tx = xf[e * 4 + 2], ty = xf[e * 4 + 3];
+  const float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
+  // fp_map_pred output = obstacle channel of the ego window
+  if (fp_out != nullptr && y < c.vr && x < c.vr) fp_out[(static_cast<size_t>(e) * c.vr + y) * c.vr + x] = ego_e[y * c.vr + x];
+
+  // second sampler: where does output cell (y, x) read `rotated`?
   const float bx = base_coord(x, n), by = base_coord(y, n);
   const float gx2 = bx * 1.f + by * (-0.f) + tx;
   const float gy2 = bx * 0.f + by * 1.f + ty;
-  p.fx2 = ((gx2 + 1.f) / 2.f) * static_cast<float>(n - 1);
-  p.fy2 = ((gy2 + 1.f) / 2.f) * static_cast<float>(n - 1);
+  const float fx2 = ((gx2 + 1.f) / 2.f) * static_cast<float>(n - 1);
+  const float fy2 = ((gy2 + 1.f) / 2.f) * static_cast<float>(n - 1);
   const float ctr = 0.5f * static_cast<float>(n - 1);
-  const float ddx = p.fx2 - ctr, ddy = p.fy2 - ctr;
-  p.d2 = ddx * ddx + ddy * ddy;
-  return p;
-}
-
-// One cell that may reach the ego window: the sixteen taps of the two chained samplers, then the channel loop.
-__device__ __noinline__ void fuse_cell_near(int n, int vr, int channels, float cs, float sn, float fx2, float fy2,
-                                            const float* __restrict__ ego_e, const float* __restrict__ ml,
-                                            long long ml_plane, float* __restrict__ mo) {
-  const int ncols = vr * vr;
-  const int wx1 = n / 2 - vr / 2, wy1 = n / 2;  // ego window origin (mapping.py:127-130)
-  const float x2f = floorf(fx2), y2f = floorf(fy2);
-  int tap_idx[16];
-  float tap_w[16];
-  int ntaps = 0;
+  const float ddx = fx2 - ctr, ddy = fy2 - ctr;
+  const bool near = ddx * ddx + ddy * ddy <= c.fuse_r2;
+  float v[kE];
 #pragma unroll
-  for (int cy = 0; cy < 2; ++cy) {
+  for (int k = 0; k < kE; ++k) v[k] = 0.f;
+  if (near) {
+    const float cs = xf[e * 4], sn = xf[e * 4 + 1];
+    const int wx1 = n / 2 - c.vr / 2, wy1 = n / 2;  // ego window origin (mapping.py:127-130)
+    const float x2f = floorf(fx2), y2f = floorf(fy2);
 #pragma unroll
-    for (int cxi = 0; cxi < 2; ++cxi) {
-      const float qxf = x2f + cxi, qyf = y2f + cy;
-      const float w2 = (cxi ? (fx2 - x2f) : (x2f + 1.f - fx2)) * (cy ? (fy2 - y2f) : (y2f + 1.f - fy2));
-      if (!(qxf >= 0.f && qxf <= static_cast<float>(n - 1) && qyf >= 0.f && qyf <= static_cast<float>(n - 1))) continue;
-      const int qx = static_cast<int>(qxf), qy = static_cast<int>(qyf);
-      // first sampler: rotated(qy, qx) reads agent_view at
-      const float rbx = base_coord(qx, n), rby = base_coord(qy, n);
-      const float gx1 = rbx * cs + rby * (-sn) + 0.f;
-      const float gy1 = rbx * sn + rby * cs + 0.f;
-      const float fx1 = ((gx1 + 1.f) / 2.f) * static_cast<float>(n - 1);
-      const float fy1 = ((gy1 + 1.f) / 2.f) * static_cast<float>(n - 1);
-      const float x1f = floorf(fx1), y1f = floorf(fy1);
+    for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
+      for (int cxi = 0; cxi < 2; ++cxi) {
+        const float qxf = x2f + cxi, qyf = y2f + cy;
+        const float w2 = (cxi ? (fx2 - x2f) : (x2f + 1.f - fx2)) * (cy ? (fy2 - y2f) : (y2f + 1.f - fy2));
+        if (!(qxf >= 0.f && qxf <= static_cast<float>(n - 1) && qyf >= 0.f && qyf <= static_cast<float>(n - 1))) continue;
+        const int qx = static_cast<int>(qxf), qy = static_cast<int>(qyf);
+        // first sampler: rotated(qy, qx) reads agent_view at
+        const float rbx = base_coord(qx, n), rby = base_coord(qy, n);
+        const float gx1 = rbx * cs + rby * (-sn) + 0.f;
+        const float gy1 = rbx * sn + rby * cs + 0.f;
+        const float fx1 = ((gx1 + 1.f) / 2.f) * static_cast<float>(n - 1);
+        const float fy1 = ((gy1 + 1.f) / 2.f) * static_cast<float>(n - 1);
+        const float x1f = floorf(fx1), y1f = floorf(fy1);
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int ax = static_cast<int>(x1f) + dx - wx1, ay = static_cast<int>(y1f) + dy - wy1;
-          const float w1 = (dx ? (fx1 - x1f) : (x1f + 1.f - fx1)) * (dy ? (fy1 - y1f) : (y1f + 1.f - fy1));
-          if (ax >= 0 && ax < vr && ay >= 0 && ay < vr) {
-            tap_idx[ntaps] = ay * vr + ax;
-            tap_w[ntaps] = w1 * w2;
-            ++ntaps;
+        for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int ax = static_cast<int>(x1f) + dx - wx1, ay = static_cast<int>(y1f) + dy - wy1;
+            const float w1 = (dx ? (fx1 - x1f) : (x1f + 1.f - fx1)) * (dy ? (fy1 - y1f) : (y1f + 1.f - fy1));
+            if (ax >= 0 && ax < c.vr && ay >= 0 && ay < c.vr) {
+              const float w = w1 * w2;
+              const float* src = ego_e + ay * c.vr + ax;
+#pragma unroll
+              for (int k = 0; k < kE; ++k) {
+                if (k < c.ego_channels) v[k] += src[static_cast<size_t>(k) * ncols] * w;
+              }
+            }
           }
         }
       }
     }
   }
   const size_t plane = static_cast<size_t>(n) * n;
-  for (int ch0 = 0; ch0 < channels; ch0 += 8) {
+  const size_t pix = static_cast<size_t>(y) * n + x;
+  const float* ml = maps_last + static_cast<size_t>(e) * ml_env + static_cast<size_t>(y) * ml_row + x;
+  float* mo = map_out + static_cast<size_t>(e) * c.channels * plane + pix;
+  // the map is streamed once (read maps_last, write map_out): keep eight channel loads in flight per thread;
+  // map channel 0, 1 <- ego channel 0, 1; channels 2, 3 (agent location) receive nothing; channel ch >= 4 <- ego ch - 2
+#pragma unroll
+  for (int ch0 = 0; ch0 < kE + 2; ch0 += 8) {
+    if (ch0 >= c.channels) break;
     float last[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) last[u] = (ch0 + u < channels) ? __ldg(ml + (ch0 + u) * ml_plane) : 0.f;
+    for (int u = 0; u < 8; ++u) last[u] = (ch0 + u < c.channels) ? __ldg(ml + (ch0 + u) * ml_plane) : 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int ch = ch0 + u;
-      if (ch >= channels) break;
-      float v = 0.f;
-      if (ntaps > 0 && ch != 2 && ch != 3) {
-        const float* src = ego_e + static_cast<size_t>(ch < 2 ? ch : ch - 2) * ncols;
-        for (int k = 0; k < ntaps; ++k) v += src[tap_idx[k]] * tap_w[k];
-      }
-      mo[ch * plane] = fmaxf(last[u], v);
-    }
-  }
-}
-
-// kV = 4: one thread per four consecutive cells of a row, 16-byte loads and stores for the plain max(maps_last, 0) of the far
-// cells (needs map side and strides divisible by 4 and 16-byte aligned bases: SemMap::forward checks); kV = 1: one thread per
-// cell, any layout.  A group is far when its first cell is farther than the reach plus the group's width.
-template <int kV>
-__global__ void __launch_bounds__(128) k_fuse(SemMapCfg c, const float* __restrict__ xf, const float* __restrict__ ego,
-                                              const float* __restrict__ maps_last, long long ml_env, long long ml_plane,
-                                              long long ml_row, float* __restrict__ map_out, float* __restrict__ fp_out) {
-  pdl_grid_sync();
-  const int e = blockIdx.z;
-  const int n = c.map_cells;
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * kV;
-  const int y = blockIdx.y;
-  if (x0 >= n) return;
-  const int ncols = c.vr * c.vr;
-  const float tx = xf[e * 4 + 2], ty = xf[e * 4 + 3];
-  const float* ego_e = ego + static_cast<size_t>(e) * c.ego_channels * ncols;
-  // fp_map_pred output = obstacle channel of the ego window
-  if (fp_out != nullptr && y < c.vr) {
-#pragma unroll
-    for (int u = 0; u < kV; ++u) {
-      if (x0 + u < c.vr) fp_out[(static_cast<size_t>(e) * c.vr + y) * c.vr + x0 + u] = ego_e[y * c.vr + x0 + u];
-    }
-  }
-  const size_t plane = static_cast<size_t>(n) * n;
-  const float* ml = maps_last + static_cast<size_t>(e) * ml_env + static_cast<size_t>(y) * ml_row + x0;
-  float* mo = map_out + (static_cast<size_t>(e) * c.channels * n + y) * n + x0;
-  const FusePos p0 = fuse_pos(x0, y, n, tx, ty);
-  if (p0.d2 > (kV == 1 ? c.fuse_r2 : c.fuse_r2_group)) {
-    // plain max(maps_last, 0): seven channel loads in flight, then their stores
-    constexpr int kU = 7;
-    for (int ch0 = 0; ch0 < c.channels; ch0 += kU) {
-      if constexpr (kV == 4) {
-        float4 last[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          last[u] = (ch0 + u < c.channels) ? __ldg(reinterpret_cast<const float4*>(ml + (ch0 + u) * ml_plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          if (ch0 + u < c.channels)
-            *reinterpret_cast<float4*>(mo + (ch0 + u) * plane) =
-                make_float4(fmaxf(last[u].x, 0.f), fmaxf(last[u].y, 0.f), fmaxf(last[u].z, 0.f), fmaxf(last[u].w, 0.f));
-        }
-      } else {
-        float last[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) last[u] = (ch0 + u < c.channels) ? __ldg(ml + (ch0 + u) * ml_plane) : 0.f;
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          if (ch0 + u < c.channels) mo[(ch0 + u) * plane] = fmaxf(last[u], 0.f);
-        }
+      if (ch < c.channels) {
+        const int k = ch < 2 ? ch : ch - 2;
+        const float val = (ch == 2 || ch == 3 || k >= kE) ? 0.f : v[k];
+        mo[ch * plane] = fmaxf(last[u], val);
       }
     }
-    return;
-  }
-  for (int u = 0; u < kV; ++u) {
-    const FusePos pu = u == 0 ? p0 : fuse_pos(x0 + u, y, n, tx, ty);
-    fuse_cell_near(n, c.vr, c.channels, xf[e * 4], xf[e * 4 + 1], pu.fx2, pu.fy2, ego_e, ml + u, ml_plane, mo + u);
   }
 }
 
@@ -1032,7 +988,6 @@ void SemMap::init(const SemMapCfg& cfg, int envs) {
     const double hy = std::max(std::fabs(wy1 - ctr), std::fabs(wy1 + c.vr - 1 - ctr));
     const double r = (std::sqrt(hx * hx + hy * hy) + std::sqrt(2.0)) * n / (n - 1) + std::sqrt(2.0) + 2.0;
     c.fuse_r2 = static_cast<float>(r * r);
-    c.fuse_r2_group = static_cast<float>((r + 4.0) * (r + 4.0));   // four-cell groups: the first cell's distance decides
   }
   PN_REQUIRE(c.nf <= kMaxFeat, "semmap: too many semantic categories");
   PN_REQUIRE(c.nz <= 126 && c.h * c.w <= 32767, "semmap: geometry out of range");
@@ -1097,12 +1052,10 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
     launch_pdl(k_columns_big<kMaxFeat>, dim3(g_big, E), 128, 32768 * 4, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
   }
   launch_pdl(k_pose, (E + 63) / 64, 64, 0, s, c, E, pose_delta, poses_inout, xf);
-  const bool vec4 = c.map_cells % 4 == 0 && ml_env % 4 == 0 && ml_plane % 4 == 0 && ml_row % 4 == 0 &&
-                    reinterpret_cast<uintptr_t>(maps_last) % 16 == 0 && reinterpret_cast<uintptr_t>(map_out) % 16 == 0;
-  if (vec4)
-    launch_pdl(k_fuse<4>, dim3((c.map_cells / 4 + 127) / 128, c.map_cells, E), 128, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
+  if (c.ego_channels <= 12)
+    launch_pdl(k_fuse<12>, dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
   else
-    launch_pdl(k_fuse<1>, dim3((c.map_cells + 127) / 128, c.map_cells, E), 128, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
+    launch_pdl(k_fuse<kMaxFeat + 1>, dim3((c.map_cells + 255) / 256, c.map_cells, E), 256, 0, s, c, xf, ego, maps_last, ml_env, ml_plane, ml_row, map_out, fp_out);
   PN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -18,8 +18,7 @@ struct SemMapCfg {
   float xc, zc, f;     // camera matrix (depth_utils.py:27-34)
   float agent_height, shift_x, res, half_vr, vr_f, z_mid, nz_f;
   float map_thr, exp_thr, cat_thr;
-  float fuse_r2 = 0.f;        // set by SemMap::init: squared reach of the ego window in k_fuse's sampling space
-  float fuse_r2_group = 0.f;  // the same with the width of a four-cell group added
+  float fuse_r2 = 0.f;  // set by SemMap::init: squared reach of the ego window in k_fuse's sampling space
 };
 
 struct SemMap {

@@ -511,7 +511,8 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
       // Two CTAs per SM: where the epilogue (one warp per SM sub-partition, issue-bound) outlasts the main loop, a second
       // resident CTA doubles the epilogue warps and runs its main loop under the first one's epilogue.  Each CTA gets half
       // the shared memory (and its 2 x BN accumulator columns must fit tensor memory twice: BN <= 128).
-      PN_REQUIRE(!pair && splits == 1 && bn <= 128 && p.epi_tma, name + ": two CTAs per SM need a single-CTA tile of at most 128 columns");
+      // With CTA pairs (round 2, last experiment): two clusters of two CTAs per SM pair - each CTA still owns 2 x BN columns.
+      PN_REQUIRE(splits == 1 && bn <= 128 && p.epi_tma, name + ": two CTAs per SM need an unsplit tile of at most 128 columns");
       const size_t half = 113 * 1024;
       PN_REQUIRE(fixed_bytes + 2 * stage_bytes <= half, name + ": two CTAs per SM do not fit shared memory");
       stages = std::min(stages, static_cast<int>((half - fixed_bytes) / stage_bytes));
@@ -527,7 +528,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
     const size_t smem = fixed_bytes + stages * stage_bytes;
     const long long tiles = static_cast<long long>(p.m_tiles) * n_tiles * splits;
-    const int grid = pair ? 2 * static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, net.num_sms / 2))
+    const int grid = pair ? 2 * static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, ((opt & 1) ? 2 : 1) * (net.num_sms / 2)))
                           : static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, ((opt & 1) ? 2 : 1) * net.num_sms));
 
     Variant v;

@@ -114,13 +114,18 @@ __global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int H
   for (int j = 0; j < 32; ++j) v[j] = 0.f;
   if (y < Hn) {
     const uint8_t* row = resized_u8 + (static_cast<size_t>(b) * Hn + y) * Wn * 3;
+    // PIXEL_STD is (1, 1, 1) in the reference's yaml: x / 1 == x exactly, and 21 IEEE divisions per thread are most of this
+    // kernel's instructions
+    const bool unit_std = std_bgr.x == 1.f && std_bgr.y == 1.f && std_bgr.z == 1.f;
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       const int x = 2 * xo - 3 + s;
       if (x >= 0 && x < Wn) {
-        v[s * 3] = (static_cast<float>(row[x * 3]) - mean_bgr.x) / std_bgr.x;
-        v[s * 3 + 1] = (static_cast<float>(row[x * 3 + 1]) - mean_bgr.y) / std_bgr.y;
-        v[s * 3 + 2] = (static_cast<float>(row[x * 3 + 2]) - mean_bgr.z) / std_bgr.z;
+        const float d0 = static_cast<float>(row[x * 3]) - mean_bgr.x, d1 = static_cast<float>(row[x * 3 + 1]) - mean_bgr.y;
+        const float d2 = static_cast<float>(row[x * 3 + 2]) - mean_bgr.z;
+        v[s * 3] = unit_std ? d0 : d0 / std_bgr.x;
+        v[s * 3 + 1] = unit_std ? d1 : d1 / std_bgr.y;
+        v[s * 3 + 2] = unit_std ? d2 : d2 / std_bgr.z;
       }
     }
     if (sizeof(T) == 4) {

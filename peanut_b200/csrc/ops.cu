@@ -115,10 +115,11 @@ struct PpmMeta {
 __device__ __forceinline__ int bin_start(int i, int L, int s) { return (i * L) / s; }
 __device__ __forceinline__ int bin_end(int i, int L, int s) { return ((i + 1) * L + s - 1) / s; }
 
+// One thread per (image row, 8 channels): 16 / 32-byte loads, the bin's cells summed in x order (fp32).
 template <typename T>
 __global__ void ppm_rows_kernel(const T* in, long long ldi, float* rowpart, int B, int H, int W, int C, PpmMeta meta) {
   pdl_grid_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const int row = blockIdx.y;  // b*H + y
   if (c >= C) return;
   const T* p = in + static_cast<long long>(row) * W * ldi + c;
@@ -127,10 +128,30 @@ __global__ void ppm_rows_kernel(const T* in, long long ldi, float* rowpart, int 
   for (int si = 0; si < meta.nscales; ++si) {
     const int s = meta.scale[si];
     for (int xb = 0; xb < s; ++xb) {
-      float acc = 0.f;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       const int x1 = bin_end(xb, W, s);
-      for (int x = bin_start(xb, W, s); x < x1; ++x) acc += to_float(p[static_cast<long long>(x) * ldi]);
-      o[static_cast<long long>(meta.bin_off[si] + xb) * C] = acc;
+      int x = bin_start(xb, W, s);
+      for (; x + 4 <= x1; x += 4) {   // four cells in flight; the adds stay in x order
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(p + static_cast<long long>(x + u) * ldi, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+        }
+      }
+      for (; x < x1; ++x) {
+        float v[8];
+        load8(p + static_cast<long long>(x) * ldi, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+      float* dst = o + static_cast<long long>(meta.bin_off[si] + xb) * C;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
   }
 }
@@ -153,6 +174,7 @@ __global__ void ppm_bins_kernel(const float* rowpart, T* out, int H, int W, int 
 
 void add_ppm_pool(Net& net, const Tensor& in, const std::vector<int>& scales, const std::vector<Tensor>& outs) {
   PN_REQUIRE(scales.size() <= 4 && scales.size() == outs.size(), "ppm: at most 4 scales");
+  PN_REQUIRE(in.C % 8 == 0 && in.ld % 8 == 0, "ppm: channel count must be a multiple of 8");
   PpmMeta meta{};
   meta.nscales = static_cast<int>(scales.size());
   int nb = 0;
@@ -168,7 +190,7 @@ void add_ppm_pool(Net& net, const Tensor& in, const std::vector<int>& scales, co
   std::vector<Tensor> o = outs;
   net.add("ppm_pool", [=](cudaStream_t s) {
     const int threads = 128;
-    dim3 g1((i.C + threads - 1) / threads, i.B * i.H);
+    dim3 g1((i.C / 8 + threads - 1) / threads, i.B * i.H);
     if (i.dt == kBF16)
       launch_pdl(ppm_rows_kernel<__nv_bfloat16>, g1, threads, 0, s, static_cast<const __nv_bfloat16*>(i.ptr), i.ld, rowpart, i.B, i.H, i.W, i.C, meta);
     else

@@ -181,7 +181,9 @@ def synth_obs(seed, args=None, scene="room", sem_density=0.1):
     """Mapper observation [14,120,160] as the reference preprocessing produces it
     (agent_helper.py:183-217): depth in cm = 50 + d*450 with invalid pixels at 45050, semantic channels
     are small non-negative overlap counts.  Scenes: 'room' (floor + walls), 'stairs' (low steps that
-    trigger the stair mask), 'wall' (flat wall at 0.6 m: worst-case points per voxel column), 'empty'."""
+    trigger the stair mask), 'wall' (flat wall at 0.6 m: worst-case points per voxel column), 'wall_near' (flat wall in front of
+    the minimum depth: every pixel clips to exactly 50 cm, more than 2 048 points per voxel column and coordinates that sit
+    exactly on a cell boundary), 'empty'."""
     a = args or default_args()
     rng = np.random.default_rng(seed)
     H, W = a.frame_height, a.frame_width
@@ -192,9 +194,9 @@ def synth_obs(seed, args=None, scene="room", sem_density=0.1):
     if scene == "empty":
         d_cm = np.full((H, W), 45050.0)
     else:
-        floor_z = {"room": -88.0, "stairs": -60.0, "wall": -88.0}[scene]
+        floor_z = {"room": -88.0, "stairs": -60.0, "wall": -88.0, "wall_near": -88.0}[scene]
         wall = {"room": 250.0 + 120.0 * np.sin(u / W * np.pi * rng.uniform(0.5, 2.0)) + rng.uniform(0, 100),
-                "stairs": np.full((1, W), 400.0), "wall": np.full((1, W), 60.0)}[scene]
+                "stairs": np.full((1, W), 400.0), "wall": np.full((1, W), 60.0), "wall_near": np.full((1, W), 40.0)}[scene]
         with np.errstate(divide="ignore", invalid="ignore"):
             d_floor = np.where(elev < 0, floor_z / elev, np.inf)
         d_cm = np.minimum(d_floor, wall)

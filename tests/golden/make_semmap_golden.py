@@ -33,6 +33,11 @@ CASES = [  # (name, seed, scene, sem_density, argparse overrides)
     # (a float32 round-trip of the height gives 25), so this case pins the obstacle height band's upper edge
     ("room_cam089", 5, "room", 0.2, {"camera_height": 0.89}),
     ("room_hfov90", 6, "room", 0.2, {"hfov": 90.0, "camera_height": 0.84}),
+    # every pixel at the minimum depth: voxel columns with more than 2 048 entries (the key-only column kernel), coordinates
+    # exactly on cell boundaries (zero-weight corners)
+    ("wall_near", 7, "wall_near", 0.2, {}),
+    # 15 semantic categories: 16 features per voxel (the 32-lane voxel slots), 17 ego channels, mapping.py:106-108's <= 16 branch
+    ("room_cat15", 8, "room", 0.2, {"num_sem_categories": 15}),
 ]
 
 

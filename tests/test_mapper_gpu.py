@@ -43,7 +43,7 @@ def test_reference_golden_single_env(module1, path):
     fp, mp, pose_pred, cur = module1(torch.from_numpy(obs)[None].cuda(), torch.from_numpy(delta).cuda(),
                                      torch.from_numpy(maps).cuda(), p, None)
     torch.cuda.synchronize()
-    assert fp.shape == (1, 100, 100) and mp.shape == (14, 480, 480)
+    assert fp.shape == (1, 100, 100) and mp.shape == (4 + args.num_sem_categories, 480, 480)
     assert pose_pred is p and cur is p  # aliasing contract
     check_against_golden(z, fp[0].cpu().numpy(), mp.cpu().numpy(), cur.cpu().numpy(), map_tol=MAP_TOL, pose_tol=POSE_TOL)
 

@@ -142,6 +142,43 @@ def test_roi_align_and_box_head(eng_tf32, otaps, weights):
     assert (out[:, 10:46] - dlt_ref).abs().max().item() <= 5e-3 * dlt_ref.abs().max().item()
 
 
+def test_roi_align_extreme_boxes(eng_tf32, otaps):
+    """ROIAlign on boxes the RPN never emits, to walk every path of k_roi_align: footprints 1..8 feature columns wide (the
+    compile-time instances), wider than 8 (predicated batches), wider than 32 cells per bin (per-sample path), empty and
+    out-of-image boxes.  Reference: torchvision's roi_align through the oracle's level assignment."""
+    e = eng_tf32
+    e.run_stages("preprocess", "rpn_proposals")
+    _inject_rpn_heads(e, otaps)
+    e.run_stages("rpn_proposals", "box_head")
+    n = otaps["proposals"].shape[0]
+    pyr = {k: e.read_tap(k, tuple(otaps["pyr"][k].shape)).cpu() for k in ("p2", "p3", "p4", "p5")}
+    boxes = e.read_tap("prop_boxes", (1000, 4)).cpu()
+    extreme = torch.tensor([
+        [10.2, 10.7, 10.9, 11.1],            # a fraction of a cell
+        [50.0, 50.0, 50.0, 50.0],            # empty: no samples, zeros
+        [0.0, 0.0, 533.0, 400.0],            # the whole image
+        [-50.0, -30.0, 600.0, 450.0],        # beyond every border
+        [0.0, 100.0, 533.0, 108.0],          # 19 cells per bin wide on p2
+        [100.0, 0.0, 108.0, 400.0],          # ... and tall
+        [-2000.0, 100.0, 2500.0, 104.0],     # 80 cells per bin on p3: per-sample path, most samples outside the map
+        [100.0, -1500.0, 104.0, 1500.0],
+        [30.0, 40.0, 44.0, 230.0],           # one column wide, 27 rows per bin
+        [5.0, 5.0, 228.0, 229.0], [5.0, 5.0, 120.0, 117.0], [300.0, 200.0, 532.9, 399.9],
+    ])
+    k = extreme.shape[0]
+    assert n > k
+    boxes[:k] = extreme
+    e.write_tap("prop_boxes", boxes)
+    e.run_stages("box_head", "detections")
+    ref_pool = O.roi_pool(pyr, boxes[:n], 7)
+    got_pool = e.read_tap("box_pooled", (1000, 256, 7, 7)).cpu()[:n]
+    scale = ref_pool.abs().max().item()
+    assert torch.isfinite(got_pool).all()
+    assert (got_pool[:k] - ref_pool[:k]).abs().max().item() <= 6e-4 * scale
+    assert (got_pool - ref_pool).abs().max().item() <= 6e-4 * scale
+    assert got_pool[1].abs().max().item() == 0.0
+
+
 def _inject_box_head(e, otaps):
     n = otaps["proposals"].shape[0]
     pb = torch.zeros((1000, 4))

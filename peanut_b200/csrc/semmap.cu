@@ -418,8 +418,8 @@ struct ColumnStage {
   float w0[kCap], w1[kCap];
   float feat[kCap * kFs];
   uint32_t zbits[4];        // z-fields (0 .. nz) that occur in the column's keys
-  int nv;
-  int vcnt[4];              // touched voxels per 32-voxel chunk
+  int vcnt[4];              // touched voxels per 32-voxel chunk (16-byte aligned: read with one vector load)
+  int nv, pad_[3];          // (kept out of that vector: thread 0 writes nv while other warps still read vcnt)
   uint8_t vox[128];         // touched voxels, any order (the height projections are sums of integers: exact, order-free)
   float red_all[32], red_agent[32];
 };

@@ -185,6 +185,17 @@ def time_cpu(step, warmup, steps, budget_s):
     return times
 
 
+MODE_DESC = {"dependent": "dependent (reference order: Mask-RCNN -> mapper -> stamp + window -> map completion)",
+             "overlapped": "overlapped (map completion on the caller's stale map, side stream)"}
+
+
+def shared_config(desc, envs, map_shape, mode):
+    """The workload description both arms print verbatim (the driver compares the two lines' `config`): what is computed, not how
+    it was timed - run bookkeeping goes into `run`."""
+    return {"workload": desc, "envs_per_gpu": envs, "frame": [480, 640], "map_shape": list(map_shape), "mode": MODE_DESC[mode],
+            "l2": "GPU arm: 256 MiB flush write between timed iterations", "timing": "GPU arm: CUDA events per step, max over ranks"}
+
+
 def resolve_workload(a, world):
     return a.workload if a.workload != "auto" else "cfg2"
 
@@ -210,9 +221,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "envs_per_gpu": E, "frame": [480, 640], "map_shape": list(map_shape),
-                       "mode": "dependent", "sample_frames_per_step": 1,
-                       "note": "CPU arm: rank 0 only, one frame per step (bounded sample of the same workload)"},
+            "config": shared_config(wl["desc"], E, map_shape, a.mode),
+            "run": {"sample_frames_per_step": 1,
+                    "note": "CPU arm: rank 0 only, one frame per step (bounded sample of the same workload)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -467,13 +478,9 @@ def run_ours(a):
     line = {"metric": METRIC, "value": frames / (m["dev_ms"] / 1000.0), "unit": "frames/s", "n_gpus": world, "steps": steps,
             "warmup": max(a.warmup, 3), "ms_per_step": m["dev_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": m["precision"], "data": "synthetic",
-            "config": {"workload": m["desc"], "envs_per_gpu": m["E"], "frame": [480, 640], "map_shape": list(map_shape),
-                       "mode": a.mode + (" (reference order: Mask-RCNN -> mapper -> stamp + window -> map completion)"
-                                         if a.mode == "dependent" else " (map completion on the caller's stale map, side stream)"),
-                       "micro_batches": m["micro_batches"],
-                       "l2": "256 MiB flush write between timed iterations", "timing": "CUDA events per step, max over ranks",
-                       "wall_ms_per_step_incl_flush": m["wall_ms"],
-                       "gather": m["gather_impl"], "gather_in_step": world > 1 and a.gather != "none", "gather_ms": m["gather_ms"]},
+            "config": shared_config(m["desc"], m["E"], map_shape, a.mode),
+            "run": {"micro_batches": m["micro_batches"], "wall_ms_per_step_incl_flush": m["wall_ms"],
+                    "gather": m["gather_impl"], "gather_in_step": world > 1 and a.gather != "none", "gather_ms": m["gather_ms"]},
             "e2e": {"value": frames / (m["e2e_ms"] / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"],
                     "d2h_bytes_per_step": m["d2h"], "ms_per_step": m["e2e_ms"],
                     "note": "pinned host rgb/depth/pose-delta/partial-map in; predicted map, pose, egocentric obstacle map out; "

@@ -9,5 +9,5 @@ for N in 8 4; do
   grep "^{" gpurun_out/r02_bench_n${N}_peer.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('N=%d value %.1f fps %.2f ms e2e %.1f gather_ms %s cfg3 %.1f fps (%.2f ms, gather %s) clocks %s' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['gather_ms'], d['cfg3']['value'], d['cfg3']['ms_per_step'], d['cfg3']['gather_ms'], d['clocks']))"
+print('N=%d value %.1f fps %.2f ms e2e %.1f gather_ms %s cfg3 %.1f fps (%.2f ms, gather %s) clocks %s' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['run']['gather_ms'], d['cfg3']['value'], d['cfg3']['ms_per_step'], d['cfg3']['gather_ms'], d['clocks']))"
 done

@@ -628,9 +628,9 @@ __global__ void __launch_bounds__(128) k_columns_warp(SemMapCfg c, const float* 
   }
 }
 
-// k_columns_cta: columns with more entries (walls and far floor: 7 % of the columns, two thirds of the entries), one CTA of
-// four warps = eight voxel slots per column, persistent over the mid list (kTinyCap < n <= kMidCap = 512, several CTAs per SM)
-// or the large list (kMidCap < n <= kLargeCap = 2048, one CTA per SM).  Bitonic sort of the keys in shared memory, then every
+// k_columns_cta: columns with more entries (walls and far floor: 7 % of the columns, two thirds of the entries), one CTA per
+// column, persistent over the mid list (kTinyCap < n <= kMidCap = 512: eight warps = sixteen voxel slots, several CTAs per SM)
+// or the large list (kMidCap < n <= kLargeCap = 2048: sixteen warps, one CTA per SM).  Bitonic sort of the keys in shared memory, then every
 // thread stages the entries at its sorted positions: a far floor cell collects hundreds of points in ONE voxel, whose
 // serial chain of additions then runs out of shared memory (a few cycles per entry) instead of global memory.
 template <int kL, int kFs, int kCap, int kList, int kWarps>
@@ -1009,9 +1009,9 @@ void SemMap::init(const SemMapCfg& cfg, int envs) {
   stair_flag = static_cast<int*>(arena.alloc(E * sizeof(int)));
   PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_big<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
   PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_big<kMaxFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<16, 12, kMidCap, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<16, 12, kMidCap, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(ColumnStage<kMidCap, 12>))));
-  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<32, kMaxFeat, kMidCap, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<32, kMaxFeat, kMidCap, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(ColumnStage<kMidCap, kMaxFeat>))));
   PN_CUDA_CHECK(cudaFuncSetAttribute(k_columns_cta<16, 12, kLargeCap, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(ColumnStage<kLargeCap, 12>))));
@@ -1038,14 +1038,14 @@ void SemMap::forward(const float* obs, const float* pose_delta, const float* map
   const int g_warp = std::min((ncols + 3) / 4, num_sms * 16), g_cta = std::min(ncols, num_sms * 6), g_big = std::min(ncols, num_sms);
   if (c.nf <= 12) {
     launch_pdl(k_columns_warp<16, 12>, dim3(g_warp, E), 128, 0, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
-    launch_pdl(k_columns_cta<16, 12, kMidCap, 2, 4>, dim3(g_cta, E), 128, sizeof(ColumnStage<kMidCap, 12>), s, c, obs, coords, col_start,
+    launch_pdl(k_columns_cta<16, 12, kMidCap, 2, 8>, dim3(g_cta, E), 256, sizeof(ColumnStage<kMidCap, 12>), s, c, obs, coords, col_start,
                entries, col_list, list_n, ego);
     launch_pdl(k_columns_cta<16, 12, kLargeCap, 3, 16>, dim3(g_big, E), 512, sizeof(ColumnStage<kLargeCap, 12>), s, c, obs, coords,
                col_start, entries, col_list, list_n, ego);
     launch_pdl(k_columns_big<12>, dim3(g_big, E), 128, 32768 * 4, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
   } else {
     launch_pdl(k_columns_warp<32, kMaxFeat>, dim3(g_warp, E), 128, 0, s, c, obs, coords, col_start, entries, col_list, list_n, ego);
-    launch_pdl(k_columns_cta<32, kMaxFeat, kMidCap, 2, 4>, dim3(g_cta, E), 128, sizeof(ColumnStage<kMidCap, kMaxFeat>), s, c, obs, coords,
+    launch_pdl(k_columns_cta<32, kMaxFeat, kMidCap, 2, 8>, dim3(g_cta, E), 256, sizeof(ColumnStage<kMidCap, kMaxFeat>), s, c, obs, coords,
                col_start, entries, col_list, list_n, ego);
     launch_pdl(k_columns_cta<32, kMaxFeat, kLargeCap, 3, 16>, dim3(g_big, E), 512, sizeof(ColumnStage<kLargeCap, kMaxFeat>), s, c, obs,
                coords, col_start, entries, col_list, list_n, ego);

@@ -84,7 +84,10 @@ void build_maskrcnn(MaskRcnn& m, const WeightStore& w, const MrcnnCfg& cfg, DTyp
   // ---- input: PIL-exact resize, BGR, mean subtraction, zero padding (yaml:26-30, 82-89)
   net.stage("preprocess");
   m.resized_u8 = static_cast<uint8_t*>(A.alloc(static_cast<size_t>(B) * m.Hn * m.Wn * 3));
-  m.input = A.tensor(B, m.Hp, m.Wp / 2, 32, dt);
+  PN_REQUIRE(m.Wp % 4 == 0, "maskrcnn: padded width must be a multiple of 4");
+  PN_REQUIRE(m.Hp % 2 == 0, "maskrcnn: padded height must be even");
+  // one packed vector per PAIR of stem output pixels and per PAIR of image rows (rows 2q - 1, 2q; see k_pack_stem)
+  m.input = A.tensor(B, m.Hp / 2 + 1, m.Wp / 4, 64, dt);
   const float mean_bgr[3] = {103.53f, 116.28f, 123.675f}, std_bgr[3] = {1.f, 1.f, 1.f};
   add_resize_pack_stem(net, &m.slots->rgb, B, cfg.H, cfg.W, m.Hn, m.Wn, m.input, m.resized_u8, mean_bgr, std_bgr);
   net.taps["stem_in"] = m.input;
@@ -94,20 +97,31 @@ void build_maskrcnn(MaskRcnn& m, const WeightStore& w, const MrcnnCfg& cfg, DTyp
   const std::string bu = "backbone.bottom_up.";
   Tensor x;
   {
-    // 7x7 stride-2 stem as a 7x1 convolution over the tap-packed input (see k_pack_stem): W'[co][r][s*3+c] = W[co][c][r][s]
+    // 7x7 stride-2 stem as a 4x1 convolution over the tap-packed input (see k_pack_stem), two output pixels per GEMM row and
+    // two image rows per input pixel:
+    //   W'[p*64 + co][r][h*32 + t*3 + c] = W[co][c][2r + h][t - 2p]  for 2r + h < 7 and 0 <= t - 2p < 7
+    // (p = parity of the output pixel, t = 0..8 packed column, r = 0..3 row-pair tap, h = row inside the pair)
     const HostArray& wt = conv_weight(w, bu + "stem.conv1.weight", 64, 3, 7);
-    std::vector<float> wp(static_cast<size_t>(64) * 32 * 7, 0.f);
-    for (int co = 0; co < 64; ++co)
-      for (int c = 0; c < 3; ++c)
-        for (int r = 0; r < 7; ++r)
-          for (int s = 0; s < 7; ++s) wp[(static_cast<size_t>(co) * 32 + (s * 3 + c)) * 7 + r] = wt.data[((static_cast<size_t>(co) * 3 + c) * 7 + r) * 7 + s];
+    std::vector<float> wp(static_cast<size_t>(128) * 64 * 4, 0.f);
+    for (int par = 0; par < 2; ++par)
+      for (int co = 0; co < 64; ++co)
+        for (int c = 0; c < 3; ++c)
+          for (int rr = 0; rr < 7; ++rr)
+            for (int s = 0; s < 7; ++s)
+              wp[(static_cast<size_t>(par * 64 + co) * 64 + ((rr & 1) * 32 + (s + 2 * par) * 3 + c)) * 4 + (rr >> 1)] =
+                  wt.data[((static_cast<size_t>(co) * 3 + c) * 7 + rr) * 7 + s];
     std::vector<float> scale, bias;
     fold_bn(w, bu + "stem.conv1.norm", 64, scale, bias, 1e-5f);
+    scale.insert(scale.end(), scale.begin(), scale.begin() + 64);   // both pixel parities
+    bias.insert(bias.end(), bias.begin(), bias.begin() + 64);
     ConvSpec s7;
-    s7.Cin = 32, s7.Cout = 64, s7.R = 7, s7.S = 1, s7.stride = 2, s7.stride_w = 1, s7.dil = 1, s7.pad = 3, s7.pad_w = 0, s7.relu = true;
+    s7.Cin = 64, s7.Cout = 128, s7.R = 4, s7.S = 1, s7.stride = 1, s7.stride_w = 1, s7.dil = 1, s7.pad = 1, s7.pad_w = 0, s7.relu = true;
     x = A.tensor(B, conv_out(m.Hp, 7, 2, 1, 3), m.Wp / 2, 64, dt);
-    add_conv(net, bu + "stem.conv1", m.input, x, wp.data(), scale.data(), bias.data(), s7);
-    // the packed channels 21..31 are zero padding: report the 7x7x3 FLOPs, not the packed K
+    Tensor xpair = x;   // the same memory seen as [B, Ho, Wo / 2, 128]: NHWC of a pixel pair = (parity, channel)
+    xpair.W = x.W / 2, xpair.C = 128, xpair.ld = 2 * x.ld;
+    PN_REQUIRE(x.ld == 64, "maskrcnn: the stem output must be dense");
+    add_conv(net, bu + "stem.conv1", m.input, xpair, wp.data(), scale.data(), bias.data(), s7);
+    // packed channels 27..31, two of the nine taps per pixel and the eighth row are padding: report the 7x7x3 FLOPs, not the packed K
     net.op_flops.back() = 2.0 * static_cast<double>(x.pixels()) * 64 * 147;
   }
   {

@@ -94,54 +94,66 @@ __global__ void k_resize_u8(const uint8_t* const* rgb_slot, int B, int H, int W,
   o[0] = static_cast<uint8_t>(clip8(acc[2])), o[1] = static_cast<uint8_t>(clip8(acc[1])), o[2] = static_cast<uint8_t>(clip8(acc[0]));
 }
 
-// Normalise + zero-pad + pack the 7 horizontal taps of the stride-2 7x7 stem convolution into channels:
-//   out[b, y, xo, s*3 + c] = (bgr[b, y, 2*xo - 3 + s, c] - mean[c]) / std[c]   (0 outside the resized image),
-// channels 21..31 zero.  The stem then runs as a 7x1 convolution with 32 input channels (K = 224 instead of the
-// 784 a 16-channel-padded 7x7 im2col would need) at stride (2, 1), padding (3, 0).
+// Normalise + zero-pad + pack the horizontal taps of the stride-2 7x7 stem convolution into channels, TWO output pixels per
+// packed vector: output pixels xo = 2j and 2j + 1 read input columns 4j - 3 .. 4j + 3 and 4j - 1 .. 4j + 5, nine columns x
+// three channels = 27 values between them:
+//   v[b, y, j, t*3 + c] = (bgr[b, y, 4*j - 3 + t, c] - mean[c]) / std[c],  t = 0..8   (0 outside the resized image),
+// channels 27..31 zero - and TWO image rows per packed pixel: out[b, q, j, h*32 + k] = v[b, 2q - 1 + h, j, k] (q = 0 .. Hp / 2;
+// row -1 and row Hp stay the zeros of the allocation).  Output row p of the stride-2 stem reads image rows 2p - 3 .. 2p + 3 =
+// row pairs p - 1 .. p + 2 (the second half of the last pair gets zero weights), so the stem runs as a 4x1 convolution with 64
+// input channels and 128 outputs (pixel parity x 64 channels, which is exactly the NHWC order of the two pixels) at stride 1,
+// padding (1, 0): four K blocks of 128 bytes (full-width swizzle, four MMA K steps each) instead of seven of 64 bytes, half the
+// GEMM rows and half the packed bytes of round 2's first one-pixel packing (891 MB written and read back per 32 frames),
+// N = 128 instead of 64 per MMA.
 template <typename T>
-__global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int Hn, int Wn, int Hp, int Wo, float3 mean_bgr,
+__global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int Hn, int Wn, int Hp, int Wq, float3 mean_bgr,
                             float3 std_bgr, T* __restrict__ out) {
   pdl_grid_sync();
+  // one thread per stored pixel (row pair q, pixel pair j): 2 x 27 values, 128 contiguous bytes (bf16) per thread
+  const int Hq = Hp / 2 + 1;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Hp * Wo;
+  const long long total = static_cast<long long>(B) * Hq * Wq;
   if (idx >= total) return;
-  const int xo = static_cast<int>(idx % Wo);
-  const long long t = idx / Wo;
-  const int y = static_cast<int>(t % Hp);
-  const int b = static_cast<int>(t / Hp);
-  float v[32];
+  const int j = static_cast<int>(idx % Wq);
+  const long long t = idx / Wq;
+  const int q = static_cast<int>(t % Hq);
+  const int b = static_cast<int>(t / Hq);
+  // PIXEL_STD is (1, 1, 1) in the reference's yaml: x / 1 == x exactly
+  const bool unit_std = std_bgr.x == 1.f && std_bgr.y == 1.f && std_bgr.z == 1.f;
+  T* o = out + idx * 64;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = 0.f;
-  if (y < Hn) {
-    const uint8_t* row = resized_u8 + (static_cast<size_t>(b) * Hn + y) * Wn * 3;
-    // PIXEL_STD is (1, 1, 1) in the reference's yaml: x / 1 == x exactly, and 21 IEEE divisions per thread are most of this
-    // kernel's instructions
-    const bool unit_std = std_bgr.x == 1.f && std_bgr.y == 1.f && std_bgr.z == 1.f;
+  for (int h = 0; h < 2; ++h) {
+    const int y = 2 * q - 1 + h;
+    float v[32];
 #pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      const int x = 2 * xo - 3 + s;
-      if (x >= 0 && x < Wn) {
-        const float d0 = static_cast<float>(row[x * 3]) - mean_bgr.x, d1 = static_cast<float>(row[x * 3 + 1]) - mean_bgr.y;
-        const float d2 = static_cast<float>(row[x * 3 + 2]) - mean_bgr.z;
-        v[s * 3] = unit_std ? d0 : d0 / std_bgr.x;
-        v[s * 3 + 1] = unit_std ? d1 : d1 / std_bgr.y;
-        v[s * 3 + 2] = unit_std ? d2 : d2 / std_bgr.z;
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+    if (y >= 0 && y < Hn) {
+      const uint8_t* row = resized_u8 + (static_cast<size_t>(b) * Hn + y) * Wn * 3;
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        const int x = 4 * j - 3 + s;
+        if (x >= 0 && x < Wn) {
+          const float d0 = static_cast<float>(row[x * 3]) - mean_bgr.x, d1 = static_cast<float>(row[x * 3 + 1]) - mean_bgr.y;
+          const float d2 = static_cast<float>(row[x * 3 + 2]) - mean_bgr.z;
+          v[s * 3] = unit_std ? d0 : d0 / std_bgr.x;
+          v[s * 3 + 1] = unit_std ? d1 : d1 / std_bgr.y;
+          v[s * 3 + 2] = unit_std ? d2 : d2 / std_bgr.z;
+        }
+      }
+      if (sizeof(T) == 4) {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          uint32_t qq;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(qq) : "f"(v[k]));
+          v[k] = __uint_as_float(qq);
+        }
       }
     }
-    if (sizeof(T) == 4) {
 #pragma unroll
-      for (int j = 0; j < 21; ++j) {
-        uint32_t q;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v[j]));
-        v[j] = __uint_as_float(q);
-      }
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      const float w[8] = {v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3], v[c0 + 4], v[c0 + 5], v[c0 + 6], v[c0 + 7]};
+      store8(o + h * 32 + c0, w);
     }
-  }
-  T* o = out + idx * 32;
-#pragma unroll
-  for (int c0 = 0; c0 < 32; c0 += 8) {
-    const float w[8] = {v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3], v[c0 + 4], v[c0 + 5], v[c0 + 6], v[c0 + 7]};
-    store8(o + c0, w);
   }
 }
 
@@ -197,8 +209,9 @@ __global__ void k_make_obs(const float* __restrict__ depth_all, const uint8_t* _
 
 void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H, int W, int Hn, int Wn, const Tensor& out,
                           uint8_t* resized_u8, const float mean_bgr[3], const float std_bgr[3]) {
-  PN_REQUIRE(out.ld == 32 && out.C == 32, "pack_stem: output must be a dense 32-channel tensor");
-  PN_REQUIRE(out.W * 2 >= Wn && out.H >= Hn, "pack_stem: output too small");
+  PN_REQUIRE(out.ld == 64 && out.C == 64, "pack_stem: output must be a dense 64-channel tensor (two image rows per pixel)");
+  const int Hp = 2 * (out.H - 1);   // padded image height: out holds Hp / 2 + 1 row pairs
+  PN_REQUIRE(out.W * 4 >= Wn && Hp >= Hn, "pack_stem: output too small");
   std::vector<int> hb, hk, vb, vk;
   int hks = 0, vks = 0;
   pil_bilinear_coeffs(W, Wn, hb, hk, hks);
@@ -215,14 +228,14 @@ void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H
   net.add("resize_u8", [=](cudaStream_t s) {
     launch_pdl(k_resize_u8, blocks1, threads, 0, s, rgb_slot, B, H, W, Hn, Wn, d_hb, d_hk, hks, d_vb, d_vk, vks, resized_u8);
   });
-  const long long total2 = out.pixels();
+  const long long total2 = out.pixels();   // one thread per stored pixel (row pair, pixel pair)
   const int blocks2 = static_cast<int>((total2 + threads - 1) / threads);
   Tensor o = out;
   net.add("pack_stem", [=](cudaStream_t s) {
     if (o.dt == kBF16)
-      launch_pdl(k_pack_stem<__nv_bfloat16>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr));
+      launch_pdl(k_pack_stem<__nv_bfloat16>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, Hp, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr));
     else
-      launch_pdl(k_pack_stem<float>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, o.H, o.W, mean, sd, static_cast<float*>(o.ptr));
+      launch_pdl(k_pack_stem<float>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, Hp, o.W, mean, sd, static_cast<float*>(o.ptr));
   });
   net.launches_per_forward += 2;
 }

@@ -71,15 +71,20 @@ def test_resize_is_pil_exact_and_input_normalised(eng_tf32, frame, ocfg, otaps):
     ref = np.asarray(Image.fromarray(np.ascontiguousarray(frame[:, :, ::-1])).resize((wn, hn), Image.BILINEAR))
     got = e.read_tap("resized_u8", (1, hn, wn, 3), torch.uint8).cpu().numpy()[0]
     assert np.array_equal(got, ref), f"{(got != ref).sum()} resized pixels differ from PIL"
-    # the stem input packs the 7 horizontal taps of the stride-2 7x7 stem into channels:
-    #   t[b, s*3 + c, y, xo] = input[b, c, y, 2*xo - 3 + s]  (0 outside), channels 21..31 zero
-    t = e.read_tap("stem_in", (1, 32, hp, wp // 2)).cpu()
-    ref = torch.nn.functional.pad(otaps["input"], (3, 3))            # [1, 3, hp, wp + 6]
-    for s in range(7):
-        want = ref[:, :, :, s:s + wp:2]                               # x = 2*xo - 3 + s  <=>  padded index 2*xo + s
+    # the stem input packs the horizontal taps of the stride-2 7x7 stem into channels, two output pixels (xo = 2j, 2j + 1) per
+    # vector:  v[b, s*3 + c, y, j] = input[b, c, y, 4*j - 3 + s], s = 0..8  (0 outside), channels 27..31 zero - and two image
+    # rows per stored pixel:  stored[b, h*32 + k, q, j] = v[b, k, 2q - 1 + h, j]  (row -1 and row hp are zeros)
+    st = e.read_tap("stem_in", (1, 64, hp // 2 + 1, wp // 4)).cpu()
+    assert (st[:, :32, 0] == 0).all() and (st[:, 32:, hp // 2] == 0).all()
+    t = torch.zeros((1, 32, hp, wp // 4))
+    t[:, :, 0::2] = st[:, 32:, :hp // 2]      # even rows y = 2q  (h = 1)
+    t[:, :, 1::2] = st[:, :32, 1:]            # odd rows  y = 2q - 1  (h = 0), q = 1 .. hp / 2
+    ref = torch.nn.functional.pad(otaps["input"], (3, 5))            # [1, 3, hp, wp + 8]
+    for s in range(9):
+        want = ref[:, :, :, s:s + wp:4]                               # x = 4*j - 3 + s  <=>  padded index 4*j + s
         # stored as tf32 (10-bit mantissa, round to nearest): |err| <= 2^-11 * 128
         assert (t[:, 3 * s:3 * s + 3] - want).abs().max().item() <= 0.0626, f"tap {s}"
-    assert (t[:, 21:] == 0).all() and (t[:, :, hn:, :] == 0).all()
+    assert (t[:, 27:] == 0).all() and (t[:, :, hn:, :] == 0).all()
 
 
 def test_backbone_fpn_rpn_head_tf32(eng_tf32, otaps):

@@ -52,7 +52,45 @@ void add_nchw_to_nhwc(Net& net, const float* const* src_slot, const Tensor& out,
 }
 
 // ---------------------------------------------------------------------------------------------
-// MaxPool2d(kernel 3, stride 2, padding 1), NHWC, 8 channels per thread.
+// MaxPool2d(kernel 3, stride 2, padding 1), NHWC, 8 channels per thread.  All nine taps are loaded before the first maximum
+// (a tap outside the image re-reads the window's centre pixel, which is always inside: the maximum does not change and no load
+// is predicated); bf16 maxima are taken on the packed pairs (the maximum of bf16 values is one of them: exact).
+__device__ __forceinline__ uint4 max8_raw(const uint4& a, const uint4& b, const __nv_bfloat16*) {
+  uint4 r;
+  const __nv_bfloat162 x0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.x), *reinterpret_cast<const __nv_bfloat162*>(&b.x));
+  const __nv_bfloat162 x1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.y), *reinterpret_cast<const __nv_bfloat162*>(&b.y));
+  const __nv_bfloat162 x2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.z), *reinterpret_cast<const __nv_bfloat162*>(&b.z));
+  const __nv_bfloat162 x3 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.w), *reinterpret_cast<const __nv_bfloat162*>(&b.w));
+  r.x = *reinterpret_cast<const uint32_t*>(&x0), r.y = *reinterpret_cast<const uint32_t*>(&x1);
+  r.z = *reinterpret_cast<const uint32_t*>(&x2), r.w = *reinterpret_cast<const uint32_t*>(&x3);
+  return r;
+}
+template <typename T>
+struct PoolVec;
+template <>
+struct PoolVec<__nv_bfloat16> {   // 8 channels = one 16-byte load
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void max_with(const PoolVec& o) { v = max8_raw(v, o.v, static_cast<const __nv_bfloat16*>(nullptr)); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+};
+template <>
+struct PoolVec<float> {           // 8 channels = two 16-byte loads
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void max_with(const PoolVec& o) {
+    a.x = fmaxf(a.x, o.a.x), a.y = fmaxf(a.y, o.a.y), a.z = fmaxf(a.z, o.a.z), a.w = fmaxf(a.w, o.a.w);
+    b.x = fmaxf(b.x, o.b.x), b.y = fmaxf(b.y, o.b.y), b.z = fmaxf(b.z, o.b.z), b.w = fmaxf(b.w, o.b.w);
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+  }
+};
+
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* in, long long ldi, T* out, long long ldo, int B, int H, int W, int Ho,
                                     int Wo, int C8) {
@@ -66,22 +104,22 @@ __global__ void maxpool3x3s2_kernel(const T* in, long long ldi, T* out, long lon
   t /= Wo;
   const int y = static_cast<int>(t % Ho);
   const int b = static_cast<int>(t / Ho);
-  float m[8];
+  const T* base = in + static_cast<long long>(b) * H * W * ldi + cg * 8;
+  PoolVec<T> v[9];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
   for (int dy = 0; dy < 3; ++dy) {
-    const int yy = 2 * y - 1 + dy;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = 0; dx < 3; ++dx) {
-      const int xx = 2 * x - 1 + dx;
-      if (xx < 0 || xx >= W) continue;
-      float v[8];
-      load8(in + ((static_cast<long long>(b) * H + yy) * W + xx) * ldi + cg * 8, v);
+    int yy = 2 * y - 1 + dy;
+    if (yy < 0 || yy >= H) yy = 2 * y;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    for (int dx = 0; dx < 3; ++dx) {
+      int xx = 2 * x - 1 + dx;
+      if (xx < 0 || xx >= W) xx = 2 * x;
+      v[dy * 3 + dx].load(base + (static_cast<long long>(yy) * W + xx) * ldi);
     }
   }
-  store8(out + ((static_cast<long long>(b) * Ho + y) * Wo + x) * ldo + cg * 8, m);
+#pragma unroll
+  for (int k = 1; k < 9; ++k) v[0].max_with(v[k]);
+  v[0].store(out + ((static_cast<long long>(b) * Ho + y) * Wo + x) * ldo + cg * 8);
 }
 
 void add_maxpool3x3s2(Net& net, const Tensor& in, const Tensor& out) {

@@ -743,7 +743,7 @@ int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, in
   sp.force_bn = force_bn & 0xfff;
   sp.force_direct_epilogue = (force_bn & 0x1000) != 0;
   sp.force_splits = (force_bn >> 16) & 0xff;
-  sp.force_opt = (force_bn >> 24) & 3;
+  sp.force_opt = (force_bn >> 24) & 7;
   sp.force_pair = (force_bn & 0x2000) ? 1 : ((force_bn & 0x4000) ? 2 : 0);
   add_conv(net, "pn_conv2d", x, y, w_host, scale_host, bias_host, sp, residual_dev ? &res : nullptr);
   net.run(nullptr);
@@ -778,7 +778,7 @@ int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int 
   sp.Cin = Cin, sp.Cout = Cout, sp.R = R, sp.S = S, sp.stride = stride, sp.dil = dil, sp.pad = pad, sp.relu = true;
   sp.force_bn = force_bn & 0xfff;
   sp.force_splits = (force_bn >> 16) & 0xff;
-  sp.force_opt = (force_bn >> 24) & 3;
+  sp.force_opt = (force_bn >> 24) & 7;
   sp.force_pair = (force_bn & 0x2000) ? 1 : ((force_bn & 0x4000) ? 2 : 0);
   long long* dbg = nullptr;
   if (std::getenv("PN_CONV_DBG")) {

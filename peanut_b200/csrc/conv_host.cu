@@ -299,7 +299,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     double t;
     int bn, splits;
     bool pair;
-    int opt = 0;  // 1: two CTAs per SM (half-size shared-memory footprint), 2: bias through the tensor core on multi-tile launches
+    int opt = 0;  // 1: two CTAs per SM (half-size shared-memory footprint), 2: bias through the tensor core on multi-tile launches, 4: weights resident
   };
   std::vector<Cand> cands;  // every valid launch configuration with its modelled time
   {
@@ -483,10 +483,17 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     // worth it where the epilogue is exposed (one tile per CTA: nothing overlaps it); persistent multi-tile launches hide
     // the epilogue behind the next tile's main loop and would only pay for the extra K block
     const bool one_tile_per_cta = static_cast<long long>(pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles <= (pair ? net.num_sms / 2 : net.num_sms);
-    p.bias_block = (p.epi_tma && splits == 1 && bias != nullptr && (one_tile_per_cta || (opt & 2))) ? 1 : 0;
-    const size_t stage_bytes = static_cast<size_t>(kBlockM + (pair ? bn / 2 : bn)) * sw;
+    // option 4: weights resident (conv_umma.cuh, ConvParams::b_resident): the n tile's whole weight slab sits beside the ring,
+    // the ring carries activations only; needs persistent multi-tile CTAs on ONE n tile each (grid a multiple of n_tiles)
+    const bool b_res = (opt & 4) != 0;
+    if (b_res) PN_REQUIRE(!pair && splits == 1 && !one_tile_per_cta, name + ": resident weights need single-CTA tiles, no split-K, several tiles per CTA");
+    p.b_resident = b_res ? 1 : 0;
+    p.bias_block = (!b_res && p.epi_tma && splits == 1 && bias != nullptr && (one_tile_per_cta || (opt & 2))) ? 1 : 0;
     const int kblocks = taps * kb_per_tap;
+    const size_t stage_bytes = b_res ? static_cast<size_t>(kBlockM) * sw : static_cast<size_t>(kBlockM + (pair ? bn / 2 : bn)) * sw;
     size_t fixed_bytes = 1024 /*align*/ + epi_bytes + 4 * bn * sizeof(float) /*bias per epilogue warp*/ + kBlockM * 32 /*ones tile*/ + 256 /*barriers*/;
+    if (b_res) fixed_bytes += static_cast<size_t>(kblocks) * bn * sw;
+    PN_REQUIRE(fixed_bytes + 2 * stage_bytes <= 227 * 1024, name + ": does not fit shared memory");
     size_t budget = 227 * 1024 - fixed_bytes;
     int stages = static_cast<int>(budget / stage_bytes);
     if (p.epi_tma && kblocks >= 32) {
@@ -528,8 +535,9 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     PN_REQUIRE(stages >= 2, name + ": shared memory budget too small for a 2-stage pipeline");
     const size_t smem = fixed_bytes + stages * stage_bytes;
     const long long tiles = static_cast<long long>(p.m_tiles) * n_tiles * splits;
-    const int grid = pair ? 2 * static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, ((opt & 1) ? 2 : 1) * (net.num_sms / 2)))
-                          : static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, ((opt & 1) ? 2 : 1) * net.num_sms));
+    int grid = pair ? 2 * static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, ((opt & 1) ? 2 : 1) * (net.num_sms / 2)))
+                    : static_cast<int>(splits > 1 ? tiles : std::min<long long>(tiles, ((opt & 1) ? 2 : 1) * net.num_sms));
+    if (b_res) grid = std::max(n_tiles, grid / n_tiles * n_tiles);   // work strides by the grid: the n tile of a CTA is then fixed
 
     Variant v;
     v.tm = tm, v.p = p, v.grid = grid, v.bn = bn, v.smem = smem, v.pair = pair;

@@ -69,6 +69,11 @@ struct ConvParams {
   long long* dbg;    // optional per-tile timeline of CTA 0 (tuning aid; nullptr in production): 16 clock64 slots per tile
   int splits;        // >= 1; BN / splits is a multiple of 8
   int kb_per_split;  // K blocks per split (the last split may be shorter)
+  // 1: weights resident.  The grid is a multiple of n_tiles, so a CTA works on ONE n tile for its whole life: it fetches that
+  // tile's weights (all K blocks) once into a dedicated region and the operand ring carries activations only.  For layers
+  // whose whole weight slab fits beside the ring (stem, res2, the small-K conv3 layers): every tile otherwise re-fetches the
+  // same weights from L2 - a third to a half of the bytes an SM ingests there.  Single-CTA tiles without split-K only.
+  int b_resident;
 };
 
 constexpr int kBlockM = 128;
@@ -320,14 +325,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t pair_mask = 3u << pair_leader;
   const uint32_t a_bytes = kBlockM * p.sw;
   const uint32_t b_bytes = kBLoad * p.sw;
-  const uint32_t stage_tx = (kPair ? 2u : 1u) * (a_bytes + b_bytes);  // bytes that complete one (leader) full barrier
+  const bool bres = !kSplit && !kPair && p.b_resident != 0;
+  const int kblocks_all = p.R * p.S * p.kb_per_tap;
+  const uint32_t stage_tx = bres ? a_bytes : (kPair ? 2u : 1u) * (a_bytes + b_bytes);  // bytes that complete one (leader) full barrier
   // persistent work items are walked by CTA (or by CTA pair)
   const int work_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int work_stride = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const uint32_t chunk_bytes = p.epi_tma ? kBlockM * p.cb : 0;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.stages * a_bytes;
-  uint8_t* smem_out = smem_b + p.stages * b_bytes;
+  uint8_t* smem_out = smem_b + (bres ? kblocks_all : p.stages) * b_bytes;
   uint8_t* smem_res = smem_out + p.out_bufs * chunk_bytes;
   float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * chunk_bytes);
   uint8_t* smem_ones = reinterpret_cast<uint8_t*>(smem_scale + 4 * BN);  // [128 rows][32 B], 32-byte swizzle: ones at k = 0, 1
@@ -338,7 +345,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* rfull_bar = tempty_bar + 2;
   uint64_t* rempty_bar = rfull_bar + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rempty_bar + 4);
+  uint64_t* bres_bar = rempty_bar + 4;   // resident weights have landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -361,6 +369,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&rfull_bar[i], 1);
       mbar_init(&rempty_bar[i], 4);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (p.bias_block && threadIdx.x < kBlockM) {
@@ -383,7 +392,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // Weights do not depend on the previous kernel: arm the first pipeline stages of this CTA's first work item and
   // fetch their weight tiles while the previous kernel drains (its tail would otherwise hide nothing but the prologue).
   int pre_armed = 0;
-  if (warp == kProducerWarp && p.m_limit == nullptr && work_first < p.m_tiles * p.n_tiles * p.splits) {
+  if (warp == kProducerWarp && p.m_limit == nullptr && !bres && work_first < p.m_tiles * p.n_tiles * p.splits) {
     const int work0 = work_first;
     const int tile0 = work0 / p.splits;
     const int split0 = work0 - tile0 * p.splits;
@@ -459,6 +468,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (bres && work_first < num_tiles) {   // this CTA's n tile never changes: its weights, all K blocks, once
+        const int n_tile0 = work_first % p.n_tiles;
+        mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(kblocks) * b_bytes);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(&tmap_b, bres_bar, smem_b + kb * b_bytes, kb * p.block_k, n_tile0 * BN);
+      }
       for (int work = work_first; work < num_tiles; work += work_stride) {
         const TileCoord tc = (work == work_first) ? first_tc : tile_coord<kPair>(p, work, cta_rank, kblocks);
         const int n_tile = tc.n_tile, m0 = tc.m0, w0 = tc.w0, h0 = tc.h0, img = tc.img;
@@ -491,7 +505,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               tma_load_im2col_4d(&tmap_a, &full_bar[stage], smem_a + stage * a_bytes, kb * p.block_k, w0, h0, img,
                                  static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
             }
-            if (!armed) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
+            if (!armed && !bres) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * b_bytes, kb_global * p.block_k, n_tile * BN);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -526,6 +540,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (bres && work_first < num_tiles) {
+        mbar_wait(bres_bar, 0);
+        tc_fence_after();
+      }
       for (int work = work_first; work < num_tiles; work += work_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -540,7 +558,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = umma_smem_desc(smem_u32(smem_a + stage * a_bytes), p.sw);
-          const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + stage * b_bytes), p.sw);
+          const uint64_t bdesc = umma_smem_desc(smem_u32(smem_b + (bres ? kb : stage) * b_bytes), p.sw);
           for (int k = 0; k < ksteps; ++k) {
             const uint32_t accum = (kb | k) ? 1u : 0u;
             if constexpr (kPair) {

@@ -238,7 +238,7 @@ struct ConvSpec {
   int force_pair = 0;    // test hook: 1 = force a CTA pair (cta_group::2), 2 = forbid it
   bool no_split = false;  // never split K (layers whose row count is dynamic keep one CTA per tile)
   long long* dbg = nullptr;  // tuning aid: per-tile clock64 timeline of CTA 0
-  int force_opt = 0;         // test hook: launch-shape options (1 two CTAs per SM, 2 bias block on multi-tile launches)
+  int force_opt = 0;         // test hook: launch-shape options (1 two CTAs per SM, 2 bias block on multi-tile launches, 4 weights resident)
   int dbg_skip = 0;          // tuning aid: epilogue parts to skip (timeline builds only)
   bool force_direct_epilogue = false;  // test hook: bypass the TMA-staged epilogue
   // Dynamic row limit: when set, only the first (*m_limit) * m_limit_rows GEMM rows are computed (device-side

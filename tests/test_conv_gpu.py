@@ -68,6 +68,19 @@ PAIR_CASES = [
 ]
 
 
+# weights resident (force_bn bits 24..26 = 4, or 5 with two CTAs per SM): persistent CTAs on one n tile each keep that tile's
+# whole weight slab in shared memory, the operand ring carries activations only
+RES = (4 << 24) | 0x4000 | (1 << 16)
+RES2 = (5 << 24) | 0x4000 | (1 << 16)
+RESIDENT_CASES = [
+    (8, 64, 100, 136, 64, 3, 1, 1, 1, RES | 64),      # res2.conv2-like: nine K blocks resident, 850 tiles on 148 CTAs
+    (4, 128, 48, 48, 512, 1, 1, 1, 0, RES | 128),     # 1x1, four n tiles: grid rounded to a multiple of four
+    (3, 64, 97, 131, 192, 1, 1, 1, 0, RES | 64),      # three n tiles (148 -> 147 CTAs), ragged last m tile
+    (16, 64, 100, 136, 256, 1, 1, 1, 0, RES2 | 128),  # res2.conv3-like with two CTAs per SM: 3 400 tiles on 296 CTAs
+    (8, 64, 100, 136, 64, 1, 1, 1, 0, RES2 | 64),     # one n tile, one K block
+]
+
+
 def _run(ctx, case, precision, with_res=True):
     B, Cin, H, W, Cout, k, stride, dil, pad, bn = case
     g = torch.Generator().manual_seed(sum(case[:9]) + (case[9] & 0x3ff))  # same data for every launch mode of a tile width
@@ -137,6 +150,18 @@ def test_conv_two_ctas_per_sm(ctx, case, precision):
     assert err <= (1e-2 if precision == _lib.PN_BF16 else 3e-3) * scale, f"max abs err {err} vs scale {scale}"
     # same tiles, same K order, same epilogue arithmetic as the one-CTA-per-SM launch: bit-identical
     y1, _ = _run(ctx, case[:9] + ((case[9] & 0x3ff) | 0x4000 | (1 << 16),), precision)
+    assert torch.equal(y, y1)
+
+
+@pytest.mark.parametrize("case", RESIDENT_CASES, ids=[str(c) for c in RESIDENT_CASES])
+def test_conv_weights_resident(ctx, case):
+    y, ref = _run(ctx, case, _lib.PN_BF16)
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= 1e-2 * scale, f"max abs err {err} vs scale {scale}"
+    # same tiles, same K order, same epilogue as the launch that streams the weights: bit-identical
+    plain = case[:9] + ((case[9] & 0x3ff) | 0x4000 | (1 << 16) | (case[9] & (1 << 24)),)
+    y1, _ = _run(ctx, plain, _lib.PN_BF16)
     assert torch.equal(y, y1)
 
 

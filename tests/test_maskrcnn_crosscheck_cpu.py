@@ -21,7 +21,9 @@ is checked against it on random inputs, with the KNOWN differences between the t
   box_head               faster_rcnn.TwoMLPHead + FastRCNNPredictor  background column first in tv
   mask_head              mask_rcnn.MaskRCNNHeads + MaskRCNNPredictor + roi_heads.maskrcnn_inference   labels 1-based in tv
   roi_pool               (torchvision.ops.roi_align is the op detectron2's ROIAlign itself dispatches to)
-  paste_masks            none: torchvision pastes with integer boxes + interpolate, a different algorithm
+  paste_masks            none in torchvision (it pastes with integer boxes + interpolate, a different algorithm): checked against a
+                         direct float64 evaluation of the published rule instead (pixel centre -> mask coordinates -> zero-padded
+                         bilinear sample -> >= 0.5), pixels within 1e-5 of the threshold excluded
 """
 import math
 
@@ -256,3 +258,36 @@ def test_box_and_mask_heads_equal_torchvision_modules(weights):
         probs = O.mask_head(mp, classes, w)
         assert probs.shape == (12, 28, 28)
         assert torch.allclose(probs, tv_probs, atol=2e-5, rtol=1e-5)
+
+
+def test_paste_masks_against_direct_evaluation():
+    """paste_masks_in_image (detectron2 layers/mask_ops.py): output pixel (y, x) samples the 28 x 28 mask at the image of its
+    CENTRE (x + 0.5, y + 0.5) under the box -> [0, 28) map, bilinearly, zeros outside, and is set when the value is >= 0.5.
+    Evaluated here pixel by pixel in float64 without grid_sample."""
+    import numpy as np
+    g = torch.Generator().manual_seed(11)
+    N, S, H, W = 6, 28, 40, 52
+    masks = torch.rand((N, S, S), generator=g)
+    boxes = torch.tensor([[3.2, 4.7, 30.9, 33.1], [0.0, 0.0, 52.0, 40.0], [-6.5, -3.0, 20.0, 18.5], [40.0, 30.0, 60.0, 47.0],
+                          [10.0, 10.0, 11.5, 31.0], [25.3, 2.2, 50.1, 9.9]])
+    got = O.paste_masks(masks, boxes, H, W, 0.5).numpy()
+    m = masks.double().numpy()
+    checked = 0
+    for n in range(N):
+        x0, y0, x1, y1 = [float(v) for v in boxes[n]]
+        for y in range(H):
+            v = (y + 0.5 - y0) / (y1 - y0) * S - 0.5          # mask row coordinate of the pixel centre
+            for x in range(W):
+                u = (x + 0.5 - x0) / (x1 - x0) * S - 0.5
+                fu, fv = math.floor(u), math.floor(v)
+                val = 0.0
+                for dv in (0, 1):
+                    for du in (0, 1):
+                        r, c = fv + dv, fu + du
+                        if 0 <= r < S and 0 <= c < S:
+                            val += m[n, r, c] * (1 - abs(v - r)) * (1 - abs(u - c))
+                if abs(val - 0.5) > 1e-5:
+                    assert bool(got[n, y, x]) == (val >= 0.5), (n, y, x, val)
+                    checked += 1
+    assert checked > 0.99 * N * H * W
+    assert got[1].any() and not got[3, :25].any()

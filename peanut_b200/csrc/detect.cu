@@ -94,15 +94,9 @@ template <typename T>
 __global__ void k_upsample2x_add(const T* __restrict__ prev, long long ldp, int h, int w, T* __restrict__ lat, long long ldl,
                                  int B, int H, int W, int C8, int round_tf32) {
   pdl_grid_sync();
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * C8;
-  if (idx >= total) return;
-  const int cg = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int x = static_cast<int>(t % W);
-  t /= W;
-  const int y = static_cast<int>(t % H);
-  const int b = static_cast<int>(t / H);
+  Idx4 ix;
+  if (!split_index(H, W, C8, static_cast<uint32_t>(B) * H * W * C8, ix)) return;
+  const int b = static_cast<int>(ix.a), y = static_cast<int>(ix.b), x = static_cast<int>(ix.c), cg = static_cast<int>(ix.d);
   const int ys = min(y >> 1, h - 1), xs = min(x >> 1, w - 1);
   float a[8], p[8];
   T* lp = lat + ((static_cast<long long>(b) * H + y) * W + x) * ldl + cg * 8;
@@ -124,15 +118,9 @@ template <typename T>
 __global__ void k_subsample2(const T* __restrict__ in, long long ldi, int H, int W, T* __restrict__ out, long long ldo, int B,
                              int Ho, int Wo, int C8) {
   pdl_grid_sync();
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
-  if (idx >= total) return;
-  const int cg = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int x = static_cast<int>(t % Wo);
-  t /= Wo;
-  const int y = static_cast<int>(t % Ho);
-  const int b = static_cast<int>(t / Ho);
+  Idx4 ix;
+  if (!split_index(Ho, Wo, C8, static_cast<uint32_t>(B) * Ho * Wo * C8, ix)) return;
+  const int b = static_cast<int>(ix.a), y = static_cast<int>(ix.b), x = static_cast<int>(ix.c), cg = static_cast<int>(ix.d);
   float v[8];
   load8(in + ((static_cast<long long>(b) * H + 2 * y) * W + 2 * x) * ldi + cg * 8, v);
   store8(out + ((static_cast<long long>(b) * Ho + y) * Wo + x) * ldo + cg * 8, v);
@@ -1089,6 +1077,7 @@ void add_upsample2x_add(Net& net, const Tensor& prev, const Tensor& lat) {
   PN_REQUIRE(lat.H == 2 * prev.H && lat.W == 2 * prev.W, "upsample_add: the fine level must be exactly 2x the coarse one");
   const int C8 = lat.C / 8;
   const long long total = lat.pixels() * C8;
+  check_u32_launch(total, "fpn elementwise kernel");
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   Tensor p = prev, l = lat;
@@ -1105,6 +1094,7 @@ void add_subsample2(Net& net, const Tensor& in, const Tensor& out) {
   PN_REQUIRE(out.H == (in.H - 1) / 2 + 1 && out.W == (in.W - 1) / 2 + 1 && in.C == out.C && in.C % 8 == 0, "subsample2: shape");
   const int C8 = in.C / 8;
   const long long total = out.pixels() * C8;
+  check_u32_launch(total, "fpn elementwise kernel");
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   Tensor i = in, o = out;

@@ -31,6 +31,11 @@ inline size_t dtype_size(DType d) { return d == kBF16 ? 2 : 4; }
     if (!(cond)) throw std::runtime_error(std::string("peanut_b200: ") + (msg));     \
   } while (0)
 
+// Kernels that split their linear thread index with 32-bit arithmetic (vec.cuh split_index): one thread per work item, < 2^32.
+inline void check_u32_launch(long long threads, const char* what) {
+  PN_REQUIRE(threads >= 0 && threads < (1ll << 32), std::string(what) + ": more than 2^32 work items in one launch");
+}
+
 
 // ---- programmatic dependent launch for every non-GEMM kernel of the launch lists.
 // Each kernel starts with pdl_grid_sync(): it lets the NEXT kernel of the stream become resident right away and then

@@ -95,15 +95,9 @@ template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* in, long long ldi, T* out, long long ldo, int B, int H, int W, int Ho,
                                     int Wo, int C8) {
   pdl_grid_sync();
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
-  if (idx >= total) return;
-  const int cg = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int x = static_cast<int>(t % Wo);
-  t /= Wo;
-  const int y = static_cast<int>(t % Ho);
-  const int b = static_cast<int>(t / Ho);
+  Idx4 ix;
+  if (!split_index(Ho, Wo, C8, static_cast<uint32_t>(B) * Ho * Wo * C8, ix)) return;
+  const int b = static_cast<int>(ix.a), y = static_cast<int>(ix.b), x = static_cast<int>(ix.c), cg = static_cast<int>(ix.d);
   const T* base = in + static_cast<long long>(b) * H * W * ldi + cg * 8;
   PoolVec<T> v[9];
 #pragma unroll
@@ -127,6 +121,7 @@ void add_maxpool3x3s2(Net& net, const Tensor& in, const Tensor& out) {
   PN_REQUIRE(in.C % 8 == 0 && out.C == in.C && in.dt == out.dt, "maxpool channels");
   const int C8 = in.C / 8;
   const long long total = out.pixels() * C8;
+  check_u32_launch(total, "maxpool3x3s2");
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   Tensor i = in, o = out;
@@ -262,15 +257,9 @@ template <typename T>
 __global__ void bilinear_into_kernel(const T* in, long long ldi, int h, int w, T* out, long long ldo, int B, int H, int W,
                                      int C8, float sy, float sx) {
   pdl_grid_sync();
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * C8;
-  if (idx >= total) return;
-  const int cg = static_cast<int>(idx % C8);
-  long long t = idx / C8;
-  const int x = static_cast<int>(t % W);
-  t /= W;
-  const int y = static_cast<int>(t % H);
-  const int b = static_cast<int>(t / H);
+  Idx4 ix;
+  if (!split_index(H, W, C8, static_cast<uint32_t>(B) * H * W * C8, ix)) return;
+  const int b = static_cast<int>(ix.a), y = static_cast<int>(ix.b), x = static_cast<int>(ix.c), cg = static_cast<int>(ix.d);
   int y0, y1, x0, x1;
   float ly0, ly1, lx0, lx1;
   bilinear_src(y, sy, h, y0, y1, ly0, ly1);
@@ -313,13 +302,9 @@ __global__ void upsample_logits_kernel(const float* in, long long ldi, int h, in
   pdl_grid_sync();
   float* dst = *dst_slot;
   const int apply_sigmoid = *sigmoid_slot;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W;
-  if (idx >= total) return;
-  const int x = static_cast<int>(idx % W);
-  const long long t = idx / W;
-  const int y = static_cast<int>(t % H);
-  const int b = static_cast<int>(t / H);
+  Idx4 ix;
+  if (!split_index(H, W, 1, static_cast<uint32_t>(B) * H * W, ix)) return;
+  const int b = static_cast<int>(ix.a), y = static_cast<int>(ix.b), x = static_cast<int>(ix.c);
   int y0, y1, x0, x1;
   float ly0, ly1, lx0, lx1;
   bilinear_src(y, sy, h, y0, y1, ly0, ly1);

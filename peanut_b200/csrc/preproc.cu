@@ -69,13 +69,10 @@ __global__ void k_resize_u8(const uint8_t* const* rgb_slot, int B, int H, int W,
                             uint8_t* __restrict__ resized_u8) {
   pdl_grid_sync();
   const uint8_t* rgb = *rgb_slot;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Hn * Wn;
-  if (idx >= total) return;
-  const int x = static_cast<int>(idx % Wn);
-  const long long t = idx / Wn;
-  const int y = static_cast<int>(t % Hn);
-  const int b = static_cast<int>(t / Hn);
+  Idx4 ix;
+  if (!split_index(Hn, Wn, 1, static_cast<uint32_t>(B) * Hn * Wn, ix)) return;
+  const int b = static_cast<int>(ix.a), y = static_cast<int>(ix.b), x = static_cast<int>(ix.c);
+  const size_t idx = (static_cast<size_t>(b) * Hn + y) * Wn + x;
   const int x0 = hb[2 * x], xn = hb[2 * x + 1];
   const int y0 = vb[2 * y], yn = vb[2 * y + 1];
   int acc[3] = {1 << 21, 1 << 21, 1 << 21};
@@ -111,13 +108,10 @@ __global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int H
   pdl_grid_sync();
   // one thread per stored pixel (row pair q, pixel pair j): 2 x 27 values, 128 contiguous bytes (bf16) per thread
   const int Hq = Hp / 2 + 1;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Hq * Wq;
-  if (idx >= total) return;
-  const int j = static_cast<int>(idx % Wq);
-  const long long t = idx / Wq;
-  const int q = static_cast<int>(t % Hq);
-  const int b = static_cast<int>(t / Hq);
+  Idx4 ix;
+  if (!split_index(Hq, Wq, 1, static_cast<uint32_t>(B) * Hq * Wq, ix)) return;
+  const int b = static_cast<int>(ix.a), q = static_cast<int>(ix.b), j = static_cast<int>(ix.c);
+  const size_t idx = (static_cast<size_t>(b) * Hq + q) * Wq + j;
   // PIXEL_STD is (1, 1, 1) in the reference's yaml: x / 1 == x exactly
   const bool unit_std = std_bgr.x == 1.f && std_bgr.y == 1.f && std_bgr.z == 1.f;
   T* o = out + idx * 64;
@@ -224,6 +218,8 @@ void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H
   const float3 sd = make_float3(std_bgr[0], std_bgr[1], std_bgr[2]);
   const int threads = 256;
   const long long total1 = static_cast<long long>(B) * Hn * Wn;
+  check_u32_launch(total1, "resize_u8");
+  check_u32_launch(out.pixels(), "pack_stem");
   const int blocks1 = static_cast<int>((total1 + threads - 1) / threads);
   net.add("resize_u8", [=](cudaStream_t s) {
     launch_pdl(k_resize_u8, blocks1, threads, 0, s, rgb_slot, B, H, W, Hn, Wn, d_hb, d_hk, hks, d_vb, d_vk, vks, resized_u8);

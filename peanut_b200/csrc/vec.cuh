@@ -6,6 +6,25 @@
 
 namespace pn {
 
+// Linear thread index of a 1-D launch split into (a, b, c, d), d fastest, in 32-bit arithmetic.  The streaming kernels
+// (pool, FPN add, resizes, packing) used 64-bit div / mod pairs for this - about a hundred instructions each, three per
+// thread - and were issue-bound at 1.5x their HBM floor because of it.  The host checks that a launch has fewer than 2^32
+// threads (check_u32_launch).
+struct Idx4 {
+  uint32_t a, b, c, d;
+};
+__device__ __forceinline__ bool split_index(uint32_t nb, uint32_t nc, uint32_t nd, uint32_t total, Idx4& o) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return false;
+  const uint32_t t = idx / nd;
+  o.d = idx - t * nd;
+  const uint32_t u = t / nc;
+  o.c = t - u * nc;
+  o.a = u / nb;
+  o.b = u - o.a * nb;
+  return true;
+}
+
 __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T>

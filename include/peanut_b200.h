@@ -27,7 +27,11 @@ typedef struct pn_ctx pn_ctx;
 /* Arithmetic of the tensor-core path. */
 enum pn_precision {
   PN_BF16 = 0, /* bf16 operands, fp32 accumulate (throughput path) */
-  PN_TF32 = 1  /* fp32 storage, tf32 operands, fp32 accumulate (fp32-parity path) */
+  PN_TF32 = 1, /* fp32 storage, tf32 operands, fp32 accumulate (fp32-parity path, the drop-in shims' default) */
+  PN_FP32 = 2  /* fp32 storage with every stored bit kept, each convolution as three tf32 tensor-core products
+                  (hi*hi + hi*lo + lo*hi, fp32 accumulate): ~1e-6 relative, about a third of PN_TF32's speed and three
+                  times its activation memory.  The strict-parity mode: what the reference's fp32 CPU / cuDNN-fp32
+                  arithmetic is compared with (segmentation.py:45, prediction.py:128-131 run in fp32). */
 };
 
 int pn_create(int device, pn_ctx** out);

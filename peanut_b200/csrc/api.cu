@@ -80,7 +80,7 @@ __global__ void nchw_to_nhwc_direct_kernel(const float* in, T* out, long long ld
   out[(static_cast<long long>(b) * HW + hw) * ldo + c] = from_float<T>(v);
 }
 
-void nchw_to_nhwc_direct(const float* in, const Tensor& t, int C, cudaStream_t s) {
+void nchw_to_nhwc_direct(const float* in, const Tensor& t, int C, cudaStream_t s, bool round_stored = true) {
   const int HW = t.H * t.W;
   const long long total = static_cast<long long>(t.B) * C * HW;
   const int threads = 256;
@@ -88,7 +88,7 @@ void nchw_to_nhwc_direct(const float* in, const Tensor& t, int C, cudaStream_t s
   if (t.dt == kBF16)
     launch_pdl(nchw_to_nhwc_direct_kernel<__nv_bfloat16>, blocks, threads, 0, s, in, static_cast<__nv_bfloat16*>(t.ptr), t.ld, t.B, C, HW, 0);
   else
-    launch_pdl(nchw_to_nhwc_direct_kernel<float>, blocks, threads, 0, s, in, static_cast<float*>(t.ptr), t.ld, t.B, C, HW, 1);
+    launch_pdl(nchw_to_nhwc_direct_kernel<float>, blocks, threads, 0, s, in, static_cast<float*>(t.ptr), t.ld, t.B, C, HW, round_stored ? 1 : 0);
 }
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
@@ -189,10 +189,11 @@ int pn_prednet_build(pn_ctx* ctx, int B, int C, int H, int W, int num_classes, i
   auto* c = reinterpret_cast<Ctx*>(ctx);
   check_device(c);
   PN_REQUIRE(B > 0 && C > 0 && H >= 8 && W >= 8 && num_classes > 0, "pn_prednet_build: bad shape");
-  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32, "pn_prednet_build: bad precision");
+  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32 || precision == PN_FP32, "pn_prednet_build: bad precision");
   c->prednet.reset();
   auto net = std::make_unique<PredNet>();
   net->net.num_sms = c->num_sms;
+  net->net.x3 = precision == PN_FP32;
   build_prednet(*net, c->weights, B, C, H, W, num_classes, precision == PN_BF16 ? kBF16 : kF32);
   PN_CUDA_CHECK(cudaDeviceSynchronize());
   c->prednet = std::move(net);
@@ -412,7 +413,7 @@ int pn_maskrcnn_build(pn_ctx* ctx, int B, int H, int W, int precision, const pn_
   auto* c = reinterpret_cast<Ctx*>(ctx);
   check_device(c);
   PN_REQUIRE(B > 0 && H > 0 && W > 0, "pn_maskrcnn_build: bad shape");
-  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32, "pn_maskrcnn_build: bad precision");
+  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32 || precision == PN_FP32, "pn_maskrcnn_build: bad precision");
   MrcnnCfg g;
   g.B = B, g.H = H, g.W = W;
   if (cfg) {
@@ -424,6 +425,7 @@ int pn_maskrcnn_build(pn_ctx* ctx, int B, int H, int W, int precision, const pn_
   c->maskrcnn.reset();
   auto net = std::make_unique<MaskRcnn>();
   net->net.num_sms = c->num_sms;
+  net->net.x3 = precision == PN_FP32;
   build_maskrcnn(*net, c->weights, g, precision == PN_BF16 ? kBF16 : kF32);
   PN_CUDA_CHECK(cudaDeviceSynchronize());
   c->maskrcnn = std::move(net);
@@ -537,7 +539,7 @@ int pn_maskrcnn_tap(pn_ctx* ctx, const char* name, int write, int channels, void
     PN_REQUIRE(channels > 0 && channels <= t.C, "pn_maskrcnn_tap: bad channel count");
     const size_t bytes = static_cast<size_t>(t.pixels()) * channels * sizeof(float);
     PN_REQUIRE(static_cast<size_t>(buf_bytes) >= bytes, "pn_maskrcnn_tap: buffer too small");
-    if (write) nchw_to_nhwc_direct(static_cast<const float*>(buf_dev), t, channels, s);
+    if (write) nchw_to_nhwc_direct(static_cast<const float*>(buf_dev), t, channels, s, !m.net.x3);
     else nhwc_to_nchw(t, channels, static_cast<float*>(buf_dev), s);
   } else if (m.net.raw_taps.count(key)) {
     auto& rt = m.net.raw_taps[key];
@@ -716,9 +718,12 @@ int pn_conv2d(pn_ctx* ctx, int precision, const float* x_dev, int B, int Cin, in
   auto* c = reinterpret_cast<Ctx*>(ctx);
   check_device(c);
   PN_REQUIRE(x_dev && w_host && y_dev, "pn_conv2d: null buffer");
+  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32 || precision == PN_FP32, "bad precision");
   const DType dt = precision == PN_BF16 ? kBF16 : kF32;
   Net net;
   net.num_sms = c->num_sms;
+  net.dt = dt;
+  net.x3 = precision == PN_FP32;
   net.use_graph = false;
   struct Slots {
     const float* x;
@@ -759,9 +764,12 @@ int pn_conv_bench(pn_ctx* ctx, int precision, int B, int Cin, int H, int W, int 
   auto* c = reinterpret_cast<Ctx*>(ctx);
   check_device(c);
   PN_REQUIRE(ms_out && iters > 0, "pn_conv_bench: bad arguments");
+  PN_REQUIRE(precision == PN_BF16 || precision == PN_TF32 || precision == PN_FP32, "bad precision");
   const DType dt = precision == PN_BF16 ? kBF16 : kF32;
   Net net;
   net.num_sms = c->num_sms;
+  net.dt = dt;
+  net.x3 = precision == PN_FP32;
   net.use_graph = false;
   Tensor x = net.arena.tensor(B, H, W, pad_channels(Cin, dt), dt);
   PN_CUDA_CHECK(cudaMemset(x.ptr, 0x3c, x.bytes()));

@@ -259,8 +259,83 @@ void fold_bn(const WeightStore& w, const std::string& prefix, int C, std::vector
   }
 }
 
+// ---- fp32 parity mode (Net::x3): a convolution as three tf32 products.
+// x = hi + lo with hi = tf32(x) (round to nearest) and lo = tf32(x - hi); w likewise.  x*w = hi*whi + hi*wlo + lo*whi + O(2^-22 |x w|):
+// the dropped lo*wlo term and the rounding of lo are both 2^-22 relative, the accumulation is the tensor core's fp32.  The three
+// products are ONE convolution over 3 x the channels: the split kernel writes [hi | hi | lo] per pixel into a scratch tensor and the
+// weights are packed as [whi | wlo | whi] per filter tap, so the kernel, its epilogue and the launch machinery are the tf32 path's.
+__device__ __forceinline__ float rn_tf32(float v) {
+  uint32_t q;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v));
+  return __uint_as_float(q);
+}
+__global__ void split3_kernel(const float* __restrict__ in, long long ldi, int C4, float* __restrict__ out, long long ldo, int cpad,
+                              long long total) {
+  pdl_grid_sync();
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const long long pix = idx / C4;
+  const int c = static_cast<int>(idx - pix * C4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(in + pix * ldi + c);
+  float4 hi, lo;
+  hi.x = rn_tf32(v.x), hi.y = rn_tf32(v.y), hi.z = rn_tf32(v.z), hi.w = rn_tf32(v.w);
+  lo.x = rn_tf32(v.x - hi.x), lo.y = rn_tf32(v.y - hi.y), lo.z = rn_tf32(v.z - hi.z), lo.w = rn_tf32(v.w - hi.w);
+  float* o = out + pix * ldo + c;
+  *reinterpret_cast<float4*>(o) = hi;
+  *reinterpret_cast<float4*>(o + cpad) = hi;
+  *reinterpret_cast<float4*>(o + 2 * cpad) = lo;
+}
+
+inline float host_rn_tf32(float v) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+  std::memcpy(&v, &u, 4);
+  return v;
+}
+
+static void add_conv_x3(Net& net, const std::string& name, const Tensor& in, const Tensor& out, const float* weight,
+                        const float* scale, const float* bias, const ConvSpec& sp, const Tensor* residual) {
+  PN_REQUIRE(in.dt == kF32, name + ": the fp32 split-precision path needs fp32 activations");
+  PN_REQUIRE(in.C % 4 == 0 && in.ld % 4 == 0, name + ": channels not a multiple of 4");
+  const int cpad = in.C;
+  const int C3 = round_up(3 * cpad, 32);  // K blocks of 32 floats (128-byte swizzle rows); the tail stays zero
+  Tensor s3 = net.arena.tensor(in.B, in.H, in.W, C3, kF32);
+  {
+    const int C4 = cpad / 4;
+    const long long total = in.pixels() * C4;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    PN_REQUIRE(blocks < (1ll << 31), name + ": split launch too large");
+    const float* src = static_cast<const float*>(in.ptr);
+    float* dst = static_cast<float*>(s3.ptr);
+    const long long ldi = in.ld, ldo = s3.ld;
+    net.add(name + ".split3", [=](cudaStream_t s) {
+      launch_pdl(split3_kernel, static_cast<int>(blocks), threads, 0, s, src, ldi, C4, dst, ldo, cpad, total);
+    });
+    net.launches_per_forward += 1;
+  }
+  const int taps = sp.R * sp.S;
+  std::vector<float> w3(static_cast<size_t>(sp.Cout) * C3 * taps, 0.f);
+  for (int co = 0; co < sp.Cout; ++co)
+    for (int ci = 0; ci < sp.Cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const float w = weight[(static_cast<size_t>(co) * sp.Cin + ci) * taps + t] * (scale ? scale[co] : 1.f);
+        const float hi = host_rn_tf32(w), lo = host_rn_tf32(w - hi);
+        float* row = w3.data() + static_cast<size_t>(co) * C3 * taps;
+        row[static_cast<size_t>(ci) * taps + t] = hi;
+        row[static_cast<size_t>(cpad + ci) * taps + t] = lo;
+        row[static_cast<size_t>(2 * cpad + ci) * taps + t] = hi;
+      }
+  ConvSpec sp3 = sp;
+  sp3.Cin = C3;
+  sp3.x3_cin = sp.Cin;
+  add_conv(net, name, s3, out, w3.data(), nullptr, bias, sp3, residual);
+}
+
 void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor& out, const float* weight,
               const float* scale, const float* bias, const ConvSpec& sp, const Tensor* residual) {
+  if (net.x3 && !sp.x3_cin) return add_conv_x3(net, name, in, out, weight, scale, bias, sp, residual);
   const DType dt = in.dt;
   const int es = static_cast<int>(dtype_size(dt));
   const int stride_w = sp.stride_w >= 0 ? sp.stride_w : sp.stride;
@@ -450,7 +525,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
     p.out = out.ptr, p.ldc = out.ld;
     p.relu = sp.relu ? 1 : 0;
     p.out_fp32 = (out.dt == kF32) ? 1 : 0;
-    p.round_tf32 = (dt == kF32 && !sp.out_fp32) ? 1 : 0;
+    p.round_tf32 = (dt == kF32 && !sp.out_fp32 && !net.x3) ? 1 : 0;
     p.dbg = sp.dbg;
     p.dbg_skip = sp.dbg_skip;
     p.m_limit = sp.m_limit;
@@ -650,7 +725,7 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   net.last_bn = bn + 1000 * splits + (pair ? 100000 : 0) + 1000000 * opt;
   const Variant chosen = make_variant(bn, splits, pair, opt);
 
-  const double flops = 2.0 * static_cast<double>(M) * sp.Cout * sp.Cin * taps;
+  const double flops = 2.0 * static_cast<double>(M) * sp.Cout * (sp.x3_cin ? sp.x3_cin : sp.Cin) * taps;  // algorithmic, also on the split-precision path
   net.add(name, [=](cudaStream_t s) { launch_variant(chosen, s); }, flops);
   net.launches_per_forward += 1;
 }

@@ -636,11 +636,11 @@ __device__ __forceinline__ void roi_bin_per_sample(const Pyramid& pyr, const flo
 
 // acc / count -> (tf32 rounding for fp32 storage) -> store, 8 channels.
 template <typename T>
-__device__ __forceinline__ void roi_bin_store(float (&acc)[8], float count, T* dst) {
+__device__ __forceinline__ void roi_bin_store(float (&acc)[8], float count, T* dst, bool rnd) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     acc[j] = acc[j] / count;
-    if (sizeof(T) == 4) {
+    if (sizeof(T) == 4 && rnd) {
       uint32_t q;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(acc[j]));
       acc[j] = __uint_as_float(q);
@@ -656,7 +656,7 @@ __device__ __forceinline__ void roi_bin_store(float (&acc)[8], float count, T* d
 // at 2.9 of 4 instructions per cycle.  Zero weights are not skipped: fma(0, v, acc) == acc, so the sums are the same.
 template <typename T, int kNC>
 __device__ __forceinline__ void roi_bins_fixed(const float (*s_wy)[32], const int* s_rlo, const int* s_nrows, float WX, const T* colp,
-                                               size_t row_stride, size_t ld, int S, float count, T* outp, long long ldo) {
+                                               size_t row_stride, size_t ld, int S, float count, T* outp, long long ldo, bool rnd) {
   constexpr int kRows = (sizeof(T) == 2 && kNC <= 4) ? 2 : 1;
   float wx[kNC];
 #pragma unroll
@@ -703,7 +703,7 @@ __device__ __forceinline__ void roi_bins_fixed(const float (*s_wy)[32], const in
         for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(w, val[j], acc[j]);
       }
     }
-    roi_bin_store<T>(acc, count, outp + static_cast<size_t>(ph) * S * ldo);
+    roi_bin_store<T>(acc, count, outp + static_cast<size_t>(ph) * S * ldo, rnd);
   }
 }
 
@@ -724,6 +724,7 @@ __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* 
   const int r = blockIdx.x;
   const int b = img[r];
   if (b < 0) return;
+  const bool rnd = pyr.keep_fp32 == 0;
   __shared__ float s_wy[14][32];   // [bin row][feature row - rlo]
   __shared__ int s_rlo[14], s_nrows[14];
   __shared__ int s_rows_bad;       // some bin row spans more than 32 feature rows (or the ROI has no samples)
@@ -794,14 +795,14 @@ __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* 
   T* outp = out + (static_cast<size_t>(r) * S * S + pw) * ldo + lane * 8;
   if (cols_ok && s_rows_bad == 0 && ncols <= 8) {
     switch (ncols) {
-      case 1: roi_bins_fixed<T, 1>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      case 2: roi_bins_fixed<T, 2>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      case 3: roi_bins_fixed<T, 3>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      case 4: roi_bins_fixed<T, 4>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      case 5: roi_bins_fixed<T, 5>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      case 6: roi_bins_fixed<T, 6>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      case 7: roi_bins_fixed<T, 7>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
-      default: roi_bins_fixed<T, 8>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo); break;
+      case 1: roi_bins_fixed<T, 1>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      case 2: roi_bins_fixed<T, 2>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      case 3: roi_bins_fixed<T, 3>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      case 4: roi_bins_fixed<T, 4>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      case 5: roi_bins_fixed<T, 5>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      case 6: roi_bins_fixed<T, 6>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      case 7: roi_bins_fixed<T, 7>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
+      default: roi_bins_fixed<T, 8>(s_wy, s_rlo, s_nrows, WX, colp, row_stride, ld, S, count, outp, ldo, rnd); break;
     }
     return;
   }
@@ -840,7 +841,7 @@ __global__ void __launch_bounds__(448, 2) k_roi_align(Pyramid pyr, const float* 
     } else {
       roi_bin_per_sample<T>(pyr, boxes, r, b, S, ph, pw, lane, acc);
     }
-    roi_bin_store<T>(acc, count, outp + static_cast<size_t>(ph) * S * ldo);
+    roi_bin_store<T>(acc, count, outp + static_cast<size_t>(ph) * S * ldo, rnd);
   }
 }
 
@@ -1081,11 +1082,12 @@ void add_upsample2x_add(Net& net, const Tensor& prev, const Tensor& lat) {
   const int threads = 256;
   const int blocks = static_cast<int>((total + threads - 1) / threads);
   Tensor p = prev, l = lat;
+  const int rnd = net.x3 ? 0 : 1;
   net.add("fpn_upsample_add", [=](cudaStream_t s) {
     if (l.dt == kBF16)
       launch_pdl(k_upsample2x_add<__nv_bfloat16>, blocks, threads, 0, s, static_cast<const __nv_bfloat16*>(p.ptr), p.ld, p.H, p.W, static_cast<__nv_bfloat16*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 0);
     else
-      launch_pdl(k_upsample2x_add<float>, blocks, threads, 0, s, static_cast<const float*>(p.ptr), p.ld, p.H, p.W, static_cast<float*>(l.ptr), l.ld, l.B, l.H, l.W, C8, 1);
+      launch_pdl(k_upsample2x_add<float>, blocks, threads, 0, s, static_cast<const float*>(p.ptr), p.ld, p.H, p.W, static_cast<float*>(l.ptr), l.ld, l.B, l.H, l.W, C8, rnd);
   });
   net.launches_per_forward += 1;
 }
@@ -1152,10 +1154,12 @@ void add_rpn_proposals(Net& net, MaskRcnn& m, const RpnMeta& meta) {
   net.launches_per_forward += 2;
 }
 
-void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr, DType dt, const float* boxes, const int* img,
+void add_roi_align(Net& net, const std::string& name, const Pyramid& pyr_in, DType dt, const float* boxes, const int* img,
                    int nrois, int S, const Tensor& out) {
   PN_REQUIRE(out.C == 256 && out.dt == dt && S <= 14, "roi_align: 256-channel pyramid, at most 14 x 14 bins expected");
   Tensor o = out;
+  Pyramid pyr = pyr_in;
+  pyr.keep_fp32 = net.x3 ? 1 : 0;
   net.add(name, [=](cudaStream_t s) {
     if (dt == kBF16)
       launch_pdl(k_roi_align<__nv_bfloat16>, dim3(nrois), S * 32, 0, s, pyr, boxes, img, S, static_cast<__nv_bfloat16*>(o.ptr), o.ld);

@@ -155,6 +155,11 @@ struct Net {
   std::map<std::string, Tensor> taps;           // named NHWC activations (parity taps)
   std::map<std::string, std::pair<void*, size_t>> raw_taps;  // named raw device buffers (pointer, bytes)
   DType dt = kBF16;
+  // fp32 parity mode (PN_FP32): fp32 storage WITHOUT the tf32 rounding of stored activations, every convolution evaluated as
+  // three tf32 tensor-core products (hi*hi + hi*lo + lo*hi, conv_host.cu add_conv) - about fp32 accuracy at a third of the
+  // tf32 path's speed.  Only meaningful with dt == kF32.
+  bool x3 = false;
+  bool round_stored() const { return dt == kF32 && !x3; }  // fp32 activations rounded to tf32 where they are stored
   int num_sms = 148;
   long long launches_per_forward = 0;
   int last_bn = 0;  // N tile chosen by the most recent add_conv (tuning aid)
@@ -250,6 +255,7 @@ struct ConvSpec {
   // count of valid ROIs x rows per ROI); tiles beyond are skipped by every warp role.
   const int* m_limit = nullptr;
   int m_limit_rows = 1;
+  int x3_cin = 0;  // internal: set on the inner call of the fp32 split-precision path (= the caller's Cin, for the FLOP count)
 };
 // weight: fp32 [Cout][Cin][R][S]; scale / bias: fp32 [Cout] (folded BN or plain bias with scale 1).
 // `out` must already describe the destination view (B, Ho, Wo, C >= Cout rounded to 8, ld).

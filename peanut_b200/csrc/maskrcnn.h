@@ -55,6 +55,7 @@ struct PyramidLevel {
 };
 struct Pyramid {
   PyramidLevel lv[4];  // p2..p5
+  int keep_fp32;       // fp32 parity mode (Net::x3): pooled values are stored unrounded
 };
 
 struct MaskRcnn {

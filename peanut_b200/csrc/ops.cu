@@ -11,7 +11,7 @@ namespace pn {
 // ---------------------------------------------------------------------------------------------
 // fp32 NCHW (caller memory, pointer read from a device slot) -> NHWC dt with zero channel padding.
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* const* src_slot, T* dst, int B, int C, int HW, int Cpad) {
+__global__ void nchw_to_nhwc_kernel(const float* const* src_slot, T* dst, int B, int C, int HW, int Cpad, int round_tf32) {
   pdl_grid_sync();
   const float* src = *src_slot;
   const long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -25,7 +25,7 @@ __global__ void nchw_to_nhwc_kernel(const float* const* src_slot, T* dst, int B,
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
       v[j] = c < C ? __ldg(src + (static_cast<long long>(b) * C + c) * HW + hw) : 0.f;
-      if (sizeof(T) == 4) {  // fp32 activations feed tf32 MMAs: round-to-nearest here, truncation there is then exact
+      if (sizeof(T) == 4 && round_tf32) {  // fp32 activations feed tf32 MMAs: round-to-nearest here, truncation there is then exact
         uint32_t r;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[j]));
         v[j] = __uint_as_float(r);
@@ -42,11 +42,12 @@ void add_nchw_to_nhwc(Net& net, const float* const* src_slot, const Tensor& out,
   const int threads = 256;
   const int blocks = static_cast<int>((pixels + threads - 1) / threads);
   Tensor o = out;
+  const int rnd = net.x3 ? 0 : 1;  // fp32 parity mode keeps every stored bit
   net.add("nchw_to_nhwc", [=](cudaStream_t s) {
     if (o.dt == kBF16)
-      launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, blocks, threads, 0, s, src_slot, static_cast<__nv_bfloat16*>(o.ptr), o.B, C, HW, o.C);
+      launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, blocks, threads, 0, s, src_slot, static_cast<__nv_bfloat16*>(o.ptr), o.B, C, HW, o.C, rnd);
     else
-      launch_pdl(nchw_to_nhwc_kernel<float>, blocks, threads, 0, s, src_slot, static_cast<float*>(o.ptr), o.B, C, HW, o.C);
+      launch_pdl(nchw_to_nhwc_kernel<float>, blocks, threads, 0, s, src_slot, static_cast<float*>(o.ptr), o.B, C, HW, o.C, rnd);
   });
   net.launches_per_forward += 1;
 }

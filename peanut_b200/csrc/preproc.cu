@@ -104,7 +104,7 @@ __global__ void k_resize_u8(const uint8_t* const* rgb_slot, int B, int H, int W,
 // N = 128 instead of 64 per MMA.
 template <typename T>
 __global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int Hn, int Wn, int Hp, int Wq, float3 mean_bgr,
-                            float3 std_bgr, T* __restrict__ out) {
+                            float3 std_bgr, T* __restrict__ out, int round_tf32) {
   pdl_grid_sync();
   // one thread per stored pixel (row pair q, pixel pair j): 2 x 27 values, 128 contiguous bytes (bf16) per thread
   const int Hq = Hp / 2 + 1;
@@ -134,7 +134,7 @@ __global__ void k_pack_stem(const uint8_t* __restrict__ resized_u8, int B, int H
           v[s * 3 + 2] = unit_std ? d2 : d2 / std_bgr.z;
         }
       }
-      if (sizeof(T) == 4) {
+      if (sizeof(T) == 4 && round_tf32) {
 #pragma unroll
         for (int k = 0; k < 27; ++k) {
           uint32_t qq;
@@ -227,11 +227,12 @@ void add_resize_pack_stem(Net& net, const uint8_t* const* rgb_slot, int B, int H
   const long long total2 = out.pixels();   // one thread per stored pixel (row pair, pixel pair)
   const int blocks2 = static_cast<int>((total2 + threads - 1) / threads);
   Tensor o = out;
+  const int rnd = net.x3 ? 0 : 1;
   net.add("pack_stem", [=](cudaStream_t s) {
     if (o.dt == kBF16)
-      launch_pdl(k_pack_stem<__nv_bfloat16>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, Hp, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr));
+      launch_pdl(k_pack_stem<__nv_bfloat16>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, Hp, o.W, mean, sd, static_cast<__nv_bfloat16*>(o.ptr), rnd);
     else
-      launch_pdl(k_pack_stem<float>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, Hp, o.W, mean, sd, static_cast<float*>(o.ptr));
+      launch_pdl(k_pack_stem<float>, blocks2, threads, 0, s, resized_u8, B, Hn, Wn, Hp, o.W, mean, sd, static_cast<float*>(o.ptr), rnd);
   });
   net.launches_per_forward += 2;
 }

@@ -125,6 +125,21 @@ def test_conv_tf32(ctx, case):
     assert err <= 3e-3 * scale, f"max abs err {err} vs scale {scale}"
 
 
+FP32_CASES = CASES[:17] + SPLIT_CASES[:2]
+
+
+@pytest.mark.parametrize("case", FP32_CASES, ids=[str(c) for c in FP32_CASES])
+def test_conv_fp32(ctx, case):
+    """Strict-parity mode: three tf32 products of hi / lo operand halves, fp32 accumulate, nothing rounded on the way out.
+    Against the float64 convolution of the SAME fp32 inputs.  Measured (tools/fp32_parity_probe.py, profiles/r02_fp32_parity.txt):
+    3e-7 .. 2e-6 of the output scale up to K = 2 304, 6.5e-6 at K = 9 216, 1.4e-5 with that K split four ways - against
+    3e-4 .. 6e-4 on the tf32 path; the growth with K is the tensor core's fp32 accumulation, not the operand split."""
+    y, ref = _run(ctx, case, _lib.PN_FP32)
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= 5e-5 * scale, f"max abs err {err} vs scale {scale}"
+
+
 @pytest.mark.parametrize("precision", [_lib.PN_BF16, _lib.PN_TF32], ids=["bf16", "tf32"])
 @pytest.mark.parametrize("case", PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
 def test_conv_pair(ctx, case, precision):

@@ -184,6 +184,17 @@ int pn_map_stamp_local(pn_ctx* ctx, const float* local_map_dev, float* full_map_
 int pn_map_crop_window(pn_ctx* ctx, const float* full_map_dev, int E, int num_channels, int full_w, int full_h, int x1, int y1,
                        int win_w, int win_h, int copy_channels, float* window_out_dev, int out_channels, void* stream);
 
+/* N4, the map-sequence file format either side of the path, on the device.
+ * pn_map_quantize: out[i] = (uint8)(map[i] * 255), fp32 multiply and truncation - `(full_map.cpu().numpy() * 255).astype(np.uint8)`
+ *   of nav/collect_maps.py:79-80 without moving the fp32 map to the host (defined, like numpy's cast, for products in [0, 256)).
+ * pn_map_sample: LoadMapFromFile.__call__ (prediction/train_prediction_model.py:66-84) on a sequence seq [T, C, W, H] uint8 that
+ *   is resident in HBM: img = seq[t_idx] / 255 as float32, written as img_hwc [W, H, C] (the reference's array) and / or img_chw
+ *   [C, W, H] (the layout pn_prednet_forward takes); gt [W, H, num_goals] int64 = seq[T-1, goal_channel0 + g] where the INPUT's
+ *   explored channel (channel 1) is still 0, else 0.  Any of the three outputs may be NULL; t_idx may be negative (from the end). */
+int pn_map_quantize(pn_ctx* ctx, const float* map_dev, long long count, unsigned char* out_dev, void* stream);
+int pn_map_sample(pn_ctx* ctx, const unsigned char* seq_dev, int T, int C, int W, int H, int t_idx, int goal_channel0, int num_goals,
+                  float* img_hwc_dev, float* img_chw_dev, long long* gt_dev, void* stream);
+
 /* Agent_State.update_goal_map (:423-452), every step, for E environments: goal_map_out [E, local_w, local_h] fp32 = the
  * cells of category channel goal_cat + 4 (binarised; eroded goal_erode times and dilated once with the 4-neighbour cross
  * unless skip_morph[e] != 0, the reference's "'tv' in goal_name") that carry no OTHER category of channels 4..9;

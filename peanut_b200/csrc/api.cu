@@ -124,7 +124,7 @@ using namespace pn;
 extern "C" {
 
 const char* pn_last_error(void) { return g_last_error.c_str(); }
-int pn_abi_version(void) { return 2; }
+int pn_abi_version(void) { return 3; }
 
 int pn_create(int device, pn_ctx** out) {
   PN_API_BEGIN
@@ -653,6 +653,30 @@ int pn_map_crop_window(pn_ctx* ctx, const float* full_map_dev, int E, int num_ch
              "pn_map_crop_window: window outside the full map");
   launch_map_crop(full_map_dev, E, num_channels, full_w, full_h, x1, y1, win_w, win_h, copy_channels, window_out_dev, out_channels,
                   static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
+int pn_map_quantize(pn_ctx* ctx, const float* map_dev, long long count, unsigned char* out_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(count >= 0 && (count == 0 || (map_dev && out_dev)), "pn_map_quantize: null buffer");
+  if (count > 0) launch_map_quantize(map_dev, count, out_dev, c->num_sms, static_cast<cudaStream_t>(stream));
+  PN_API_END
+}
+
+int pn_map_sample(pn_ctx* ctx, const unsigned char* seq_dev, int T, int C, int W, int H, int t_idx, int goal_channel0, int num_goals,
+                  float* img_hwc_dev, float* img_chw_dev, long long* gt_dev, void* stream) {
+  PN_API_BEGIN
+  auto* c = reinterpret_cast<Ctx*>(ctx);
+  check_device(c);
+  PN_REQUIRE(seq_dev != nullptr, "pn_map_sample: null sequence");
+  PN_REQUIRE(T > 0 && C >= 2 && W > 0 && H > 0, "pn_map_sample: bad sequence shape (the explored channel is channel 1)");
+  PN_REQUIRE(t_idx >= -T && t_idx < T, "pn_map_sample: time step out of range");
+  PN_REQUIRE(!gt_dev || (num_goals > 0 && goal_channel0 >= 0 && goal_channel0 + num_goals <= C), "pn_map_sample: goal channels outside the map");
+  PN_REQUIRE(img_hwc_dev || img_chw_dev || gt_dev, "pn_map_sample: no output requested");
+  launch_map_sample(seq_dev, T, C, W, H, t_idx < 0 ? t_idx + T : t_idx, goal_channel0, gt_dev ? num_goals : 0, img_hwc_dev, img_chw_dev,
+                    gt_dev, static_cast<cudaStream_t>(stream));
   PN_API_END
 }
 

@@ -321,6 +321,53 @@ __global__ void __launch_bounds__(256) k_map_crop(const float* __restrict__ full
   }
 }
 
+
+// ---- N4, the map-sequence file format either side of the path: the two byte-level transforms on the device.
+// Writer side, collect_maps.py:79-80: (full_map * 255).astype(uint8) - an fp32 multiply (this file is built with -fmad=false)
+// and a truncation toward zero; numpy's result is only defined for products in [0, 256), which map values in [0, 1] satisfy.
+__global__ void __launch_bounds__(256) k_map_quantize(const float* __restrict__ in, long long n, uint8_t* __restrict__ out, int vec) {
+  pdl_grid_sync();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (; i < n4; i += stride) {
+      const float4 v = reinterpret_cast<const float4*>(in)[i];
+      uchar4 q;
+      q.x = static_cast<uint8_t>(static_cast<int>(v.x * 255.f)), q.y = static_cast<uint8_t>(static_cast<int>(v.y * 255.f));
+      q.z = static_cast<uint8_t>(static_cast<int>(v.z * 255.f)), q.w = static_cast<uint8_t>(static_cast<int>(v.w * 255.f));
+      reinterpret_cast<uchar4*>(out)[i] = q;
+    }
+    i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  }
+  for (; i < n; i += stride) out[i] = static_cast<uint8_t>(static_cast<int>(in[i] * 255.f));
+}
+
+// Reader side, LoadMapFromFile.__call__ (train_prediction_model.py:66-84) on a sequence [T, C, W, H] uint8 resident in HBM:
+//   img  = seq[t].transpose(1, 2, 0).astype(float32) / 255.          -> img_hwc [W, H, C] (the reference's array) and / or
+//                                                                       img_chw [C, W, H] (what the completion net takes)
+//   gt   = (seq[-1, goal0 : goal0 + G] * (1 - (img[:, :, 1] > 0))).transpose(1, 2, 0)   -> int64 [W, H, G]
+// One thread per map cell: the plane reads and the CHW writes are coalesced across the warp, the HWC / target rows are the
+// thread's own C (G) contiguous values.
+__global__ void __launch_bounds__(256) k_map_sample(const uint8_t* __restrict__ seq, int T, int C, long long cells, int t_idx,
+                                                    int goal0, int G, float* __restrict__ img_hwc, float* __restrict__ img_chw,
+                                                    long long* __restrict__ gt) {
+  pdl_grid_sync();
+  const long long cell = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= cells) return;
+  const uint8_t* cur = seq + static_cast<long long>(t_idx) * C * cells + cell;
+  const uint8_t* last = seq + static_cast<long long>(T - 1) * C * cells + cell;
+  const bool explored = cur[cells] > 0;   // channel 1 of the INPUT time step
+  for (int c = 0; c < C; ++c) {
+    const float v = static_cast<float>(cur[static_cast<long long>(c) * cells]) / 255.f;
+    if (img_hwc) img_hwc[cell * C + c] = v;
+    if (img_chw) img_chw[static_cast<long long>(c) * cells + cell] = v;
+  }
+  if (gt)
+    for (int g = 0; g < G; ++g)
+      gt[cell * G + g] = explored ? 0ll : static_cast<long long>(last[static_cast<long long>(goal0 + g) * cells]);
+}
+
 }  // namespace
 
 void launch_map_stamp_local(const float* local_map, float* full_map, const int* lmb, int E, int nc, int local_w, int local_h,
@@ -341,6 +388,23 @@ void launch_map_crop(const float* full_map, int E, int nc, int full_w, int full_
   const dim3 grid(static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 64)), nc_copy, E);
   if (vec) launch_pdl(k_map_crop<float4>, grid, dim3(256), 0, s, full_map, nc, full_w, full_h, x1, y1, win_w, win_h, out, out_channels);
   else launch_pdl(k_map_crop<float>, grid, dim3(256), 0, s, full_map, nc, full_w, full_h, x1, y1, win_w, win_h, out, out_channels);
+  PN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_map_quantize(const float* map, long long n, uint8_t* out, int num_sms, cudaStream_t s) {
+  const int vec = (reinterpret_cast<uintptr_t>(map) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0) ? 1 : 0;
+  const long long items = vec ? (n + 3) / 4 : n;
+  const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((items + 255) / 256, 8ll * num_sms)));
+  launch_pdl(k_map_quantize, dim3(blocks), dim3(256), 0, s, map, n, out, vec);
+  PN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_map_sample(const uint8_t* seq, int T, int C, int W, int H, int t_idx, int goal0, int G, float* img_hwc, float* img_chw,
+                       long long* gt, cudaStream_t s) {
+  const long long cells = static_cast<long long>(W) * H;
+  const long long blocks = (cells + 255) / 256;
+  PN_REQUIRE(blocks < (1ll << 31), "map sample: map too large");
+  launch_pdl(k_map_sample, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, seq, T, C, cells, t_idx, goal0, G, img_hwc, img_chw, gt);
   PN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -107,6 +107,10 @@ void launch_map_stamp_local(const float* local_map, float* full_map, const int* 
                             int full_w, int full_h, cudaStream_t s);
 void launch_map_crop(const float* full_map, int E, int nc, int full_w, int full_h, int x1, int y1, int win_w, int win_h,
                      int nc_copy, float* out, int out_channels, cudaStream_t s);
+// N4 (mapstate.cu): writer-side quantisation and reader-side sample construction of the map-sequence format
+void launch_map_quantize(const float* map, long long n, uint8_t* out, int num_sms, cudaStream_t s);
+void launch_map_sample(const uint8_t* seq, int T, int C, int W, int H, int t_idx, int goal0, int G, float* img_hwc, float* img_chw,
+                       long long* gt, cudaStream_t s);
 void launch_global_goal(int device, int num_sms, const pn_goal_cfg& cfg, const pn_goal_arrays& arrays, int E, int only_distance,
                         cudaStream_t s);
 void map_bookkeeping(int op, const pn_map_cfg& cfg, const pn_map_arrays& arrays, int E, cudaStream_t s);

@@ -8,9 +8,11 @@ time step ``t_idx`` of a file into the network input (HWC float32 in [0, 1]) and
 goal-category channels where the input's explored channel is still empty); ``SemMapDataset.load_annotations`` enumerates
 ten time steps per file.
 
-Host-side code (numpy / torch as plumbing): this is I/O around the device path, not a kernel.  ``quantize_full_map``
-accepts the device-resident ``full_map`` of ``peanut_b200.map_state.MapState`` and does the scale + truncate where the
-tensor lives, so a quarter of the bytes cross to the host.
+File I/O is host-side code (numpy); the two byte-level transforms either side of it run on the device when the map lives
+there: ``quantize_full_map`` of a CUDA tensor (the device-resident ``full_map`` of ``peanut_b200.map_state.MapState``) is the
+``pn_map_quantize`` kernel, so a quarter of the bytes cross to the host, and ``DeviceMapSequence`` keeps an uploaded sequence in
+HBM and builds network inputs and targets with ``pn_map_sample`` - both bit-identical to the reference's numpy expressions
+(tests/test_map_dataset_gpu.py).  CUDA inputs never fall back to a host path: the library must be there.
 """
 import os
 
@@ -29,8 +31,74 @@ def quantize_full_map(full_map):
     import torch
     if full_map.dtype != torch.float32:
         raise TypeError("full_map must be float32")
-    q = (full_map * 255).to(torch.uint8)    # fp32 multiply, truncation toward zero: numpy's astype on [0, 256)
-    return q.cpu().numpy()
+    if full_map.is_cuda:
+        return quantize_full_map_device(full_map).cpu().numpy()
+    return (full_map * 255).to(torch.uint8).numpy()    # fp32 multiply, truncation toward zero: numpy's astype on [0, 256)
+
+
+def _ctx_for(tensor):
+    from . import _lib
+    key = tensor.device.index if tensor.device.index is not None else 0
+    ctx = _CTX.get(key)
+    if ctx is None:
+        ctx = _CTX[key] = _lib.Context(key)
+    return ctx
+
+
+_CTX = {}
+
+
+def quantize_full_map_device(full_map):
+    """``pn_map_quantize``: CUDA float32 tensor (any shape) -> CUDA uint8 tensor of the same shape, on the current stream."""
+    import torch
+    from . import _lib
+    if not (full_map.is_cuda and full_map.dtype == torch.float32):
+        raise TypeError("quantize_full_map_device takes a CUDA float32 tensor")
+    x = full_map.contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    ctx = _ctx_for(x)
+    with torch.cuda.device(x.device):
+        _lib.check(ctx.lib.pn_map_quantize(ctx.handle, x.data_ptr(), x.numel(), out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+class DeviceMapSequence:
+    """One map-sequence file resident in HBM: ``LoadMapFromFile`` (train_prediction_model.py:47-91) per time step on the device.
+
+    ``maps``: uint8 [T, C, W, H] (numpy array, e.g. ``np.load(path)["maps"]``, or a tensor).  ``sample(t_idx)`` returns the
+    reference reader's two arrays as CUDA tensors - ``img`` float32 [W, H, C] and ``gt_semantic_seg`` int64 [W, H, 6] - plus
+    ``input`` float32 [C, W, H], the layout ``PEANUT_Prediction_Model.get_prediction`` / ``pn_prednet_forward`` take."""
+
+    def __init__(self, maps, device="cuda:0"):
+        import torch
+        t = torch.as_tensor(maps)
+        if t.dtype != torch.uint8 or t.dim() != 4:
+            raise TypeError("maps must be uint8 [T, C, W, H]")
+        self.seq = t.to(device).contiguous()
+        self.T, self.C, self.W, self.H = (int(v) for v in self.seq.shape)
+        self.ctx = _ctx_for(self.seq)
+
+    @classmethod
+    def from_file(cls, path, device="cuda:0"):
+        maps = np.load(path)
+        if path[-1] == "z":
+            maps = maps["maps"]
+        return cls(maps, device)
+
+    def sample(self, t_idx, hwc=True, chw=True, target=True):
+        import torch
+        from . import _lib
+        dev = self.seq.device
+        img = torch.empty((self.W, self.H, self.C), dtype=torch.float32, device=dev) if hwc else None
+        inp = torch.empty((self.C, self.W, self.H), dtype=torch.float32, device=dev) if chw else None
+        gt = torch.empty((self.W, self.H, NUM_TARGET_CATEGORIES), dtype=torch.int64, device=dev) if target else None
+        ptr = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(self.ctx.lib.pn_map_sample(self.ctx.handle, self.seq.data_ptr(), self.T, self.C, self.W, self.H, int(t_idx), 4,
+                                                  NUM_TARGET_CATEGORIES, ptr(img), ptr(inp), ptr(gt),
+                                                  torch.cuda.current_stream().cuda_stream))
+        return {"img": img, "input": inp, "gt_semantic_seg": gt}
 
 
 class MapSequenceWriter:

@@ -630,7 +630,9 @@ void add_conv(Net& net, const std::string& name, const Tensor& in, const Tensor&
   // the model's choice; test hooks (force_*) bypass both.
   int opt = sp.force_opt;
   const bool forced = sp.force_opt || sp.force_bn || sp.force_splits || sp.force_pair || sp.force_direct_epilogue || sp.dbg;
-  if (!forced && autotune_mode() != 0 && cands.size() > 1) {
+  // (the split-precision parity mode never times: the tile model's choice, identical in every process, so its results are
+  //  reproducible run to run; its speed is not the point)
+  if (!forced && autotune_mode() != 0 && cands.size() > 1 && !sp.x3_cin) {
     // The key holds everything the candidate set and the timings depend on (incl. padding, the dynamic-row-limit flag, the
     // device's SM count and the opt-in modes), so an entry is only ever reused for an identical launch problem.
     char key[320];

@@ -347,25 +347,37 @@ __global__ void __launch_bounds__(256) k_map_quantize(const float* __restrict__ 
 //   img  = seq[t].transpose(1, 2, 0).astype(float32) / 255.          -> img_hwc [W, H, C] (the reference's array) and / or
 //                                                                       img_chw [C, W, H] (what the completion net takes)
 //   gt   = (seq[-1, goal0 : goal0 + G] * (1 - (img[:, :, 1] > 0))).transpose(1, 2, 0)   -> int64 [W, H, G]
-// One thread per map cell: the plane reads and the CHW writes are coalesced across the warp, the HWC / target rows are the
-// thread's own C (G) contiguous values.
+// One thread per map cell: the plane reads and the CHW writes are coalesced across the warp; the cell-major outputs (C floats /
+// G int64 per cell) go through shared memory, so that the CTA's 256 cells leave as one contiguous, coalesced run instead of 256
+// scattered 56-byte pieces (img + input + target at 960 x 960: 97 -> see profiles/r02_map_dataset.txt).
 __global__ void __launch_bounds__(256) k_map_sample(const uint8_t* __restrict__ seq, int T, int C, long long cells, int t_idx,
                                                     int goal0, int G, float* __restrict__ img_hwc, float* __restrict__ img_chw,
                                                     long long* __restrict__ gt) {
   pdl_grid_sync();
-  const long long cell = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (cell >= cells) return;
-  const uint8_t* cur = seq + static_cast<long long>(t_idx) * C * cells + cell;
-  const uint8_t* last = seq + static_cast<long long>(T - 1) * C * cells + cell;
-  const bool explored = cur[cells] > 0;   // channel 1 of the INPUT time step
-  for (int c = 0; c < C; ++c) {
-    const float v = static_cast<float>(cur[static_cast<long long>(c) * cells]) / 255.f;
-    if (img_hwc) img_hwc[cell * C + c] = v;
-    if (img_chw) img_chw[static_cast<long long>(c) * cells + cell] = v;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_img = reinterpret_cast<float*>(s_raw);                                   // [256][C] when img_hwc
+  long long* s_gt = reinterpret_cast<long long*>(s_raw + (img_hwc ? sizeof(float) * 256 * C : 0));   // [256][G] when gt
+  const long long base = static_cast<long long>(blockIdx.x) * blockDim.x;
+  const long long cell = base + threadIdx.x;
+  const int live = static_cast<int>(min(static_cast<long long>(blockDim.x), cells - base));
+  if (cell < cells) {
+    const uint8_t* cur = seq + static_cast<long long>(t_idx) * C * cells + cell;
+    const uint8_t* last = seq + static_cast<long long>(T - 1) * C * cells + cell;
+    const bool explored = cur[cells] > 0;   // channel 1 of the INPUT time step
+    for (int c = 0; c < C; ++c) {
+      const float v = static_cast<float>(cur[static_cast<long long>(c) * cells]) / 255.f;
+      if (img_hwc) s_img[threadIdx.x * C + c] = v;
+      if (img_chw) img_chw[static_cast<long long>(c) * cells + cell] = v;
+    }
+    if (gt)
+      for (int g = 0; g < G; ++g)
+        s_gt[threadIdx.x * G + g] = explored ? 0ll : static_cast<long long>(last[static_cast<long long>(goal0 + g) * cells]);
   }
+  __syncthreads();
+  if (img_hwc)
+    for (int i = threadIdx.x; i < live * C; i += blockDim.x) img_hwc[base * C + i] = s_img[i];
   if (gt)
-    for (int g = 0; g < G; ++g)
-      gt[cell * G + g] = explored ? 0ll : static_cast<long long>(last[static_cast<long long>(goal0 + g) * cells]);
+    for (int i = threadIdx.x; i < live * G; i += blockDim.x) gt[base * G + i] = s_gt[i];
 }
 
 }  // namespace
@@ -404,7 +416,9 @@ void launch_map_sample(const uint8_t* seq, int T, int C, int W, int H, int t_idx
   const long long cells = static_cast<long long>(W) * H;
   const long long blocks = (cells + 255) / 256;
   PN_REQUIRE(blocks < (1ll << 31), "map sample: map too large");
-  launch_pdl(k_map_sample, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, seq, T, C, cells, t_idx, goal0, G, img_hwc, img_chw, gt);
+  const size_t smem = (img_hwc ? sizeof(float) * 256 * C : 0) + (gt ? sizeof(long long) * 256 * G : 0);
+  PN_REQUIRE(smem <= 48 * 1024, "map sample: too many channels for the staging buffer");
+  launch_pdl(k_map_sample, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, s, seq, T, C, cells, t_idx, goal0, G, img_hwc, img_chw, gt);
   PN_CUDA_CHECK(cudaGetLastError());
 }
 

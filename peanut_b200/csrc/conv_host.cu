@@ -297,7 +297,7 @@ inline float host_rn_tf32(float v) {
 static void add_conv_x3(Net& net, const std::string& name, const Tensor& in, const Tensor& out, const float* weight,
                         const float* scale, const float* bias, const ConvSpec& sp, const Tensor* residual) {
   PN_REQUIRE(in.dt == kF32, name + ": the fp32 split-precision path needs fp32 activations");
-  PN_REQUIRE(in.C % 4 == 0 && in.ld % 4 == 0, name + ": channels not a multiple of 4");
+  PN_REQUIRE(in.C % 4 == 0 && in.ld % 4 == 0 && reinterpret_cast<uintptr_t>(in.ptr) % 16 == 0, name + ": input of the split kernel not 16-byte aligned");
   const int cpad = in.C;
   const int C3 = round_up(3 * cpad, 32);  // K blocks of 32 floats (128-byte swizzle rows); the tail stays zero
   Tensor s3 = net.arena.tensor(in.B, in.H, in.W, C3, kF32);

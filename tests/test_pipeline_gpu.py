@@ -221,5 +221,13 @@ def test_whole_chain_strict_parity_vs_oracle_chain():
     # 99.9952 %, predicted probabilities max 8.3e-6 / mean 3.4e-6 from the oracle chain's
     assert close >= 0.999 and float(dp.mean()) <= 5e-5, \
         f"predicted map within 2e-3 on {close} of the cells (max {dp.max():.3e}, mean {dp.mean():.3e})"
+    # the integer category map derived from the prediction: equal wherever the oracle's top-2 margin is above the noise
+    got_p, ref_p = pred[0].cpu().numpy(), ref["pred"]
+    srt = np.sort(ref_p, axis=0)
+    confident = (srt[-1] - srt[-2]) > 2e-4
+    assert (got_p.argmax(0)[confident] == ref_p.argmax(0)[confident]).all()
+    amax_eq = float((got_p.argmax(0) == ref_p.argmax(0)).mean())
+    assert amax_eq >= 0.999, f"argmax category map equal on {amax_eq} of the cells"
+    print(f"whole chain fp32: argmax map equal {amax_eq:.6f} (confident cells {float(confident.mean()):.4f})")
     print(f"whole chain fp32: sem equal {sem_eq:.6f}, fp equal {fp_eq:.6f}, map within 1e-4 on "
           f"{float((dm <= 1e-4).float().mean()):.6f}, prediction max err {dp.max():.3e} mean {dp.mean():.3e} close {close:.6f}")

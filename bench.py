@@ -44,6 +44,29 @@ METRIC = "frames/sec (RGB-D -> predicted semantic map)"
 VERBOSE = False
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when the box
+    sets NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a private
+    duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def log(*a):
     if VERBOSE:
         print(f"[bench {time.strftime('%H:%M:%S')}]", *a, file=sys.stderr, flush=True)
@@ -226,7 +249,7 @@ def run_reference(a):
                     "note": "CPU arm: rank 0 only, one frame per step (bounded sample of the same workload)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -526,7 +549,7 @@ def run_ours(a):
         cms = 1000.0 * sum(times) / len(times)
         line["cpu_baseline"] = {"value": 1000.0 / cms, "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": f"{len(times)} frames, batch 1 fp32, oracle (PyTorch CPU) after 1 warm-up"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -534,6 +557,7 @@ def run_ours(a):
 if __name__ == "__main__":
     args = parse()
     VERBOSE = args.verbose or bool(os.environ.get("PN_BENCH_VERBOSE"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

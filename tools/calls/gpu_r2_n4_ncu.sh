@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2: DRAM traffic of the N4 kernels against their algorithmic bytes (ncu, no clock control).
 mkdir -p gpurun_out
-timeout 240 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_map_ --launch-skip 8 -c 16 --csv \
+timeout 240 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_map_sample --launch-skip 3 -c 4 --csv \
    --log-file gpurun_out/r02_map_dataset_ncu.csv python tools/map_dataset_profile.py > gpurun_out/r02_map_dataset_ncu.log 2>&1; echo "ncu exit $?"
 grep -v "^==" gpurun_out/r02_map_dataset_ncu.csv | python -c "
 import csv, sys

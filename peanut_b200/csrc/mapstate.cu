@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(256) k_map_quantize(const float* __restrict__ 
 //   gt   = (seq[-1, goal0 : goal0 + G] * (1 - (img[:, :, 1] > 0))).transpose(1, 2, 0)   -> int64 [W, H, G]
 // One thread per map cell: the plane reads and the CHW writes are coalesced across the warp; the cell-major outputs (C floats /
 // G int64 per cell) go through shared memory, so that the CTA's 256 cells leave as one contiguous, coalesced run instead of 256
-// scattered 56-byte pieces (img + input + target at 960 x 960: 97 -> see profiles/r02_map_dataset.txt).
+// scattered 56-byte pieces (img + input + target at 960 x 960: 97 -> 56 us, profiles/r02_map_dataset.txt).  Takes the shapes
+// k_map_sample4 below cannot (cell count not a multiple of four, unaligned buffers).
 __global__ void __launch_bounds__(256) k_map_sample(const uint8_t* __restrict__ seq, int T, int C, long long cells, int t_idx,
                                                     int goal0, int G, float* __restrict__ img_hwc, float* __restrict__ img_chw,
                                                     long long* __restrict__ gt) {
@@ -378,6 +379,51 @@ __global__ void __launch_bounds__(256) k_map_sample(const uint8_t* __restrict__ 
     for (int i = threadIdx.x; i < live * C; i += blockDim.x) img_hwc[base * C + i] = s_img[i];
   if (gt)
     for (int i = threadIdx.x; i < live * G; i += blockDim.x) gt[base * G + i] = s_gt[i];
+}
+
+// Four cells per thread (cells % 4 == 0): one uchar4 load per plane instead of four 1-byte loads (a warp's load covers a full 128-byte
+// line instead of one 32-byte sector), float4 stores of the [C, W, H] planes, the cell-major outputs staged as above (the target as
+// bytes, widened to int64 on the way out).  128 threads = 512 cells per CTA.  56 -> 43 us at 960 x 960, all three outputs.
+__global__ void __launch_bounds__(128) k_map_sample4(const uint8_t* __restrict__ seq, int T, int C, long long cells, int t_idx,
+                                                     int goal0, int G, float* __restrict__ img_hwc, float* __restrict__ img_chw,
+                                                     long long* __restrict__ gt) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_img = reinterpret_cast<float*>(s_raw);                                          // [512][C] when img_hwc
+  uint8_t* s_gt = s_raw + (img_hwc ? sizeof(float) * 512 * C : 0);                         // [512][G] when gt
+  const long long base = static_cast<long long>(blockIdx.x) * 512;
+  const long long cell = base + 4 * threadIdx.x;
+  const int live = static_cast<int>(min(512ll, cells - base));                             // a multiple of 4
+  if (cell < cells) {
+    const uint8_t* cur = seq + static_cast<long long>(t_idx) * C * cells + cell;
+    const uint8_t* last = seq + static_cast<long long>(T - 1) * C * cells + cell;
+    const uchar4 ex = *reinterpret_cast<const uchar4*>(cur + cells);   // channel 1 of the INPUT time step
+    for (int c = 0; c < C; ++c) {
+      const uchar4 q = *reinterpret_cast<const uchar4*>(cur + static_cast<long long>(c) * cells);
+      float4 v;
+      v.x = static_cast<float>(q.x) / 255.f, v.y = static_cast<float>(q.y) / 255.f;
+      v.z = static_cast<float>(q.z) / 255.f, v.w = static_cast<float>(q.w) / 255.f;
+      if (img_chw) *reinterpret_cast<float4*>(img_chw + static_cast<long long>(c) * cells + cell) = v;
+      if (img_hwc) {
+        float* d = s_img + (4 * threadIdx.x) * C + c;
+        d[0] = v.x, d[C] = v.y, d[2 * C] = v.z, d[3 * C] = v.w;
+      }
+    }
+    if (gt)
+      for (int g = 0; g < G; ++g) {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(last + static_cast<long long>(goal0 + g) * cells);
+        uint8_t* d = s_gt + (4 * threadIdx.x) * G + g;
+        d[0] = ex.x ? 0 : q.x, d[G] = ex.y ? 0 : q.y, d[2 * G] = ex.z ? 0 : q.z, d[3 * G] = ex.w ? 0 : q.w;
+      }
+  }
+  __syncthreads();
+  if (img_hwc) {
+    float4* dst = reinterpret_cast<float4*>(img_hwc + base * C);
+    const float4* src = reinterpret_cast<const float4*>(s_img);
+    for (int i = threadIdx.x; i < live * C / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  if (gt)
+    for (int i = threadIdx.x; i < live * G; i += blockDim.x) gt[base * G + i] = static_cast<long long>(s_gt[i]);
 }
 
 }  // namespace
@@ -414,11 +460,20 @@ void launch_map_quantize(const float* map, long long n, uint8_t* out, int num_sm
 void launch_map_sample(const uint8_t* seq, int T, int C, int W, int H, int t_idx, int goal0, int G, float* img_hwc, float* img_chw,
                        long long* gt, cudaStream_t s) {
   const long long cells = static_cast<long long>(W) * H;
-  const long long blocks = (cells + 255) / 256;
-  PN_REQUIRE(blocks < (1ll << 31), "map sample: map too large");
-  const size_t smem = (img_hwc ? sizeof(float) * 256 * C : 0) + (gt ? sizeof(long long) * 256 * G : 0);
-  PN_REQUIRE(smem <= 48 * 1024, "map sample: too many channels for the staging buffer");
-  launch_pdl(k_map_sample, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, s, seq, T, C, cells, t_idx, goal0, G, img_hwc, img_chw, gt);
+  const size_t smem4 = (img_hwc ? sizeof(float) * 512 * C : 0) + (gt ? static_cast<size_t>(512) * G : 0);
+  const bool aligned = cells % 4 == 0 && reinterpret_cast<uintptr_t>(seq) % 4 == 0 && reinterpret_cast<uintptr_t>(img_hwc) % 16 == 0 &&
+                       reinterpret_cast<uintptr_t>(img_chw) % 16 == 0;
+  if (aligned && smem4 <= 48 * 1024) {
+    const long long blocks = (cells + 511) / 512;
+    PN_REQUIRE(blocks < (1ll << 31), "map sample: map too large");
+    launch_pdl(k_map_sample4, dim3(static_cast<unsigned>(blocks)), dim3(128), smem4, s, seq, T, C, cells, t_idx, goal0, G, img_hwc, img_chw, gt);
+  } else {
+    const long long blocks = (cells + 255) / 256;
+    PN_REQUIRE(blocks < (1ll << 31), "map sample: map too large");
+    const size_t smem = (img_hwc ? sizeof(float) * 256 * C : 0) + (gt ? sizeof(long long) * 256 * G : 0);
+    PN_REQUIRE(smem <= 48 * 1024, "map sample: too many channels for the staging buffer");
+    launch_pdl(k_map_sample, dim3(static_cast<unsigned>(blocks)), dim3(256), smem, s, seq, T, C, cells, t_idx, goal0, G, img_hwc, img_chw, gt);
+  }
   PN_CUDA_CHECK(cudaGetLastError());
 }
 

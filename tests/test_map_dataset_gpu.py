@@ -34,6 +34,27 @@ def test_sample_matches_reference_fixture(tmp_path):
     assert only_input["img"] is None and only_input["gt_semantic_seg"] is None and only_input["input"].shape == (14, 48, 48)
 
 
+@pytest.mark.parametrize("shape", [(3, 10, 7, 7), (2, 14, 10, 26), (4, 14, 33, 64), (2, 12, 5, 3)])
+def test_sample_matches_numpy_on_odd_shapes(shape):
+    """Both sample kernels against the reference's numpy expressions (train_prediction_model.py:66-84): cell counts that are not
+    a multiple of four take the one-cell-per-thread kernel, the others the four-cells-per-thread one (with a partial last CTA)."""
+    rng = np.random.default_rng(sum(shape))
+    maps = rng.integers(0, 256, shape, dtype=np.uint8)
+    maps[:, 1][rng.random(maps[:, 1].shape) < 0.5] = 0
+    seq = D.DeviceMapSequence(maps)
+    for t_idx in (0, shape[0] - 1):
+        img = maps[t_idx].transpose(1, 2, 0).astype(np.float32) / 255.
+        mask = img[:, :, 1] > 0
+        gt = (maps[-1, range(4, 4 + D.NUM_TARGET_CATEGORIES)] * (1 - mask)).transpose(1, 2, 0)
+        dev = seq.sample(t_idx)
+        torch.cuda.synchronize()
+        assert np.array_equal(dev["img"].cpu().numpy(), img)
+        assert np.array_equal(dev["input"].cpu().numpy(), img.transpose(2, 0, 1))
+        assert np.array_equal(dev["gt_semantic_seg"].cpu().numpy(), gt) and gt.dtype == np.int64
+        part = seq.sample(t_idx, hwc=False)
+        assert np.array_equal(part["gt_semantic_seg"].cpu().numpy(), gt) and np.array_equal(part["input"].cpu().numpy(), img.transpose(2, 0, 1))
+
+
 @pytest.mark.parametrize("shape", [(14, 32, 32), (3, 7, 11), (1, 1, 1), (14, 480, 480)])
 def test_quantize_matches_numpy(shape):
     rng = np.random.default_rng(sum(shape))
